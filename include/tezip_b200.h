@@ -1,0 +1,166 @@
+/* tezip_b200 -- C ABI of the B200-native TEZip hot path (libtezip_b200.so).
+ *
+ * The reference (kento/TEZip) is pure Python and has no FFI of its own; these entry points are what a
+ * ctypes binding inside the reference's compress.py / decompress.py would call instead of Keras / NumPy /
+ * CuPy (see INTEGRATION.md for the stubs).  Every entry point cites the reference lines it replaces
+ * (paths under /root/reference/src).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - all data pointers are DEVICE pointers on the handle's / current device unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous on it
+ *     unless stated otherwise.
+ *   - the caller owns every buffer; the library allocates device memory only inside tz_prednet_create().
+ *   - every function returns 0 on success or a negative TZ_E* code; tz_last_error() gives a thread-local
+ *     message.  There is no CPU fallback: without a usable sm_100 device the calls fail with TZ_ECUDA.
+ *   - frames are [n, H, W, C] u8, C fastest (the reference's channels_last layout, compress.py:116-121);
+ *     predictions are [n, Hp, Wp, C] f32 with Hp, Wp = H, W rounded up to a multiple of 8
+ *     (data_utils.py:77-107).
+ */
+#ifndef TEZIP_B200_H
+#define TEZIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZ_ABI_VERSION 1
+
+#define TZ_OK 0
+#define TZ_EINVAL (-1)  /* bad argument */
+#define TZ_ECUDA (-2)   /* CUDA runtime / driver error, or no sm_100 device */
+#define TZ_ERANGE (-3)  /* data outside the domain the reference itself accepts */
+#define TZ_ENOMEM (-4)
+
+#define TZ_MAX_LAYERS 8
+#define TZ_SYMBOL_OFFSET 1600 /* compress.py:348, decompress.py:236 */
+#define TZ_HIST_BINS 4096     /* symbols 1600 - y must fall in [0, 4096); valid streams use 1090..2110 */
+
+/* error-bound modes, compress.py:28-45 */
+#define TZ_MODE_ABS 0
+#define TZ_MODE_REL 1
+#define TZ_MODE_ABSREL 2
+#define TZ_MODE_PWREL 3
+
+int tz_abi_version(void);
+const char *tz_last_error(void);
+/* number of usable devices with compute capability 10.x; negative on error */
+int tz_device_count(void);
+/* kernels launched by this library since load (all handles, this process) -- bench.py's gpu_launches */
+long long tz_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ PredNet
+ * Replaces PredNet(...) + keras Model.predict (prednet.py:24-325; call sites compress.py:195,227 and
+ * decompress.py:143,154,165,175).  Inference subset only: output_mode='prediction', channels_last,
+ * extrap_start_time=None, 3x3 filters, relu/relu/tanh/hard_sigmoid.
+ */
+typedef struct tz_prednet tz_prednet;
+
+typedef struct tz_prednet_config {
+  int n_layers;                     /* prednet.py:84 nb_layers (2..TZ_MAX_LAYERS) */
+  int stack_sizes[TZ_MAX_LAYERS];   /* prednet.py:83 */
+  int r_stack_sizes[TZ_MAX_LAYERS]; /* prednet.py:86 */
+  int Hp, Wp;                       /* padded frame size, multiples of 2^(n_layers-1) */
+  float pixel_max;                  /* prednet.py:94 */
+  int max_batch;                    /* largest B ever passed to tz_prednet_next */
+  int device;                       /* CUDA ordinal */
+  int flags;                        /* TZ_PREDNET_* */
+} tz_prednet_config;
+
+#define TZ_PREDNET_FP32_DIRECT 1 /* fp32 CUDA-core kernels for every conv (validation path; slow) */
+
+/* weights_host: n_weights host pointers in the reference's weight-list order (prednet.py:210-227: keys
+ * a, ahat, c, f, i, o; layers ascending; kernel [3,3,Cin,Cout] then bias [Cout]); weight_elems[i] is the
+ * element count of array i (checked).  Synchronous.  Pre-computes everything that does not depend on the
+ * input frame (the t=0 R/C/Ahat maps, prednet.py:143-190,249-271 with zero state). */
+int tz_prednet_create(const tz_prednet_config *cfg, const float *const *weights_host,
+                      const long long *weight_elems, int n_weights, tz_prednet **out);
+int tz_prednet_destroy(tz_prednet *h);
+
+/* P0 = Model.predict(anything)[0,0] (compress.py:197, decompress.py:143): out f32 [Hp,Wp,C]. */
+int tz_prednet_p0(tz_prednet *h, float *out, void *stream);
+
+/* out[b] = Model.predict([in[b], zeros])[0,1] (compress.py:224-229, decompress.py:161-179) for b < B.
+ * in/out f32 [B,Hp,Wp,C], contiguous; out may not alias in.  Bitwise independent of B and of which other
+ * frames share the batch. */
+int tz_prednet_next(tz_prednet *h, const float *in, float *out, int B, void *stream);
+
+/* bytes of device memory the handle holds */
+long long tz_prednet_device_bytes(tz_prednet *h);
+/* algorithmic FLOPs per predicted frame */
+double tz_prednet_flops_per_frame(tz_prednet *h);
+
+/* ------------------------------------------------------------------------------------------------ codec ops */
+
+/* Key-frame normalisation + padding: out[b] = pad8(lut[frames[frame_idx[b]]]) with lut[k] = f32(k)/255
+ * (compress.py:138,176,219; decompress.py:117,120).  frame_idx (device, int32[B]) may be NULL = 0..B-1.
+ * lut: device f32[256]. */
+int tz_pad_normalize(const uint8_t *frames, const int32_t *frame_idx, const float *lut, float *out, int B,
+                     int H, int W, int C, int Hp, int Wp, void *stream);
+
+/* Residual (compress.py:293-314): x[f] = trunc_f32(pred_pool[pred_slot[f]] * 255) - frames[f] cropped to
+ * HxW, or 0 where pred_slot[f] < 0 (first frame of every window, compress.py:314).
+ * pred_pool f32 [slots,Hp,Wp,C]; pred_slot device int32[nt]; x int16 [nt,H,W,C]. */
+int tz_residual(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, int16_t *x,
+                long long nt, int H, int W, int C, int Hp, int Wp, void *stream);
+
+/* error_bound (compress.py:23-70, driven at :315-319): in place on x for every frame f with apply[f] != 0,
+ * one greedy scan per (frame, channel) plane in IEEE double, midpoint truncated toward zero.
+ * mode TZ_MODE_*; b0,b1 = BOUND_VALUE[0], [1].  b0 == 0 is the identity (compress.py:24). */
+int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long long nt, int H, int W,
+                   int C, int mode, double b0, double b1, void *stream);
+
+/* finding_difference (compress.py:73-77) fused with the symbol histogram (compress.py:348-355):
+ * y[i] = x[i-1] - x[i]; y[0] = x[0] if has_prev == 0 else prev_x - x[0] (prev_x = last x of the previous
+ * shard).  hist[s] += 1 for s = 1600 - y.  hist: device u64[TZ_HIST_BINS], caller-zeroed.
+ * overflow: device u64[1], caller-zeroed, counts symbols outside [0, TZ_HIST_BINS). */
+int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsigned long long *hist,
+                  unsigned long long *overflow, void *stream);
+
+/* finding_difference + replacing_based_on_frequency (compress.py:84-90,339-340,348,369):
+ * out[i] = lut[1600 - y[i]] (lut: device int16[TZ_HIST_BINS], symbol -> rank), or y[i] when lut == NULL
+ * (the -n / ENTROPY_RUN False stream). */
+int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const int16_t *lut, int16_t *out,
+                  void *stream);
+
+/* Fused lossless encode (compress.py:293-314,339-369 with b0 == 0): the same results as
+ * tz_residual + tz_delta_hist (pass 0) or tz_residual + tz_delta_rank (pass 1) without materialising x. */
+int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt,
+                       int H, int W, int C, int Hp, int Wp, int has_prev, int prev_x, int pass,
+                       unsigned long long *hist, unsigned long long *overflow, const int16_t *lut,
+                       int16_t *out, void *stream);
+
+/* Decoder (decompress.py:31-36,229,236 + :22-29,240-245 + :252-256,269):
+ *   s = table_len >= 0 ? rank_lut[body] : body;  y = table_len >= 0 ? 1600 - s : body
+ *   x[0] = first_mode == 0 ? y[0] : first_x;  x[i] = x[i-1] - y[i]     (int16 wrap-around arithmetic)
+ *   out = clamp(P - x, 0, 255),  P = pred_slot[f] >= 0 ? trunc_f32(pred_pool[slot]*255) : key_plane[f]
+ * rank_lut: device int16[TZ_HIST_BINS], rank -> symbol; the host builds it from the table with the
+ * reference's sequential where() semantics (identity beyond the table); body values outside
+ * [0, TZ_HIST_BINS) are left unchanged, as where() leaves them.  Ignored when table_len < 0.
+ * workspace: device, tz_reconstruct_workspace_bytes(n) bytes.  out u8 [nt,H,W,C]; x_out optional int16[n]. */
+long long tz_reconstruct_workspace_bytes(long long n);
+int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int Hp, int Wp, int table_len,
+                   const int16_t *rank_lut, int first_mode, int first_x, const float *pred_pool,
+                   const int32_t *pred_slot, const uint8_t *key_plane, uint8_t *out, int16_t *x_out,
+                   void *workspace, void *stream);
+
+/* DWP metric (compress.py:245-246): sse[b] = sum over the padded Hp x Wp x C area of
+ * (f64(lut[frame]) - f64(pred))^2 with zeros in the padding, fixed reduction order (deterministic).
+ * frames u8 [*,H,W,C]; frame_idx device int32[B]; pred f32 [B,Hp,Wp,C]; sse device f64[B]. */
+int tz_window_sse(const uint8_t *frames, const int32_t *frame_idx, const float *lut, const float *pred,
+                  double *sse, int B, int H, int W, int C, int Hp, int Wp, void *stream);
+
+/* key-frame plane (compress.py:183,190,220,261): out[f] = is_key[f] ? frames[f] : 0. */
+int tz_key_plane(const uint8_t *frames, const uint8_t *is_key, uint8_t *out, long long nt,
+                 long long frame_bytes, void *stream);
+
+/* decompress.py:123-127: nonzero[f] = any(key_plane[f] != 0). nonzero: device u8[nt]. */
+int tz_frames_nonzero(const uint8_t *key_plane, uint8_t *nonzero, long long nt, long long frame_bytes,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEZIP_B200_H */

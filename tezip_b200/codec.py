@@ -1,0 +1,307 @@
+"""Array-level compress / decompress: the window scheduler (compress.py:188-268, decompress.py:138-189) driving
+batched PredNet steps, and the codec kernels (compress.py:293-395, decompress.py:201-256) through the C ABI.
+
+Everything between "frames on the device" and "int16 stream + key plane on the device" happens here; file I/O,
+zstd and the CLI sit in compress.py / decompress.py / container.py.
+
+Scheduling.  Windows are independent, and inside a window frame k is predicted from the prediction of frame
+k-1 (from the key frame for k = 1).  So all windows advance in lock step: step k runs ONE batched
+`PredNet.next` over every window that is longer than k.  Windows are ordered by length (descending, stable) so
+that the live set is always a prefix and each step reads / writes one contiguous block of the prediction pool.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import TezipError, TZ_HIST_BINS
+
+
+# ------------------------------------------------------------------------------------------------ schedules
+def padding_size(num):
+    """data_utils.py:103-107."""
+    return num if num % 8 == 0 else (int(num / 8) + 1) * 8
+
+
+def swp_keys(nt, p, window):
+    """Static-window key frames (compress.py:189-190,217-220,249-263): warm-up frames 0..p-1, then
+    p, p+W, p+2W, ..."""
+    if nt < p + 2:
+        raise TezipError("need at least p+2 frames (the reference crashes otherwise, compress.py:267)")
+    if window < 1:
+        raise TezipError("window size must be >= 1")
+    return list(range(p)) + list(range(p, nt, window))
+
+
+@dataclass
+class Plan:
+    """Which prediction-pool slot every frame uses, and the batched steps that fill the pool."""
+    nt: int
+    p: int
+    keys: list                       # key-frame indices as the decoder will see them (warm-up frames included)
+    windows: list                    # (first_frame, n_frames) of the real windows (first_frame >= p)
+    pred_slot: np.ndarray            # int32 [nt]: pool slot, or -1 where the frame is its own "prediction"
+    apply_eb: np.ndarray             # uint8 [nt]: 1 where error_bound runs (compress.py:315-319)
+    steps: list = field(default_factory=list)   # [(key_idx int32[B] | None, slot0, B)] for k = 1, 2, ...
+    n_slots: int = 1
+
+
+def plan_from_keys(nt, p, keys):
+    """Builds the lock-step plan from a key-frame list (used by SWP compress and by every decode)."""
+    keys = sorted(int(k) for k in keys)
+    real = [k for k in keys if k >= p]
+    if not real or real[0] != p:
+        raise TezipError("frame %d must be a key frame" % p)
+    bounds = real + [nt]
+    windows = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(len(real))]
+    pred_slot = np.full(nt, -1, np.int32)
+    apply_eb = np.zeros(nt, np.uint8)
+    if p > 1:
+        pred_slot[1:p] = 0                      # warm-up frames 1..p-1 are coded against P0 (compress.py:197-206)
+    order = sorted(range(len(windows)), key=lambda i: -windows[i][1])   # stable: ties keep stream order
+    firsts = np.array([windows[i][0] for i in order], np.int32)
+    lens = np.array([windows[i][1] for i in order], np.int64)
+    steps, slot = [], 1
+    k = 1
+    while True:
+        B = int(np.count_nonzero(lens > k))
+        if B == 0:
+            break
+        steps.append((firsts[:B].copy() if k == 1 else None, slot, B))
+        pred_slot[firsts[:B] + k] = slot + np.arange(B, dtype=np.int32)
+        apply_eb[firsts[:B] + k] = 1
+        slot += B
+        k += 1
+    return Plan(nt, p, keys, windows, pred_slot, apply_eb, steps, slot)
+
+
+def run_plan(net, frames, plan, pool):
+    """Fills pool[1:] with the predictions of every non-key frame; pool[0] = P0."""
+    net.p0(out=pool[0])
+    mb = net.max_batch
+    prev = None
+    for key_idx, slot0, B in plan.steps:
+        if key_idx is not None:
+            idx = torch.from_numpy(key_idx).to(frames.device)
+            prev = ops.pad_normalize(frames, idx, net.Hp, net.Wp)          # compress.py:219 / decompress.py:161
+        out = pool[slot0:slot0 + B]
+        for b0 in range(0, B, mb):
+            net.next(prev[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])  # compress.py:222-229
+        prev = out
+
+
+def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None):
+    """Dynamic-window scheduler (compress.py:214-266 with THRESHOLD): a chain closes its window at frame idx
+    when the mean squared error over the padded frames key+1..idx exceeds `threshold`; idx then becomes the
+    next key and its prediction is dropped.  n_chains > 1 splits [p, nt) into contiguous sub-ranges that run
+    as a batch, each starting with a forced key frame (container-legal; key placement then differs from the
+    sequential reference at the sub-range starts).  Returns (keys, pred_slot, apply_eb, n_slots)."""
+    nt = frames.shape[0]
+    if nt < p + 2:
+        raise TezipError("need at least p+2 frames (the reference crashes otherwise, compress.py:267)")
+    dev = frames.device
+    Hp, Wp, C = net.frame_shape()
+    denom = float(Hp * Wp * C)
+    n_chains = max(1, min(int(n_chains), nt - p))
+    edges = [p + (nt - p) * c // n_chains for c in range(n_chains + 1)]
+    chains = [{"key": edges[c], "idx": edges[c] + 1, "end": edges[c + 1], "last": -1, "sse": 0.0, "cnt": 0}
+              for c in range(n_chains) if edges[c + 1] > edges[c]]
+    keys = set(range(p)) | {c["key"] for c in chains}
+    pred_slot = np.full(nt, -1, np.int32)
+    apply_eb = np.zeros(nt, np.uint8)
+    if p > 1:
+        pred_slot[1:p] = 0
+    net.p0(out=pool[0])
+    cursor = 1
+    mb = net.max_batch
+    while True:
+        act = [c for c in chains if c["idx"] < c["end"]]
+        if not act:
+            break
+        B = len(act)
+        X = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=dev)
+        from_key = [i for i, c in enumerate(act) if c["idx"] == c["key"] + 1]
+        from_pred = [i for i, c in enumerate(act) if c["idx"] != c["key"] + 1]
+        if from_key:
+            kidx = torch.tensor([act[i]["key"] for i in from_key], dtype=torch.int32, device=dev)
+            X[torch.tensor(from_key, device=dev)] = ops.pad_normalize(frames, kidx, Hp, Wp)   # compress.py:219
+        if from_pred:
+            src = torch.tensor([act[i]["last"] for i in from_pred], device=dev)
+            X[torch.tensor(from_pred, device=dev)] = pool[src]                               # compress.py:222
+        out = pool[cursor:cursor + B]
+        for b0 in range(0, B, mb):
+            net.next(X[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])
+        fidx = torch.tensor([c["idx"] for c in act], dtype=torch.int32, device=dev)
+        sse = ops.window_sse(frames, fidx, out).cpu().numpy()                               # compress.py:245-246
+        for i, c in enumerate(act):
+            c["sse"] += float(sse[i])
+            c["cnt"] += 1
+            stop_point = c["sse"] / (c["cnt"] * denom)
+            idx = c["idx"]
+            closes = (threshold is not None and stop_point > threshold) or \
+                     (window is not None and (idx - p) % window == 0)                       # compress.py:249
+            if closes:
+                keys.add(idx)                                                               # compress.py:256-263
+                c["key"], c["sse"], c["cnt"], c["last"] = idx, 0.0, 0, -1
+            else:
+                pred_slot[idx] = cursor + i
+                apply_eb[idx] = 1
+                c["last"] = cursor + i
+            c["idx"] = idx + 1
+        cursor += B
+    return sorted(keys), pred_slot, apply_eb, cursor
+
+
+# ------------------------------------------------------------------------------------------------ compress
+@dataclass
+class Encoded:
+    shape: tuple                 # (1, nt, H, W, C) as written in the trailer (compress.py:390-391)
+    p: int
+    keys: list
+    key_plane: torch.Tensor      # u8 [nt,H,W,C] (device)
+    body: torch.Tensor           # int16 [N] (device): ranks, or the delta stream with entropy=False
+    table: np.ndarray            # int16 [T] or None
+    pred_slot: np.ndarray
+    pool: torch.Tensor = None    # kept only when keep_pool=True
+    x: torch.Tensor = None
+
+    def payload(self):
+        """entropy.dat before zstd (compress.py:375-395), host int16."""
+        return pack_payload(self.body.cpu().numpy(), self.table, self.shape, self.p)
+
+
+def pack_payload(body, table, shape, p):
+    tail = []
+    if table is not None:
+        tail += [int(v) for v in table] + [len(table)]        # compress.py:383-385
+    else:
+        tail += [-1]                                          # compress.py:387
+    tail += [int(v) for v in shape] + [int(p)]                # compress.py:390-392
+    return np.concatenate([np.asarray(body, np.int16), np.array(tail, np.int64).astype(np.int16)])  # :394
+
+
+def is_lossless(mode, bound):
+    """compress.py:24,35: BOUND_VALUE[0] == 0 (or absrel with BOUND_VALUE[1] == 0) leaves diff untouched."""
+    return float(bound[0]) == 0.0 or (mode == "absrel" and float(bound[1]) == 0.0)
+
+
+def pool_slots_upper_bound(nt):
+    return nt + 1
+
+
+def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
+                  keep_x=False, has_prev=False, prev_x=0, hist_reduce=None):
+    """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
+
+    hist_reduce: optional callable(hist_int64_device_tensor) -> None that sums the symbol histogram across
+    ranks in place (multi-GPU: every rank must derive the same table)."""
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4
+    nt, H, W, C = frames.shape
+    dev = frames.device
+    Hp, Wp = padding_size(H), padding_size(W)
+    if (Hp, Wp, C) != net.frame_shape():
+        raise TezipError("ERROR:Image size is out of scope for this model.")            # compress.py:178-181
+    if mode not in ops.MODES:
+        raise TezipError("unknown mode %r" % (mode,))
+    if any(float(b) < 0 for b in bound) and mode != "abs":
+        raise TezipError("error bounds must be non-negative")
+    if threshold is None:
+        plan = plan_from_keys(nt, p, swp_keys(nt, p, window))
+        pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
+        run_plan(net, frames, plan, pool)
+        keys, pred_slot_np, apply_np = plan.keys, plan.pred_slot, plan.apply_eb
+    else:
+        pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
+        keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
+    return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
+                            has_prev, prev_x, hist_reduce)
+
+
+def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
+                     keep_x=False, has_prev=False, prev_x=0, hist_reduce=None):
+    """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map."""
+    nt, H, W, C = frames.shape
+    dev = frames.device
+    pred_slot = torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)).to(dev)
+    is_key = np.zeros(nt, np.uint8)
+    is_key[list(keys)] = 1
+    key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))                  # compress.py:183-263
+    N = nt * H * W * C
+    body = torch.empty(N, dtype=torch.int16, device=dev)
+    table = None
+    x = None
+    lossless = is_lossless(mode, bound)
+    if not lossless or keep_x:
+        x = ops.residual(frames, pool, pred_slot)                                        # compress.py:293-314
+        if not lossless:
+            ops.error_bound(frames, x, torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev), mode,
+                            list(bound))                                                 # compress.py:315-319
+    if entropy:
+        hist = torch.zeros(TZ_HIST_BINS, dtype=torch.int64, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+        if x is not None:
+            ops.finding_difference_hist(x, hist, ovf, has_prev, prev_x)                  # :339-340,348-355
+        else:
+            ops.encode_lossless(frames, pool, pred_slot, 0, hist=hist, overflow=ovf, has_prev=has_prev,
+                                prev_x=prev_x)
+        if hist_reduce is not None:
+            hist_reduce(hist)
+            hist_reduce(ovf)
+        hist_np = hist.cpu().numpy()
+        if int(ovf.item()) != 0:
+            raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
+                             "cannot represent this bound" % TZ_HIST_BINS)
+        table = ops.build_table(hist_np)                                                 # :352-361
+        lut = torch.from_numpy(ops.encode_lut(table)).to(dev)
+    else:
+        lut = None
+    if x is not None:
+        ops.finding_difference_rank(x, lut, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
+    else:
+        ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut, out=body, has_prev=has_prev, prev_x=prev_x)
+    return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),
+                   pool if keep_pool else None, x if keep_x else None)
+
+
+# ------------------------------------------------------------------------------------------------ decompress
+def parse_payload(data):
+    """decompress.py:103-113,203-221 -> (body view int16, table or None, shape(5), p)."""
+    data = np.asarray(data, dtype=np.int16)
+    if data.size < 8:
+        raise TezipError("entropy.dat payload is too short")
+    p = int(data[-1])
+    shape = tuple(int(v) for v in data[-6:-1])
+    data = data[:-6]
+    table_len = int(data[-1])
+    if table_len == -1:
+        return data[:-1], None, shape, p
+    if table_len < 0 or table_len + 1 > data.size:
+        raise TezipError("corrupt entropy.dat trailer (table length %d)" % table_len)
+    table_start = data.size - table_len - 1
+    return data[:table_start], data[table_start:-1].copy(), shape, p
+
+
+def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0):
+    """decompress.py:115-256,269 on device tensors: key_plane u8 [nt,H,W,C], body int16 [N] -> u8 frames."""
+    _one, nt, H, W, C = shape
+    dev = key_plane.device
+    Hp, Wp = padding_size(H), padding_size(W)
+    if (Hp, Wp, C) != net.frame_shape():
+        raise TezipError("ERROR:keyframe size and model size do not match.")             # decompress.py:131-135
+    if body.numel() != nt * H * W * C:
+        raise TezipError("entropy.dat holds %d residuals, shape needs %d" % (body.numel(), nt * H * W * C))
+    key_plane = key_plane.view(nt, H, W, C)
+    nz = ops.frames_nonzero(key_plane).cpu().numpy()                                     # decompress.py:123-127
+    keys = [int(i) for i in np.nonzero(nz)[0]]
+    plan = plan_from_keys(nt, p, keys)
+    pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
+    run_plan(net, key_plane, plan, pool)                                                 # decompress.py:138-189
+    pred_slot = torch.from_numpy(plan.pred_slot).to(dev)
+    if table is not None:
+        lut = torch.from_numpy(ops.decode_lut(table)).to(dev)
+        tl = len(table)
+    else:
+        lut, tl = None, -1
+    return ops.reconstruct(body, (nt, H, W, C), Hp, Wp, tl, lut, pool, pred_slot, key_plane, first_mode, first_x,
+                           want_x=want_x), plan

@@ -1,0 +1,104 @@
+"""The on-disk container: filename.txt, key_frame.dat, entropy.dat -- unchanged from
+the reference (compress.py:133-136,271-278,394-400; decompress.py:48-56,87-103).
+
+zstd: the reference calls python-zstd 1.4.5.1 `zstd.compress(bytes, 9)` / `zstd.decompress(bytes)`
+(docs/index.rst:267), i.e. ONE frame that carries its content size.  Here libzstd.so.1 is driven through ctypes;
+`workers > 0` uses the multithreaded single-frame encoder (ZSTD_c_nbWorkers), which the reference's decoder reads
+as-is.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+ZSTD_LEVEL = 9                       # compress.py:276,398
+KEY_FILE, ENTROPY_FILE, NAMES_FILE = "key_frame.dat", "entropy.dat", "filename.txt"
+_ZSTD_c_compressionLevel, _ZSTD_c_contentSizeFlag, _ZSTD_c_nbWorkers = 100, 200, 400
+
+_z = None
+
+
+def _zlib():
+    global _z
+    if _z is None:
+        z = ctypes.CDLL("libzstd.so.1")
+        sz, vp, ci = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
+        z.ZSTD_compressBound.restype, z.ZSTD_compressBound.argtypes = sz, [sz]
+        z.ZSTD_compress.restype, z.ZSTD_compress.argtypes = sz, [vp, sz, vp, sz, ci]
+        z.ZSTD_decompress.restype, z.ZSTD_decompress.argtypes = sz, [vp, sz, vp, sz]
+        z.ZSTD_getFrameContentSize.restype, z.ZSTD_getFrameContentSize.argtypes = ctypes.c_ulonglong, [vp, sz]
+        z.ZSTD_isError.restype, z.ZSTD_isError.argtypes = ctypes.c_uint, [sz]
+        z.ZSTD_createCCtx.restype, z.ZSTD_createCCtx.argtypes = vp, []
+        z.ZSTD_freeCCtx.restype, z.ZSTD_freeCCtx.argtypes = sz, [vp]
+        z.ZSTD_CCtx_setParameter.restype, z.ZSTD_CCtx_setParameter.argtypes = sz, [vp, ci, ci]
+        z.ZSTD_compress2.restype, z.ZSTD_compress2.argtypes = sz, [vp, vp, sz, vp, sz]
+        _z = z
+    return _z
+
+
+def zstd_compress(buf, level=ZSTD_LEVEL, workers=0):
+    """buf: bytes or a C-contiguous numpy array.  Returns bytes (one zstd frame with content size)."""
+    z = _zlib()
+    a = np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else \
+        np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    n = a.size
+    cap = z.ZSTD_compressBound(n)
+    dst = np.empty(cap, np.uint8)
+    if workers > 0:
+        c = z.ZSTD_createCCtx()
+        try:
+            z.ZSTD_CCtx_setParameter(c, _ZSTD_c_compressionLevel, level)
+            z.ZSTD_CCtx_setParameter(c, _ZSTD_c_contentSizeFlag, 1)
+            z.ZSTD_CCtx_setParameter(c, _ZSTD_c_nbWorkers, int(workers))
+            r = z.ZSTD_compress2(c, dst.ctypes.data, cap, a.ctypes.data, n)
+        finally:
+            z.ZSTD_freeCCtx(c)
+    else:
+        r = z.ZSTD_compress(dst.ctypes.data, cap, a.ctypes.data, n, level)
+    if z.ZSTD_isError(r):
+        raise RuntimeError("zstd compression failed")
+    return dst[:r].tobytes()
+
+
+def zstd_decompress(data):
+    """Returns a numpy uint8 array (one-shot decode sized from the frame header, like python-zstd)."""
+    z = _zlib()
+    src = np.frombuffer(data, np.uint8)
+    size = z.ZSTD_getFrameContentSize(src.ctypes.data, src.size)
+    if size >= (1 << 62):
+        raise RuntimeError("zstd frame does not carry its content size")
+    dst = np.empty(max(int(size), 1), np.uint8)
+    r = z.ZSTD_decompress(dst.ctypes.data, int(size), src.ctypes.data, src.size)
+    if z.ZSTD_isError(r) or r != size:
+        raise RuntimeError("zstd decompression failed")
+    return dst[:r]
+
+
+def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
+    """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd)."""
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, NAMES_FILE), "w", encoding="UTF-8") as f:     # compress.py:133-136
+        f.write("%d\n" % int(is_rgb))
+        for nm in names:
+            f.write("%s\n" % nm)
+    kb = zstd_compress(np.ascontiguousarray(key_plane, np.uint8), ZSTD_LEVEL, workers)     # compress.py:271-278
+    with open(os.path.join(out_dir, KEY_FILE), "wb") as f:
+        f.write(kb)
+    eb = zstd_compress(np.ascontiguousarray(payload, "<i2"), ZSTD_LEVEL, workers)          # compress.py:394-400
+    with open(os.path.join(out_dir, ENTROPY_FILE), "wb") as f:
+        f.write(eb)
+    return len(kb), len(eb)
+
+
+def read_container(comp_dir):
+    """-> (names, is_rgb, key_plane u8 flat, payload int16)  (decompress.py:48-56,87-103)."""
+    with open(os.path.join(comp_dir, NAMES_FILE), "r", encoding="UTF-8") as f:
+        names = [s.strip() for s in f.readlines()]
+    is_rgb = True
+    if names and len(names[0]) == 1 and names[0].isdigit():                               # decompress.py:55-56
+        is_rgb = bool(int(names.pop(0)))
+    with open(os.path.join(comp_dir, KEY_FILE), "rb") as f:
+        key_plane = zstd_decompress(f.read())
+    with open(os.path.join(comp_dir, ENTROPY_FILE), "rb") as f:
+        payload = zstd_decompress(f.read()).view("<i2")
+    return names, is_rgb, key_plane, payload

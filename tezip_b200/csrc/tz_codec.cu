@@ -1,0 +1,760 @@
+// tezip_b200 -- codec kernels: residual, error-bound quantisation, 1-D delta + histogram, rank map,
+// decoder (rank -> symbol -> prefix scan -> reconstruct), DWP metric, key plane.
+// HBM-bound integer/byte work: coalesced 16-byte accesses, shared-memory histograms/LUTs, grids sized in
+// multiples of the SM count.  Reference lines cited per kernel (paths under /root/reference/src).
+#include "tz_common.cuh"
+
+namespace {
+
+struct Geo {
+  int H, W, C, Hp, Wp;
+  int rowlen;              // W*C   samples per cropped row
+  int prow;                // Wp*C  floats per padded row
+  long long frame_elems;   // H*W*C
+  long long pframe_elems;  // Hp*Wp*C
+};
+
+static Geo make_geo(int H, int W, int C, int Hp, int Wp) {
+  Geo g;
+  g.H = H; g.W = W; g.C = C; g.Hp = Hp; g.Wp = Wp;
+  g.rowlen = W * C;
+  g.prow = Wp * C;
+  g.frame_elems = (long long)H * W * C;
+  g.pframe_elems = (long long)Hp * Wp * C;
+  return g;
+}
+
+// compress.py:307,310-311: float32 product, then truncation toward zero.
+__device__ __forceinline__ int q255(float p) { return __float2int_rz(__fmul_rn(p, 255.0f)); }
+
+// compress.py:293-314 for one sample (generic addressing).
+__device__ __forceinline__ int resid_at(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
+                                        const int32_t *__restrict__ slot, const Geo &g, long long i) {
+  long long f = i / g.frame_elems;
+  int s = slot[f];
+  if (s < 0) return 0;
+  int r = (int)(i - f * g.frame_elems);
+  int row = r / g.rowlen;
+  int col = r - row * g.rowlen;
+  float p = pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col];
+  return q255(p) - (int)frames[i];
+}
+
+// Loads the residuals of 8 consecutive samples i0..i0+7 (i0 % 8 == 0) into v[0..7].
+// Fast path (rowlen % 8 == 0): one 8-byte frame load + two 16-byte prediction loads.
+template <bool FAST>
+__device__ __forceinline__ void resid8(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
+                                       const int32_t *__restrict__ slot, const Geo &g, long long i0,
+                                       long long n, int v[8]) {
+  if (FAST) {
+    long long f = i0 / g.frame_elems;
+    int s = slot[f];
+    if (s < 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = 0;
+      return;
+    }
+    int r = (int)(i0 - f * g.frame_elems);
+    int row = r / g.rowlen;
+    int col = r - row * g.rowlen;
+    uint2 a = *reinterpret_cast<const uint2 *>(frames + i0);
+    const float4 *pp =
+        reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
+    float4 p0 = pp[0], p1 = pp[1];
+    v[0] = q255(p0.x) - (int)(a.x & 0xff);
+    v[1] = q255(p0.y) - (int)((a.x >> 8) & 0xff);
+    v[2] = q255(p0.z) - (int)((a.x >> 16) & 0xff);
+    v[3] = q255(p0.w) - (int)(a.x >> 24);
+    v[4] = q255(p1.x) - (int)(a.y & 0xff);
+    v[5] = q255(p1.y) - (int)((a.y >> 8) & 0xff);
+    v[6] = q255(p1.z) - (int)((a.y >> 16) & 0xff);
+    v[7] = q255(p1.w) - (int)(a.y >> 24);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? resid_at(frames, pool, slot, g, i0 + k) : 0;
+  }
+}
+
+__device__ __forceinline__ void load8_i16(const int16_t *__restrict__ x, long long i0, long long n, int v[8]) {
+  if (i0 + 8 <= n) {
+    uint4 a = *reinterpret_cast<const uint4 *>(x + i0);
+    v[0] = (int16_t)(a.x & 0xffff); v[1] = (int16_t)(a.x >> 16);
+    v[2] = (int16_t)(a.y & 0xffff); v[3] = (int16_t)(a.y >> 16);
+    v[4] = (int16_t)(a.z & 0xffff); v[5] = (int16_t)(a.z >> 16);
+    v[6] = (int16_t)(a.w & 0xffff); v[7] = (int16_t)(a.w >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? (int)x[i0 + k] : 0;
+  }
+}
+
+__device__ __forceinline__ void store8_i16(int16_t *__restrict__ out, long long i0, long long n, const int v[8]) {
+  if (i0 + 8 <= n) {
+    uint4 a;
+    a.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+    a.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+    a.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+    a.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+    *reinterpret_cast<uint4 *>(out + i0) = a;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (i0 + k < n) out[i0 + k] = (int16_t)v[k];
+  }
+}
+
+// compress.py:75: y[i] = x[i-1] - x[i] in int16 arithmetic; y[0] = x[0] (or prev_x - x[0] on a shard).
+__device__ __forceinline__ void delta8(const int v[8], int prev, bool is_first_global, int y[8]) {
+  y[0] = is_first_global ? v[0] : (int)(int16_t)(prev - v[0]);
+#pragma unroll
+  for (int k = 1; k < 8; k++) y[k] = (int)(int16_t)(v[k - 1] - v[k]);
+}
+
+// ------------------------------------------------------------------------------------------------ residual
+// compress.py:293-314.  One thread per 8 samples.
+template <bool FAST>
+__global__ void __launch_bounds__(256) residual_kernel(const uint8_t *__restrict__ frames,
+                                                       const float *__restrict__ pool,
+                                                       const int32_t *__restrict__ slot, int16_t *__restrict__ x,
+                                                       long long n, Geo g) {
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    int v[8];
+    resid8<FAST>(frames, pool, slot, g, gi * 8, n, v);
+    store8_i16(x, gi * 8, n, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ error_bound
+// compress.py:23-70: greedy interval-intersection scan, one thread per (frame, channel) plane, IEEE double
+// with explicit _rn intrinsics so that nothing is contracted into an FMA (NumPy evaluates E, d+E, d-E and
+// (u+l)/2 as separately rounded operations).
+__global__ void __launch_bounds__(32) error_bound_kernel(const uint8_t *__restrict__ frames,
+                                                         int16_t *__restrict__ x,
+                                                         const uint8_t *__restrict__ apply, long long nt, Geo g,
+                                                         int mode, double b0, double b1) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt * g.C) return;
+  long long f = t / g.C;
+  int c = (int)(t - f * g.C);
+  if (!apply[f]) return;
+  const int n = g.H * g.W;
+  const int C = g.C;
+  const uint8_t *o = frames + f * g.frame_elems + c;
+  int16_t *d = x + f * g.frame_elems + c;
+  double E = 0.0;
+  if (mode == TZ_MODE_ABS) {
+    E = fabs(b0);                                                        // :29
+  } else if (mode == TZ_MODE_REL || mode == TZ_MODE_ABSREL) {
+    int mx = o[0], mn = o[0];                                            // :31-32 / :36-37
+    for (int i = 1; i < n; i++) {
+      int v = o[(long long)i * C];
+      mx = max(mx, v);
+      mn = min(mn, v);
+    }
+    if (mode == TZ_MODE_REL) {
+      E = __dmul_rn((double)(mx - mn), b0);                              // :33
+    } else {
+      double a = fabs(b0), r = __dmul_rn((double)(mx - mn), b1);         // :38-39
+      E = (a < r) ? a : r;                                               // :40-43
+    }
+  }
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  double u = INF, l = -INF;                                              // :55-56
+  int head = 0;
+  for (int i = 0; i < n; i++) {                                          // :58
+    double di = (double)d[(long long)i * C];
+    double e = (mode == TZ_MODE_PWREL) ? __dmul_rn((double)o[(long long)i * C], b0) : E;   // :45
+    double Du = __dadd_rn(di, e);                                        // :47
+    double Dl = __dsub_rn(di, e);                                        // :48
+    double mnu = (Du < u) ? Du : u;
+    double mxl = (Dl > l) ? Dl : l;
+    if (__dsub_rn(mnu, mxl) < 0.0) {                                     // :60
+      if (head < i) {
+        double mid = __dmul_rn(__dadd_rn(u, l), 0.5);                    // :61 (u+l)/2, exact halving
+        int16_t q = (int16_t)(long long)mid;                             // int64 slice assignment truncates
+        for (int j = head; j < i; j++) d[(long long)j * C] = q;
+      }
+      u = INF; l = -INF;                                                 // :62-63
+      head = i;                                                          // :64
+    }
+    if (Du < u) u = Du;                                                  // :65
+    if (l < Dl) l = Dl;                                                  // :66
+  }
+  if (head < n) {
+    double mid = __dmul_rn(__dadd_rn(u, l), 0.5);                        // :67
+    int16_t q = (int16_t)(long long)mid;
+    for (int j = head; j < n; j++) d[(long long)j * C] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ delta + histogram
+// compress.py:73-77 + :348-355.  Shared-memory histogram (16 KB), run-length aggregated atomics, one
+// 64-bit global atomic per non-empty bin per block.  SRC 0: x is materialised (int16); SRC 1/2: the
+// residual is recomputed from frames + predictions (fused lossless path), FAST = SRC 2.
+template <int SRC>
+__device__ __forceinline__ void fetch8(const int16_t *__restrict__ x, const uint8_t *__restrict__ frames,
+                                       const float *__restrict__ pool, const int32_t *__restrict__ slot,
+                                       const Geo &g, long long i0, long long n, int v[8], int &prev) {
+  if (SRC == 0) {
+    load8_i16(x, i0, n, v);
+    prev = (i0 > 0) ? (int)x[i0 - 1] : 0;
+  } else {
+    resid8<SRC == 2>(frames, pool, slot, g, i0, n, v);
+    prev = (i0 > 0) ? resid_at(frames, pool, slot, g, i0 - 1) : 0;
+  }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restrict__ x,
+                                                         const uint8_t *__restrict__ frames,
+                                                         const float *__restrict__ pool,
+                                                         const int32_t *__restrict__ slot, Geo g, long long n,
+                                                         int has_prev, int prev_x,
+                                                         unsigned long long *__restrict__ hist,
+                                                         unsigned long long *__restrict__ overflow) {
+  __shared__ unsigned int sh[TZ_HIST_BINS];
+  __shared__ unsigned int sh_ovf;
+  for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x == 0) sh_ovf = 0;
+  __syncthreads();
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    long long i0 = gi * 8;
+    int v[8], y[8], prev;
+    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev);
+    if (i0 == 0 && has_prev) prev = prev_x;
+    delta8(v, prev, i0 == 0 && !has_prev, y);
+    int cur = -1, cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (i0 + k < n) {
+        int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);                 // :348 int16 arithmetic
+        if (s == cur) {
+          cnt++;
+        } else {
+          if (cnt) {
+            if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+          }
+          cur = s;
+          cnt = 1;
+        }
+      }
+    }
+    if (cnt) {
+      if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) {
+    unsigned int c = sh[i];
+    if (c) atomicAdd(&hist[i], (unsigned long long)c);
+  }
+  if (threadIdx.x == 0 && sh_ovf) atomicAdd(overflow, (unsigned long long)sh_ovf);
+}
+
+// ------------------------------------------------------------------------------------------------ delta + rank map
+// compress.py:84-90 with the symbol -> rank table held in shared memory (pure LUT: SURVEY.md A13).
+template <int SRC>
+__global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restrict__ x,
+                                                         const uint8_t *__restrict__ frames,
+                                                         const float *__restrict__ pool,
+                                                         const int32_t *__restrict__ slot, Geo g, long long n,
+                                                         int has_prev, int prev_x,
+                                                         const int16_t *__restrict__ lut,
+                                                         int16_t *__restrict__ out) {
+  __shared__ int16_t sl[TZ_HIST_BINS];
+  if (lut) {
+    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
+    __syncthreads();
+  }
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    long long i0 = gi * 8;
+    int v[8], y[8], prev;
+    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev);
+    if (i0 == 0 && has_prev) prev = prev_x;
+    delta8(v, prev, i0 == 0 && !has_prev, y);
+    if (lut) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);
+        y[k] = ((unsigned)s < TZ_HIST_BINS) ? (int)sl[s] : s;            // where() leaves other values alone
+      }
+    }
+    store8_i16(out, i0, n, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_CHUNK = DEC_THREADS * 8;
+
+// decompress.py:31-36,236: rank -> symbol (LUT) -> y = 1600 - s; or y = body with -n streams.
+__device__ __forceinline__ void map8(const int16_t *sl, bool use_lut, int v[8]) {
+  if (use_lut) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int r = v[k];
+      int s = ((unsigned)r < TZ_HIST_BINS) ? (int)sl[r] : r;
+      v[k] = (int)(int16_t)(TZ_SYMBOL_OFFSET - s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) decode_chunksum_kernel(const int16_t *__restrict__ body, long long n,
+                                                                      int use_lut,
+                                                                      const int16_t *__restrict__ lut,
+                                                                      unsigned int *__restrict__ sums) {
+  __shared__ int16_t sl[TZ_HIST_BINS];
+  __shared__ unsigned int wsum[DEC_THREADS / 32];
+  if (use_lut) {
+    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
+    __syncthreads();
+  }
+  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
+  int v[8];
+  load8_i16(body, i0, n, v);   // zeros beyond n
+  map8(sl, use_lut != 0, v);
+  unsigned int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (i0 + k < n) s += (unsigned int)v[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < DEC_THREADS / 32; w++) t += wsum[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the chunk sums, single block (at most a few 10^4 chunks).
+__global__ void __launch_bounds__(1024) decode_scan_kernel(unsigned int *__restrict__ sums, long long nchunks) {
+  __shared__ unsigned int wtot[32];
+  __shared__ unsigned int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < nchunks; base += 1024) {
+    long long i = base + threadIdx.x;
+    unsigned int v = (i < nchunks) ? sums[i] : 0;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned int w = wtot[threadIdx.x];
+      unsigned int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (threadIdx.x >= o) winc += t;
+      }
+      wtot[threadIdx.x] = winc - w;   // exclusive warp offsets
+    }
+    __syncthreads();
+    unsigned int carry = carry_s;
+    unsigned int excl = carry + wtot[threadIdx.x >> 5] + inc - v;
+    if (i < nchunks) sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wtot[31] + inc;
+    __syncthreads();
+  }
+}
+
+// decompress.py:22-29 (as a prefix sum), :252-256, :269.
+template <bool FAST>
+__global__ void __launch_bounds__(DEC_THREADS) decode_reconstruct_kernel(
+    const int16_t *__restrict__ body, long long n, int use_lut, const int16_t *__restrict__ lut,
+    const unsigned int *__restrict__ chunk_prefix, int first_mode, int first_x, const float *__restrict__ pool,
+    const int32_t *__restrict__ slot, const uint8_t *__restrict__ key_plane, uint8_t *__restrict__ out,
+    int16_t *__restrict__ x_out, Geo g) {
+  __shared__ int16_t sl[TZ_HIST_BINS];
+  __shared__ unsigned int wtot[DEC_THREADS / 32];
+  if (use_lut) {
+    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
+    __syncthreads();
+  }
+  // y[0] of the whole stream (needed because x[i] = x0 + y0 - S[i], S inclusive from element 0)
+  int y0;
+  {
+    int r = body[0];
+    if (use_lut) {
+      int s = ((unsigned)r < TZ_HIST_BINS) ? (int)sl[r] : r;
+      y0 = (int)(int16_t)(TZ_SYMBOL_OFFSET - s);
+    } else {
+      y0 = r;
+    }
+  }
+  const int x0 = (first_mode == 0) ? y0 : first_x;
+  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
+  int v[8];
+  load8_i16(body, i0, n, v);
+  map8(sl, use_lut != 0, v);
+  unsigned int loc[8];
+  unsigned int run = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    run += (i0 + k < n) ? (unsigned int)v[k] : 0u;
+    loc[k] = run;
+  }
+  unsigned int inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wtot[w];
+  unsigned int base = chunk_prefix[blockIdx.x] + woff + inc - run;   // sum of all y before i0
+  if (i0 >= n) return;
+  int xs[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) xs[k] = (int)(int16_t)((unsigned int)(x0 + y0) - (base + loc[k]));
+  if (x_out) store8_i16(x_out, i0, n, xs);
+  if (FAST && i0 + 8 <= n) {
+    long long f = i0 / g.frame_elems;
+    int s = slot[f];
+    int P[8];
+    if (s < 0) {
+      uint2 a = *reinterpret_cast<const uint2 *>(key_plane + i0);
+      P[0] = a.x & 0xff; P[1] = (a.x >> 8) & 0xff; P[2] = (a.x >> 16) & 0xff; P[3] = a.x >> 24;
+      P[4] = a.y & 0xff; P[5] = (a.y >> 8) & 0xff; P[6] = (a.y >> 16) & 0xff; P[7] = a.y >> 24;
+    } else {
+      int r = (int)(i0 - f * g.frame_elems);
+      int row = r / g.rowlen;
+      int col = r - row * g.rowlen;
+      const float4 *pp =
+          reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
+      float4 p0 = pp[0], p1 = pp[1];
+      P[0] = q255(p0.x); P[1] = q255(p0.y); P[2] = q255(p0.z); P[3] = q255(p0.w);
+      P[4] = q255(p1.x); P[5] = q255(p1.y); P[6] = q255(p1.z); P[7] = q255(p1.w);
+    }
+    unsigned int o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = (unsigned int)min(max(P[k] - xs[k], 0), 255);   // :252-256,269
+    uint2 w;
+    w.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    w.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+    *reinterpret_cast<uint2 *>(out + i0) = w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      long long i = i0 + k;
+      if (i < n) {
+        long long f = i / g.frame_elems;
+        int s = slot[f];
+        int P;
+        if (s < 0) {
+          P = key_plane[i];
+        } else {
+          int r = (int)(i - f * g.frame_elems);
+          int row = r / g.rowlen;
+          int col = r - row * g.rowlen;
+          P = q255(pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col]);
+        }
+        out[i] = (uint8_t)min(max(P - xs[k], 0), 255);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+// compress.py:138,176 / decompress.py:117,120: normalise through the 256-entry LUT and zero-pad.
+__global__ void __launch_bounds__(256) pad_normalize_kernel(const uint8_t *__restrict__ frames,
+                                                            const int32_t *__restrict__ frame_idx,
+                                                            const float *__restrict__ lut, float *__restrict__ out,
+                                                            int B, Geo g) {
+  __shared__ float sl[256];
+  sl[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  long long total = (long long)B * g.pframe_elems;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / g.pframe_elems;
+    int r = (int)(i - b * g.pframe_elems);
+    int row = r / g.prow;
+    int col = r - row * g.prow;
+    float v = 0.0f;
+    if (row < g.H && col < g.rowlen) {
+      long long f = frame_idx ? (long long)frame_idx[b] : b;
+      v = sl[frames[f * g.frame_elems + (long long)row * g.rowlen + col]];
+    }
+    out[i] = v;
+  }
+}
+
+// compress.py:245-246: sum of squared error over the padded frame, float64, fixed reduction order.
+__global__ void __launch_bounds__(1024) window_sse_kernel(const uint8_t *__restrict__ frames,
+                                                          const int32_t *__restrict__ frame_idx,
+                                                          const float *__restrict__ lut,
+                                                          const float *__restrict__ pred, double *__restrict__ sse,
+                                                          Geo g) {
+  __shared__ float sl[256];
+  __shared__ double red[1024];
+  if (threadIdx.x < 256) sl[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const int b = blockIdx.x;
+  const long long f = frame_idx ? (long long)frame_idx[b] : (long long)b;
+  const float *p = pred + (long long)b * g.pframe_elems;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < (int)g.pframe_elems; i += 1024) {
+    int row = i / g.prow;
+    int col = i - row * g.prow;
+    double a = 0.0;
+    if (row < g.H && col < g.rowlen) a = (double)sl[frames[f * g.frame_elems + (long long)row * g.rowlen + col]];
+    double d = __dsub_rn(a, (double)p[i]);
+    acc = __dadd_rn(acc, __dmul_rn(d, d));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = __dadd_rn(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sse[b] = red[0];
+}
+
+__global__ void __launch_bounds__(256) key_plane_kernel(const uint8_t *__restrict__ frames,
+                                                        const uint8_t *__restrict__ is_key,
+                                                        uint8_t *__restrict__ out, long long nt,
+                                                        long long frame_bytes) {
+  // grid.y = frame; 16-byte vector path when frame_bytes % 16 == 0
+  long long f = blockIdx.y;
+  const bool key = is_key[f] != 0;
+  const uint8_t *src = frames + f * frame_bytes;
+  uint8_t *dst = out + f * frame_bytes;
+  if ((frame_bytes & 15) == 0) {
+    long long nv = frame_bytes >> 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+         i += (long long)gridDim.x * blockDim.x) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (key) v = reinterpret_cast<const uint4 *>(src)[i];
+      reinterpret_cast<uint4 *>(dst)[i] = v;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frame_bytes;
+         i += (long long)gridDim.x * blockDim.x)
+      dst[i] = key ? src[i] : (uint8_t)0;
+  }
+}
+
+__global__ void __launch_bounds__(256) frames_nonzero_kernel(const uint8_t *__restrict__ plane,
+                                                             uint8_t *__restrict__ nonzero,
+                                                             long long frame_bytes) {
+  long long f = blockIdx.x;
+  const uint8_t *src = plane + f * frame_bytes;
+  int any = 0;
+  if ((frame_bytes & 15) == 0) {
+    long long nv = frame_bytes >> 4;
+    for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
+      uint4 v = reinterpret_cast<const uint4 *>(src)[i];
+      any |= (v.x | v.y | v.z | v.w) != 0;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < frame_bytes; i += blockDim.x) any |= src[i] != 0;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) nonzero[f] = any ? 1 : 0;
+}
+
+static int stream_grid(long long work_items, int threads, int per_sm) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)tz::sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static bool fast_ok(const Geo &g) { return (g.rowlen % 8) == 0; }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int tz_pad_normalize(const uint8_t *frames, const int32_t *frame_idx, const float *lut, float *out, int B,
+                     int H, int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && lut && out && B >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_pad_normalize: bad arguments");
+  if (B == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  int grid = stream_grid((long long)B * g.pframe_elems, 256, 8);
+  pad_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, frame_idx, lut, out, B, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_residual(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, int16_t *x,
+                long long nt, int H, int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && pred_slot && x && nt >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_residual: bad arguments");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  int grid = stream_grid((n + 7) / 8, 256, 8);
+  if (fast_ok(g))
+    residual_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, x, n, g);
+  else
+    residual_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, x, n, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long long nt, int H, int W,
+                   int C, int mode, double b0, double b1, void *stream) {
+  TZ_REQUIRE(frames && x && apply && nt >= 0 && H > 0 && W > 0 && C > 0, "tz_error_bound: bad arguments");
+  TZ_REQUIRE(mode >= TZ_MODE_ABS && mode <= TZ_MODE_PWREL, "tz_error_bound: unknown mode %d", mode);
+  if (b0 == 0.0) return TZ_OK;                                   // compress.py:24
+  if (mode == TZ_MODE_ABSREL && b1 == 0.0) return TZ_OK;         // compress.py:35
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, H, W);
+  long long planes = nt * C;
+  const int threads = 32;
+  long long blocks = (planes + threads - 1) / threads;
+  error_bound_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode, b0, b1);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsigned long long *hist,
+                  unsigned long long *overflow, void *stream) {
+  TZ_REQUIRE(x && hist && overflow && n >= 0, "tz_delta_hist: bad arguments");
+  if (n == 0) return TZ_OK;
+  Geo g = make_geo(1, 1, 1, 1, 1);
+  int grid = stream_grid((n + 7) / 8, 256, 4);
+  delta_hist_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x,
+                                                              hist, overflow);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const int16_t *lut, int16_t *out,
+                  void *stream) {
+  TZ_REQUIRE(x && out && n >= 0, "tz_delta_rank: bad arguments");
+  if (n == 0) return TZ_OK;
+  Geo g = make_geo(1, 1, 1, 1, 1);
+  int grid = stream_grid((n + 7) / 8, 256, 4);
+  delta_rank_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x,
+                                                              lut, out);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt,
+                       int H, int W, int C, int Hp, int Wp, int has_prev, int prev_x, int pass,
+                       unsigned long long *hist, unsigned long long *overflow, const int16_t *lut,
+                       int16_t *out, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && pred_slot && nt >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_encode_lossless: bad arguments");
+  TZ_REQUIRE(pass == 0 || pass == 1, "tz_encode_lossless: pass must be 0 or 1");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  int grid = stream_grid((n + 7) / 8, 256, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pass == 0) {
+    TZ_REQUIRE(hist && overflow, "tz_encode_lossless: pass 0 needs hist and overflow");
+    if (fast_ok(g))
+      delta_hist_kernel<2><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, hist, overflow);
+    else
+      delta_hist_kernel<1><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, hist, overflow);
+  } else {
+    TZ_REQUIRE(out, "tz_encode_lossless: pass 1 needs out");
+    if (fast_ok(g))
+      delta_rank_kernel<2><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, lut, out);
+    else
+      delta_rank_kernel<1><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, lut, out);
+  }
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+long long tz_reconstruct_workspace_bytes(long long n) {
+  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
+  return (nchunks + 1) * (long long)sizeof(unsigned int);
+}
+
+int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int Hp, int Wp, int table_len,
+                   const int16_t *rank_lut, int first_mode, int first_x, const float *pred_pool,
+                   const int32_t *pred_slot, const uint8_t *key_plane, uint8_t *out, int16_t *x_out,
+                   void *workspace, void *stream) {
+  TZ_REQUIRE(body && pred_pool && pred_slot && key_plane && out && workspace && nt >= 0 && H > 0 && W > 0 &&
+                 C > 0 && Hp >= H && Wp >= W,
+             "tz_reconstruct: bad arguments");
+  TZ_REQUIRE(table_len < 0 || rank_lut, "tz_reconstruct: rank_lut required when table_len >= 0");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
+  TZ_REQUIRE(nchunks < 2147483647LL, "tz_reconstruct: stream too long for one call");
+  unsigned int *sums = (unsigned int *)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  int use_lut = table_len >= 0;
+  decode_chunksum_kernel<<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(body, n, use_lut, rank_lut, sums);
+  TZ_CHECK_LAUNCH();
+  decode_scan_kernel<<<1, 1024, 0, st>>>(sums, nchunks);
+  TZ_CHECK_LAUNCH();
+  if (fast_ok(g))
+    decode_reconstruct_kernel<true><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
+        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+  else
+    decode_reconstruct_kernel<false><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
+        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_window_sse(const uint8_t *frames, const int32_t *frame_idx, const float *lut, const float *pred,
+                  double *sse, int B, int H, int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && lut && pred && sse && B >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_window_sse: bad arguments");
+  if (B == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  TZ_REQUIRE(g.pframe_elems < 2147483647LL, "tz_window_sse: frame too large");
+  window_sse_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(frames, frame_idx, lut, pred, sse, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_key_plane(const uint8_t *frames, const uint8_t *is_key, uint8_t *out, long long nt,
+                 long long frame_bytes, void *stream) {
+  TZ_REQUIRE(frames && is_key && out && nt >= 0 && frame_bytes > 0 && nt < 65536LL * 32768LL,
+             "tz_key_plane: bad arguments");
+  if (nt == 0) return TZ_OK;
+  // grid.y is limited to 65535: loop over slabs of frames
+  for (long long f0 = 0; f0 < nt; f0 += 65535) {
+    long long nf = nt - f0 < 65535 ? nt - f0 : 65535;
+    int gx = (int)((frame_bytes / 16 + 255) / 256);
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, (unsigned)nf);
+    key_plane_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames + f0 * frame_bytes, is_key + f0,
+                                                            out + f0 * frame_bytes, nf, frame_bytes);
+    TZ_CHECK_LAUNCH();
+  }
+  return TZ_OK;
+}
+
+int tz_frames_nonzero(const uint8_t *key_plane, uint8_t *nonzero, long long nt, long long frame_bytes,
+                      void *stream) {
+  TZ_REQUIRE(key_plane && nonzero && nt >= 0 && frame_bytes > 0 && nt < 2147483647LL,
+             "tz_frames_nonzero: bad arguments");
+  if (nt == 0) return TZ_OK;
+  frames_nonzero_kernel<<<(unsigned)nt, 256, 0, (cudaStream_t)stream>>>(key_plane, nonzero, frame_bytes);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""Device-side codec ops: thin torch-tensor wrappers over the C ABI (include/tezip_b200.h).
+
+Names follow the reference's module-level functions (compress.py:23-90, decompress.py:22-36) so parity tests
+read like the reference's code.  All tensors are CUDA tensors; every op runs on torch's current stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODES, TZ_HIST_BINS, TZ_SYMBOL_OFFSET, check, ptr
+
+
+def _st(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_LUT_CACHE = {}
+
+
+def norm_lut(device):
+    """lut[k] = float32(k)/255 as compress.py:138 computes it (identical to decompress.py:117)."""
+    key = str(device)
+    if key not in _LUT_CACHE:
+        _LUT_CACHE[key] = torch.from_numpy(np.arange(256).astype(np.float32) / 255).to(device)
+    return _LUT_CACHE[key]
+
+
+def pad_normalize(frames, frame_idx, Hp, Wp, out=None):
+    """frames u8 [n,H,W,C]; frame_idx int32 [B] (device) or None -> f32 [B,Hp,Wp,C]."""
+    n, H, W, C = frames.shape
+    B = n if frame_idx is None else frame_idx.numel()
+    if out is None:
+        out = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=frames.device)
+    check(_lib.load().tz_pad_normalize(ptr(frames), ptr(frame_idx), ptr(norm_lut(frames.device)), ptr(out), B, H, W, C,
+                                       Hp, Wp, _st(frames.device)), "tz_pad_normalize")
+    return out
+
+
+def residual(frames, pred_pool, pred_slot, out=None):
+    """compress.py:293-314 -> int16 [n,H,W,C]."""
+    n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    if out is None:
+        out = torch.empty((n, H, W, C), dtype=torch.int16, device=frames.device)
+    check(_lib.load().tz_residual(ptr(frames), ptr(pred_pool), ptr(pred_slot), ptr(out), n, H, W, C, Hp, Wp,
+                                  _st(frames.device)), "tz_residual")
+    return out
+
+
+def error_bound(frames, x, apply, mode, value):
+    """compress.py:23-70 applied in place to every flagged frame of x (int16 [n,H,W,C])."""
+    n, H, W, C = frames.shape
+    b0 = float(value[0])
+    b1 = float(value[1]) if len(value) > 1 else 0.0
+    check(_lib.load().tz_error_bound(ptr(frames), ptr(x), ptr(apply), n, H, W, C, MODES[mode], b0, b1,
+                                     _st(frames.device)), "tz_error_bound")
+    return x
+
+
+def finding_difference_hist(x, hist, overflow, has_prev=False, prev_x=0):
+    """compress.py:73-77 + :348-355: accumulates the histogram of 1600 - y into hist (u64 as int64[4096])."""
+    check(_lib.load().tz_delta_hist(ptr(x), x.numel(), int(has_prev), int(prev_x), ptr(hist), ptr(overflow),
+                                    _st(x.device)), "tz_delta_hist")
+
+
+def finding_difference_rank(x, lut, out=None, has_prev=False, prev_x=0):
+    """compress.py:73-77 + replacing_based_on_frequency (:84-90); lut None -> the raw delta stream."""
+    if out is None:
+        out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+    check(_lib.load().tz_delta_rank(ptr(x), x.numel(), int(has_prev), int(prev_x), ptr(lut), ptr(out),
+                                    _st(x.device)), "tz_delta_rank")
+    return out
+
+
+def encode_lossless(frames, pred_pool, pred_slot, pass_, hist=None, overflow=None, lut=None, out=None,
+                    has_prev=False, prev_x=0):
+    n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    check(_lib.load().tz_encode_lossless(ptr(frames), ptr(pred_pool), ptr(pred_slot), n, H, W, C, Hp, Wp,
+                                         int(has_prev), int(prev_x), pass_, ptr(hist), ptr(overflow), ptr(lut),
+                                         ptr(out), _st(frames.device)), "tz_encode_lossless")
+    return out
+
+
+def build_table(hist_np):
+    """compress.py:352-361: symbols with count > 0 sorted by count descending, ties by ascending symbol."""
+    ii = np.nonzero(hist_np)[0]
+    order = np.lexsort((ii, -hist_np[ii].astype(np.int64)))
+    return ii[order].astype(np.int16)
+
+
+def encode_lut(table):
+    """symbol -> rank over the whole 4096-symbol domain, with the reference's sequential where() passes
+    (compress.py:84-90) so that value/index collisions behave identically."""
+    result = np.arange(TZ_HIST_BINS, dtype=np.int16)
+    for idx, num in enumerate(table):
+        result = np.where(result == num, np.int16(idx), result)
+    return result.astype(np.int16)
+
+
+def decode_lut(table):
+    """rank -> symbol (decompress.py:31-36), identity beyond the table."""
+    result = np.arange(TZ_HIST_BINS, dtype=np.int16)
+    for idx, num in enumerate(table):
+        result = np.where(result == idx, np.int16(num), result)
+    return result.astype(np.int16)
+
+
+def reconstruct(body, shape, Hp, Wp, table_len, rank_lut, pred_pool, pred_slot, key_plane, first_mode=0, first_x=0,
+                want_x=False):
+    """decompress.py:229,236,240-245,252-256,269 -> u8 [n,H,W,C] (and x int16 if want_x)."""
+    n, H, W, C = shape
+    dev = body.device
+    lib = _lib.load()
+    ws = torch.empty(int(lib.tz_reconstruct_workspace_bytes(n * H * W * C)), dtype=torch.uint8, device=dev)
+    out = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
+    x = torch.empty(n * H * W * C, dtype=torch.int16, device=dev) if want_x else None
+    check(lib.tz_reconstruct(ptr(body), n, H, W, C, Hp, Wp, int(table_len), ptr(rank_lut), int(first_mode),
+                             int(first_x), ptr(pred_pool), ptr(pred_slot), ptr(key_plane), ptr(out), ptr(x), ptr(ws),
+                             _st(dev)), "tz_reconstruct")
+    return (out, x) if want_x else out
+
+
+def window_sse(frames, frame_idx, pred, out=None):
+    """compress.py:245-246 numerator per chain: f64 [B]."""
+    _n, H, W, C = frames.shape
+    B, Hp, Wp, _c = pred.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.float64, device=frames.device)
+    check(_lib.load().tz_window_sse(ptr(frames), ptr(frame_idx), ptr(norm_lut(frames.device)), ptr(pred), ptr(out), B,
+                                    H, W, C, Hp, Wp, _st(frames.device)), "tz_window_sse")
+    return out
+
+
+def key_plane(frames, is_key, out=None):
+    n = frames.shape[0]
+    fb = frames[0].numel() * frames.element_size()
+    if out is None:
+        out = torch.empty_like(frames)
+    check(_lib.load().tz_key_plane(ptr(frames), ptr(is_key), ptr(out), n, fb, _st(frames.device)), "tz_key_plane")
+    return out
+
+
+def frames_nonzero(plane):
+    n = plane.shape[0]
+    fb = plane[0].numel() * plane.element_size()
+    out = torch.empty(n, dtype=torch.uint8, device=plane.device)
+    check(_lib.load().tz_frames_nonzero(ptr(plane), ptr(out), n, fb, _st(plane.device)), "tz_frames_nonzero")
+    return out
