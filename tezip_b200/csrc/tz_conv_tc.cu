@@ -1,7 +1,674 @@
-// placeholder: tensor-core path (filled in next)
+// tezip_b200 -- PredNet convolutions as implicit GEMMs on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every 3x3 convolution of `next()` (prednet.py:255-258,290):
+//   M = 128 output pixels (a TB x TH x TW patch of the NHWC activation tensor), N = up to 256 output channels,
+//   K = 9 taps x Cin, walked tap-major in blocks of KC channels.
+//   warp 4  : TMA producer.  The A operand of tap (dy,dx) is the SAME 4-D box of the fp16 activation tensor
+//             shifted by (dy-1, dx-1); TMA zero-fills out-of-bounds rows/columns, which is exactly Keras'
+//             'same' padding, so no im2col buffer exists anywhere.  The B operand is a [N_tile x KC] box of the
+//             pre-packed K-major weight matrix.  Both land in 128B/64B/32B-swizzled shared memory.
+//   warp 5  : allocates TMEM and issues tcgen05.mma (M128 x N x K16, fp16 x fp16 -> fp32 in TMEM) from one
+//             elected lane; tcgen05.commit releases smem stages / publishes the accumulator.
+//   warps 0-3: epilogue.  tcgen05.ld the accumulator rows (one pixel per thread) and finish the layer in
+//             registers: bias + relu + 2x2 max-pool + error units (A path, prednet.py:274-277,290-291), or
+//             bias-map + hard-sigmoid/tanh LSTM cell (R path, prednet.py:255-259) with the nearest-neighbour
+//             up-sampling (prednet.py:263-264) folded into the store.  Two TMEM accumulator stages overlap the
+//             epilogue of tile i with the MMAs of tile i+1.
+// Determinism: one kernel configuration per layer, no split-K, no atomics; each output element is a fixed-order
+// sum over K inside the tensor core, independent of batch size, tile position and grid size.
 #include "tz_prednet.cuh"
+
+#include <cuda.h>
+#include <string.h>
+
 namespace tz {
-int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &) { set_error("tensor-core path not built"); return TZ_ECUDA; }
-void tc_destroy(tz_prednet *) {}
-int tc_next(tz_prednet *, const float *, float *, int, cudaStream_t) { set_error("tensor-core path not built"); return TZ_ECUDA; }
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait for the phase with the given parity.  A pipeline bug must surface as an error, never as a hung GPU:
+// after ~4 s of waiting the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns: thread i of the warp receives TMEM lane (base lane + i)
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ kernel arguments
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
+constexpr int TC_TMEM_COLS = 512;
+
+struct ConvArgs {
+  int B, H, W;
+  int tw_log, th_log, tb_log;    // tile = 2^tb x 2^th x 2^tw pixels = 128
+  int tiles_w, tiles_h, n_tiles_n;
+  int kchunks, ksteps;           // K blocks per tap, MMAs (K=16) per K block
+  int KC, cin_pad;               // channels per K block, kchunks*KC
+  int n_tile;                    // MMA N (multiple of 16)
+  int stages;
+  uint32_t a_stride, stage_stride, tx_bytes;
+  uint32_t desc_hi;              // upper half of the smem matrix descriptor (SBO, version, swizzle)
+  uint32_t idesc;
+  // --- A epilogue (pool + error units)
+  const float *bias;             // [N]
+  const float *ahat_next;        // [H/2, W/2, S_next]
+  __half *xe_out;                // X_{l+1}: [B, H/2, W/2, xe_cstride], e written at channels [0, 2*S_next)
+  int xe_cstride, S_next;
+  // --- R epilogue (LSTM)
+  const float *bm;               // [H, W, 4R]
+  const float *c0;               // [H, W, R]
+  int R, NC, NCp;                // channels, channels per N tile, gate-block column pitch (NC rounded up to 8)
+  __half *xr_out;                // X_{l-1}: [B, 2H, 2W, xr_cstride], r written up-sampled at channel xr_coff
+  int xr_cstride, xr_coff;
+  float *r0_out;                 // layer 0: r as fp32 [B, H, W, R] (xr_out == nullptr)
+};
+
+__device__ __forceinline__ float hsig(float x) {
+  return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.0f), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int EPI>  // 0: A path (pool + E), 1: R path (LSTM)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+
+  const int tiles_img = P.tiles_w * P.tiles_h;
+  const int tiles_b = (P.B + (1 << P.tb_log) - 1) >> P.tb_log;
+  const int n_tiles = tiles_img * tiles_b * P.n_tiles_n;
+  const int kblocks = 9 * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; s++) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 4) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nt = t % P.n_tiles_n;
+        int mt = t / P.n_tiles_n;
+        const int twi = mt % P.tiles_w;
+        mt /= P.tiles_w;
+        const int thi = mt % P.tiles_h;
+        const int tbi = mt / P.tiles_h;
+        const int w0 = twi << P.tw_log, h0 = thi << P.th_log, b0 = tbi << P.tb_log;
+        const int n0 = nt * P.n_tile;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int tap = kb / P.kchunks, ch = kb - tap * P.kchunks;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t full = full0 + 8 * s;
+          mbar_expect_tx(full, P.tx_bytes);
+          const uint32_t sa = smem0 + s * P.stage_stride;
+          tma_load_4d(sa, &tmA, full, ch * P.KC, w0 + dx - 1, h0 + dy - 1, b0);
+          tma_load_2d(sa + P.a_stride, &tmB, full, tap * P.cin_pad + ch * P.KC, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+        const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+        mbar_wait(tempty0 + 8 * a, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * TC_ACC_STRIDE;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + s * P.stage_stride;
+          const uint64_t hi = (uint64_t)P.desc_hi << 32;
+          const uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFFu) | (1u << 16));
+          const uint64_t bdesc = hi | (uint64_t)((((sa + P.a_stride) >> 4) & 0x3FFFu) | (1u << 16));
+          for (int k = 0; k < P.ksteps; k++)  // advance 32 bytes (16 fp16 of K) inside the swizzled row
+            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+          tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+        }
+        tc_commit(tfull0 + 8 * a);    // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 0..3)
+    const int m = warp * 32 + lane;  // accumulator row == pixel inside the tile
+    const int tw = m & ((1 << P.tw_log) - 1);
+    const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
+    const int tb = m >> (P.tw_log + P.th_log);
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+      const int nt = t % P.n_tiles_n;
+      int mt = t / P.n_tiles_n;
+      const int twi = mt % P.tiles_w;
+      mt /= P.tiles_w;
+      const int thi = mt % P.tiles_h;
+      const int tbi = mt / P.tiles_h;
+      const int w = (twi << P.tw_log) + tw, h = (thi << P.th_log) + th, b = (tbi << P.tb_log) + tb;
+      const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
+      const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+      mbar_wait(tfull0 + 8 * a, aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * TC_ACC_STRIDE;
+      if (EPI == 0) {
+        // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
+        const int Ho = P.H >> 1, Wo = P.W >> 1;
+        const bool writer = valid && ((tw & 1) == 0) && ((th & 1) == 0);
+        const long long opix = ((long long)b * Ho + (h >> 1)) * Wo + (w >> 1);
+        const float *ah = P.ahat_next + ((long long)(h >> 1) * Wo + (w >> 1)) * P.S_next;
+        __half *dst = P.xe_out + opix * P.xe_cstride;
+        const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
+        for (int j0 = 0; j0 < n_real; j0 += 8) {
+          float v[8];
+          tc_ld8(trow + j0, v);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int ch = nt * P.n_tile + j0 + j;
+            float x = (ch < P.S_next) ? fmaxf(__fadd_rn(v[j], P.bias[ch]), 0.0f) : 0.0f;
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1 << P.tw_log));
+            v[j] = x;
+          }
+          if (writer) {
+            const int ch0 = nt * P.n_tile + j0;
+            if (ch0 + 8 <= P.S_next && ((P.S_next | P.xe_cstride) & 7) == 0) {
+              float4 a0 = *reinterpret_cast<const float4 *>(ah + ch0), a1 = *reinterpret_cast<const float4 *>(ah + ch0 + 4);
+              const float ahv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              __align__(16) __half up[8], dn[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                up[j] = __float2half_rn(fmaxf(__fsub_rn(ahv[j], v[j]), 0.0f));
+                dn[j] = __float2half_rn(fmaxf(__fsub_rn(v[j], ahv[j]), 0.0f));
+              }
+              *reinterpret_cast<uint4 *>(dst + ch0) = *reinterpret_cast<const uint4 *>(up);
+              *reinterpret_cast<uint4 *>(dst + P.S_next + ch0) = *reinterpret_cast<const uint4 *>(dn);
+            } else {
+              for (int j = 0; j < 8 && ch0 + j < P.S_next; j++) {
+                const float ahj = ah[ch0 + j];
+                dst[ch0 + j] = __float2half_rn(fmaxf(__fsub_rn(ahj, v[j]), 0.0f));
+                dst[P.S_next + ch0 + j] = __float2half_rn(fmaxf(__fsub_rn(v[j], ahj), 0.0f));
+              }
+            }
+          }
+        }
+      } else {
+        // LSTM cell: columns [g*NCp + j], g = i,f,c,o.  c = f*C0 + i*tanh(.), r = o*tanh(c)
+        const long long pix = (long long)h * P.W + w;
+        const float *bm = P.bm + pix * 4 * P.R + nt * P.NC;
+        const float *c0 = P.c0 + pix * P.R + nt * P.NC;
+        for (int j0 = 0; j0 < P.NC; j0 += 8) {
+          float vi[8], vf[8], vc[8], vo[8];
+          tc_ld8(trow + 0 * P.NCp + j0, vi);
+          tc_ld8(trow + 1 * P.NCp + j0, vf);
+          tc_ld8(trow + 2 * P.NCp + j0, vc);
+          tc_ld8(trow + 3 * P.NCp + j0, vo);
+          tc_ld_wait();
+          if (valid) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              if (j0 + j < P.NC) {
+                const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
+                const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
+                const float gc = tanhf(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
+                const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
+                const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
+                r[j] = __fmul_rn(go, tanhf(c));
+              } else {
+                r[j] = 0.0f;
+              }
+            }
+            const int ch0 = nt * P.NC + j0;
+            if (P.xr_out) {
+              // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
+              const int H2 = P.H * 2, W2 = P.W * 2;
+              const bool vec = (j0 + 8 <= P.NC) && (((P.xr_coff + ch0) | P.xr_cstride) & 7) == 0;
+              __align__(16) __half hv[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) hv[j] = __float2half_rn(r[j]);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                __half *dst = P.xr_out + (((long long)b * H2 + 2 * h + (q >> 1)) * W2 + 2 * w + (q & 1)) * P.xr_cstride +
+                              P.xr_coff + ch0;
+                if (vec) {
+                  *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hv);
+                } else {
+                  for (int j = 0; j < 8 && j0 + j < P.NC; j++) dst[j] = hv[j];
+                }
+              }
+            } else {
+              float *dst = P.r0_out + ((long long)b * P.H * P.W + pix) * P.R + ch0;
+              for (int j = 0; j < 8 && j0 + j < P.NC; j++) dst[j] = r[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// prednet.py:274-277 at layer 0, t=0, written as fp16 into channels [0, 2C) of X_0.
+__global__ void __launch_bounds__(256) e0_tc_kernel(const float *__restrict__ in, const float *__restrict__ p0,
+                                                    __half *__restrict__ x0, long long total, long long frame, int C,
+                                                    int cstride) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  int c = (int)(id % C);
+  long long pix = id / C;
+  float a = in[id];
+  float ah = p0[id % frame];
+  x0[pix * cstride + c] = __float2half_rn(fmaxf(__fsub_rn(ah, a), 0.0f));
+  x0[pix * cstride + C + c] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
+}
+
+__global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct ConvTc {
+  CUtensorMap tmA, tmB;
+  ConvArgs args;
+  int epi;
+  uint32_t smem_bytes;
+  __half *wpack;
+};
+
+}  // namespace tz
+
+struct TcState {
+  int L;
+  __half *X[TZ_MAX_LAYERS];   // X_l: [maxB, H_l, W_l, cx[l]] fp16: [e_l | up(r_{l+1}) | zero pad]
+  int cx[TZ_MAX_LAYERS];
+  float *r0;                  // [maxB, H_0, W_0, R_0] fp32
+  tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
+  tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
+  int sm_count;
+};
+
+namespace tz {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static int pick_kc(int c) { return (c % 64 == 0) ? 64 : (c % 32 == 0) ? 32 : 16; }
+static int largest_divisor_le(int n, int cap) {
+  for (int d = cap < n ? cap : n; d >= 1; d--)
+    if (n % d == 0) return d;
+  return 1;
+}
+
+// tile = 2^tb x 2^th x 2^tw pixels (128 in total), chosen to minimise padded work at this resolution.
+static void pick_tile(int H, int W, bool pool, int *tw_log, int *th_log, int *tb_log) {
+  double best = 1e30;
+  for (int a = pool ? 1 : 0; a <= (pool ? 4 : 7); a++)      // TW <= 16 when the epilogue pools inside a warp
+    for (int b = pool ? 1 : 0; a + b <= 7; b++) {
+      int TW = 1 << a, TH = 1 << b, TB = 128 / (TW * TH);
+      if (TW > 256 || TH > 256 || TB > 128) continue;
+      if (pool && TW * 2 > 32) continue;
+      double cost = (double)((W + TW - 1) / TW) * ((H + TH - 1) / TH) / TB + 1e-3 * (7 - a) + 1e-4 * TB;
+      if (cost < best) {
+        best = cost;
+        *tw_log = a;
+        *th_log = b;
+        *tb_log = 7 - a - b;
+      }
+    }
+}
+
+static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx, int cin_real /*channels read*/,
+                     const std::vector<float> &wsrc /*fp32 [3][3][cin_w][cout_w]*/, int cin_w, int cin_ofs, int cout_w,
+                     int n_real /*output channels or R*/) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return TZ_ECUDA;
+  }
+  memset(c, 0, sizeof(*c));
+  ConvArgs &A = c->args;
+  c->epi = epi;
+  A.H = h->H[l];
+  A.W = h->W[l];
+  pick_tile(A.H, A.W, epi == 0, &A.tw_log, &A.th_log, &A.tb_log);
+  A.tiles_w = (A.W + (1 << A.tw_log) - 1) >> A.tw_log;
+  A.tiles_h = (A.H + (1 << A.th_log) - 1) >> A.th_log;
+  A.cin_pad = round_up(cin_real, 16);
+  if (A.cin_pad > cx) {
+    set_error("internal: conv reads %d channels of a %d-channel buffer", A.cin_pad, cx);
+    return TZ_EINVAL;
+  }
+  A.KC = pick_kc(A.cin_pad);
+  A.kchunks = A.cin_pad / A.KC;
+  A.ksteps = A.KC / 16;
+  int rows_total;
+  if (epi == 1) {
+    A.R = n_real;
+    A.NC = largest_divisor_le(n_real, 64);
+    A.NCp = round_up(A.NC, 8);
+    A.n_tile = round_up(4 * A.NCp, 16);
+    A.n_tiles_n = n_real / A.NC;
+  } else {
+    int nt = largest_divisor_le(n_real, 256);
+    A.n_tile = round_up(nt, 16);
+    A.n_tiles_n = n_real / nt;
+    if (A.n_tiles_n > 1 && (nt % 16) != 0) {
+      set_error("unsupported channel count %d for the tensor-core path", n_real);
+      return TZ_EINVAL;
+    }
+  }
+  rows_total = A.n_tiles_n * A.n_tile;
+  const int Ktot = 9 * A.cin_pad;
+  // ---- pack weights: row n (tile-major; gates interleaved per tile), K-major, k = tap*cin_pad + c
+  std::vector<float> wp((size_t)rows_total * Ktot, 0.0f);
+  for (int nt = 0; nt < A.n_tiles_n; nt++)
+    for (int r = 0; r < A.n_tile; r++) {
+      int src_col = -1;
+      if (epi == 1) {
+        int g = r / A.NCp, j = r - g * A.NCp;
+        if (g < 4 && j < A.NC) src_col = g * n_real + nt * A.NC + j;
+      } else {
+        int per = n_real / A.n_tiles_n;
+        if (r < per) src_col = nt * per + r;
+      }
+      if (src_col < 0) continue;
+      float *dst = wp.data() + (size_t)(nt * A.n_tile + r) * Ktot;
+      for (int tap = 0; tap < 9; tap++)
+        for (int ci = 0; ci < cin_real; ci++)
+          dst[tap * A.cin_pad + ci] = wsrc[((size_t)tap * cin_w + cin_ofs + ci) * cout_w + src_col];
+    }
+  float *tmp = nullptr;
+  TZ_CHECK_CUDA(cudaMalloc(&tmp, wp.size() * sizeof(float)));
+  c->wpack = (__half *)dev_alloc(h, wp.size() * sizeof(__half));
+  if (!c->wpack) {
+    cudaFree(tmp);
+    return TZ_ENOMEM;
+  }
+  cudaMemcpy(tmp, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice);
+  f32_to_f16_kernel<<<(unsigned)((wp.size() + 255) / 256), 256>>>(tmp, c->wpack, (long long)wp.size());
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(tmp);
+  if (e != cudaSuccess) {
+    set_error("weight packing failed: %s", cudaGetErrorString(e));
+    return TZ_ECUDA;
+  }
+  // ---- shared-memory plan
+  const uint32_t row_bytes = (uint32_t)A.KC * 2;
+  const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)A.n_tile * row_bytes;
+  A.a_stride = (a_bytes + 1023u) & ~1023u;
+  A.stage_stride = A.a_stride + ((b_bytes + 1023u) & ~1023u);
+  A.tx_bytes = a_bytes + b_bytes;
+  int stages = (int)((200u * 1024u) / A.stage_stride);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) {
+    set_error("internal: pipeline stage of %u bytes does not fit", A.stage_stride);
+    return TZ_EINVAL;
+  }
+  A.stages = stages;
+  c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
+  // ---- descriptors
+  const CUtensorMapSwizzle swz = A.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : A.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const uint32_t layout_type = A.KC == 64 ? 2u : A.KC == 32 ? 4u : 6u;   // UMMA SWIZZLE_128B / 64B / 32B
+  const uint32_t sbo = 8u * row_bytes;                                   // 8-row core-matrix group stride
+  A.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+  A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | ((128u >> 4) << 24);   // f32 acc, f16 x f16, K-major
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
+    cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
+    cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(A, layer %d) failed: %d", l, (int)r);
+      return TZ_ECUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows_total};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)A.KC, (cuuint32_t)A.n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&c->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->wpack, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(B, layer %d) failed: %d", l, (int)r);
+      return TZ_ECUDA;
+    }
+  }
+  return TZ_OK;
+}
+
+int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
+  const int L = h->L;
+  TcState *T = new TcState();
+  memset(T, 0, sizeof(*T));
+  h->tc = T;
+  T->L = L;
+  T->sm_count = sm_count();
+  const int mb = h->cfg.max_batch;
+  for (int l = 0; l < L; l++) {
+    TZ_REQUIRE(h->H[l] % 2 == 0 || l == L - 1, "tensor-core path: odd layer height");
+    T->cx[l] = round_up(2 * h->S[l] + (l < L - 1 ? h->R[l + 1] : 0), 16);
+    size_t bytes = (size_t)mb * h->H[l] * h->W[l] * T->cx[l] * sizeof(__half);
+    T->X[l] = (__half *)dev_alloc(h, bytes);
+    if (!T->X[l]) return TZ_ENOMEM;
+    TZ_CHECK_CUDA(cudaMemset(T->X[l], 0, bytes));   // pad channels multiply zero weights: they must stay finite
+  }
+  T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
+  if (!T->r0) return TZ_ENOMEM;
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+
+  for (int l = 0; l < L; l++) {
+    // gate conv: reads all of X_l = [e_l | up(r_{l+1})]; the r_{t-1} slice of the kernel is hoisted into BM_l
+    const int cin_real = 2 * h->S[l] + (l < L - 1 ? h->R[l + 1] : 0);
+    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], cin_real, wg_host[l], h->cin_g[l], h->R[l],
+                       4 * h->R[l], h->R[l]);
+    if (rc) return rc;
+    ConvArgs &G = T->gconv[l].args;
+    G.bm = h->BM[l];
+    G.c0 = h->C0[l];
+    if (l > 0) {
+      G.xr_out = T->X[l - 1];
+      G.xr_cstride = T->cx[l - 1];
+      G.xr_coff = 2 * h->S[l - 1];
+    } else {
+      G.xr_out = nullptr;
+      G.r0_out = T->r0;
+    }
+    if (l < L - 1) {
+      // a conv: reads channels [0, 2S_l) of X_l
+      std::vector<float> wa((size_t)9 * 2 * h->S[l] * h->S[l + 1]);
+      TZ_CHECK_CUDA(cudaMemcpy(wa.data(), h->w_a[l], wa.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      rc = make_conv(h, &T->aconv[l], 0, l, T->X[l], T->cx[l], 2 * h->S[l], wa, 2 * h->S[l], 0, h->S[l + 1],
+                     h->S[l + 1]);
+      if (rc) return rc;
+      ConvArgs &Aa = T->aconv[l].args;
+      Aa.bias = h->b_a[l];
+      Aa.ahat_next = h->Ahat0[l + 1];
+      Aa.xe_out = T->X[l + 1];
+      Aa.xe_cstride = T->cx[l + 1];
+      Aa.S_next = h->S[l + 1];
+    }
+  }
+  return TZ_OK;
+}
+
+void tc_destroy(tz_prednet *h) {
+  delete h->tc;
+  h->tc = nullptr;
+}
+
+static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
+  ConvArgs A = c->args;
+  A.B = B;
+  const int tiles_b = (B + (1 << A.tb_log) - 1) >> A.tb_log;
+  long long n_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b * A.n_tiles_n;
+  int grid = n_tiles < T->sm_count ? (int)n_tiles : T->sm_count;
+  if (c->epi == 0)
+    conv_tc_kernel<0><<<grid, TC_THREADS, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  else
+    conv_tc_kernel<1><<<grid, TC_THREADS, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st) {
+  TcState *T = h->tc;
+  const int L = h->L;
+  {
+    const int C = h->S[0];
+    long long total = (long long)B * h->H[0] * h->W[0] * C;
+    e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], T->X[0], total,
+                                                                 (long long)h->H[0] * h->W[0] * C, C, T->cx[0]);
+    TZ_CHECK_LAUNCH();
+  }
+  for (int l = 0; l < L - 1; l++) {
+    int rc = launch_conv(T, &T->aconv[l], B, st);
+    if (rc) return rc;
+  }
+  for (int l = L - 1; l >= 0; l--) {
+    int rc = launch_conv(T, &T->gconv[l], B, st);
+    if (rc) return rc;
+  }
+  ConvSrc s = {T->r0, h->R[0], 0, 0, (long long)h->H[0] * h->W[0] * h->R[0]};
+  return conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,
+                        h->cfg.pixel_max, st);
+}
+
+}  // namespace tz
