@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- raw MB/s of the TEZip predict-delta-encode hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- error-bounded lossy compression (`-m abs -b 2`, i.e.
+floor(1e-2 * 255) levels) of 1000 synthetic 128x160x3 uint8 frames with a random-init 4-layer
+(3,48,96,192) PredNet (weight set (ii): U(+-0.1) biases), static window 10, p = 0.  A "step" is one compress
+pass over the whole sequence; the decompress pass over the same container is timed the same way and reported
+under "decompress".  N > 1 (torchrun, one rank per GPU): every rank owns one 1000-frame shard of an N*1000-frame
+sequence (sharded by whole windows, weak scaling); NCCL only all-reduces the symbol histogram and all-gathers
+halo / sizes.
+
+  value  : compress MB/s, frames resident in HBM -> int16 stream + key plane resident in HBM.
+  e2e    : same through the array-level API with HOST buffers (pinned): H2D of the frames and D2H of the stream
+           and key plane inside the timed region.  Boundary = packed int16 stream + key plane (before zstd), the
+           same boundary the reference arm times.
+  --impl reference : the CPU oracle port of the reference (oracle/, torch-CPU fp32 PredNet + C loops) on a bounded
+           sample of the same workload, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STACK = (3, 48, 96, 192)
+H, W, C = 128, 160, 3
+WORKLOAD = "lossy abs bound 2 levels (~1e-2), 1000x128x160x3 u8 synthetic frames, 4-layer PredNet (3,48,96,192), SWP window 10, p=0"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--window", type=int, default=10)
+    ap.add_argument("--mode", default="abs")
+    ap.add_argument("--bound", type=float, nargs="*", default=[2.0])
+    ap.add_argument("--cpu-sample-frames", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tf_burst": float(p["bf16_tflops"]),
+                "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ================================================================================================ reference arm
+def cpu_port_run(frames, ws, window, mode, bound, threads=None):
+    """One compress + one decompress of `frames` with the oracle port; returns seconds and stream sizes."""
+    import torch
+    from oracle import codec_oracle as co
+    from oracle.prednet_oracle import PredNetOracle
+    if threads:
+        torch.set_num_threads(threads)
+    net = PredNetOracle(ws, STACK, STACK)
+    tc, td = {}, {}
+    t0 = time.perf_counter()
+    r = co.compress_arrays(frames, net, 0, window, None, mode, bound, True, timers=tc)
+    t1 = time.perf_counter()
+    out, _ = co.decompress_arrays(r["key_plane"], r["payload"], net, timers=td)
+    t2 = time.perf_counter()
+    return {"compress_s": t1 - t0, "decompress_s": t2 - t1, "r": r, "out": out, "stages_c": tc, "stages_d": td}
+
+
+def run_reference(args):
+    import torch
+    from tezip_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import build as obuild
+    obuild.build()
+    n = args.cpu_sample_frames
+    ws = synth.make_weights(STACK, bias="uniform", seed=7)
+    frames = synth.make_frames(n, H, W, C, seed=1)
+    raw_mb = frames.size / 1e6
+    for _ in range(args.warmup):
+        cpu_port_run(frames[:min(n, 11)], ws, args.window, args.mode, args.bound)
+    tcs, tds = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_port_run(frames, ws, args.window, args.mode, args.bound)
+        tcs.append(r["compress_s"]); tds.append(r["decompress_s"])
+    wall = time.perf_counter() - t0
+    v = raw_mb / float(np.mean(tcs))
+    vd = raw_mb / float(np.mean(tds))
+    cores = torch.get_num_threads()
+    sample = "first %d frames of the workload (%.2f MB raw) per step, oracle port, %d torch threads" % (n, raw_mb, cores)
+    line = {"impl": "reference", "metric": "raw_MB_per_s_compress", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(tcs)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 + int64/int16 (CPU)",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "boundary": "packed int16 stream + key plane, before zstd",
+                                            "sample_frames": n},
+            "decompress": {"value": vd, "unit": "MB/s", "ms_per_step": 1e3 * float(np.mean(tds))},
+            "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port", "sample": sample,
+                             "decompress_value": vd, "host_cpus": os.cpu_count()},
+            "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line))
+
+
+# ================================================================================================ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from tezip_b200 import synth, codec, ops, _lib, build
+    from tezip_b200.prednet import PredNet
+    from tezip_b200.dist import ShardComm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = ShardComm(None, dev)
+    build.build()
+    lib = _lib.load()
+
+    nt, Wn, mode, bound = args.frames, args.window, args.mode, list(args.bound)
+    ws = synth.make_weights(STACK, bias="uniform", seed=7)
+    frames_np = synth.make_frames(nt, H, W, C, seed=1 + rank)
+    raw_bytes = frames_np.size
+    n_win = -(-nt // Wn)
+    net = PredNet(STACK, STACK, weights=ws, input_hw=(H, W), max_batch=min(n_win, 128), device=local)
+    frames_host = torch.from_numpy(frames_np).pin_memory()
+    frames_dev = frames_host.to(dev)
+    N = nt * H * W * C
+    body_host = torch.empty(N, dtype=torch.int16).pin_memory()
+    keyp_host = torch.empty((nt, H, W, C), dtype=torch.uint8).pin_memory()
+    out_host = torch.empty((nt, H, W, C), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def compress_dev():
+        return codec.encode_frames(frames_dev, net, 0, Wn, None, mode, bound, True, comm=comm)
+
+    def compress_e2e():
+        fd = frames_host.to(dev, non_blocking=True)
+        enc = codec.encode_frames(fd, net, 0, Wn, None, mode, bound, True, comm=comm)
+        body_host.copy_(enc.body, non_blocking=True)
+        keyp_host.copy_(enc.key_plane, non_blocking=True)
+        if comm is not None:
+            comm.stream_offsets(enc.body.numel())
+        torch.cuda.synchronize(dev)
+        return enc
+
+    enc0 = compress_dev()
+    first_mode, first_x = (0, 0) if rank == 0 else (1, 0)
+
+    def decompress_dev():
+        return codec.decode_arrays(enc0.key_plane, enc0.body, enc0.table, enc0.shape, 0, net, first_mode=first_mode,
+                                   first_x=first_x)[0]
+
+    def decompress_e2e():
+        kp = keyp_host.to(dev, non_blocking=True)
+        bd = body_host.to(dev, non_blocking=True)
+        out = codec.decode_arrays(kp, bd, enc0.table, enc0.shape, 0, net, first_mode=first_mode, first_x=first_x)[0]
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return out
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.tz_launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        launches = lib.tz_launch_count() - l0
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps, float(t[1]) / steps, launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_c, wall_c, launches = timed(compress_dev, args.steps, args.warmup)
+    ms_d, wall_d, launches_d = timed(decompress_dev, args.steps, args.warmup)
+    clocks = sampler.stop()
+    _ms, wall_ce, _ = timed(compress_e2e, args.steps, max(1, args.warmup - 1))
+    _ms, wall_de, _ = timed(decompress_e2e, args.steps, max(1, args.warmup - 1))
+
+    # correctness inside the bench: the decoded frames respect the bound
+    dec = decompress_dev()
+    maxerr = int((dec.to(torch.int16) - frames_dev.to(torch.int16)).abs().max().item())
+
+    # ---- per-kernel roofline (device events between the launches of one next(); B = windows in flight)
+    pk = peaks()
+    Bk = min(n_win, net.max_batch)
+    xin = ops.pad_normalize(frames_dev, torch.arange(Bk, dtype=torch.int32, device=dev) * Wn, H, W)
+    xout = torch.empty_like(xin)
+    names = net.kernels()
+    acc = np.zeros(len(names))
+    reps = 6
+    for i in range(reps + 2):
+        ms = net.next_timed(xin, xout)
+        if i >= 2:
+            acc += np.array(ms)
+    acc /= reps
+    kern = []
+    for (nm, fl), ms in zip(names, acc):
+        kern.append({"kernel": nm, "ms": float(ms), "tflops": (fl * Bk / (ms * 1e-3) / 1e12) if ms > 0 else 0.0})
+    dom = max(range(len(kern)), key=lambda i: kern[i]["ms"] if kern[i]["kernel"].startswith("conv_tc") else -1)
+    total_ms = float(acc.sum())
+    achieved = kern[dom]["tflops"]
+    roofline = {"bound": "tensor", "kernel": kern[dom]["kernel"], "achieved": achieved, "peak": pk["tf_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "peak_source": "%s bf16 dense sustained (kernel timed inside a 9-launch step); fp16 operands" % pk["src"],
+                "launch_ms": kern[dom]["ms"], "share_of_next": kern[dom]["ms"] / total_ms,
+                "next_step": {"ms": total_ms, "tflops": net.flops_per_frame() * Bk / (total_ms * 1e-3) / 1e12,
+                              "frac": net.flops_per_frame() * Bk / (total_ms * 1e-3) / 1e12 / pk["tf_sustained"]},
+                "kernels": kern}
+
+    # ---- codec kernels against the HBM roofline (7 B/sample algorithmic)
+    enc_keep = codec.encode_frames(frames_dev, net, 0, Wn, None, mode, bound, True, keep_pool=True, comm=None)
+    pool, slot = enc_keep.pool, torch.from_numpy(enc_keep.pred_slot).to(dev)
+    apply_t = torch.from_numpy((enc_keep.pred_slot >= 0).astype(np.uint8)).to(dev)
+    hist = torch.zeros(_lib.TZ_HIST_BINS, dtype=torch.int64, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+    lut = torch.from_numpy(ops.encode_lut(enc_keep.table)).to(dev)
+    xbuf = torch.empty((nt, H, W, C), dtype=torch.int16, device=dev)
+    obuf = torch.empty(N, dtype=torch.int16, device=dev)
+
+    def ev_time(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    codec_ms = {
+        "residual": ev_time(lambda: ops.residual(frames_dev, pool, slot, out=xbuf)),
+        "error_bound": ev_time(lambda: ops.error_bound(frames_dev, xbuf, apply_t, mode, bound)),
+        "delta_hist": ev_time(lambda: ops.finding_difference_hist(xbuf, hist, ovf)),
+        "delta_rank": ev_time(lambda: ops.finding_difference_rank(xbuf, lut, out=obuf)),
+        "fused_lossless_hist": ev_time(lambda: ops.encode_lossless(frames_dev, pool, slot, 0, hist=hist, overflow=ovf)),
+        "fused_lossless_rank": ev_time(lambda: ops.encode_lossless(frames_dev, pool, slot, 1, lut=lut, out=obuf)),
+    }
+    lut_d = torch.from_numpy(ops.decode_lut(enc_keep.table)).to(dev)
+    codec_ms["reconstruct"] = ev_time(lambda: ops.reconstruct(enc_keep.body, (nt, H, W, C), H, W, len(enc_keep.table),
+                                                              lut_d, pool, slot, enc_keep.key_plane))
+    enc_total = codec_ms["residual"] + codec_ms["error_bound"] + codec_ms["delta_hist"] + codec_ms["delta_rank"]
+    roofline_codec = {"bound": "hbm", "kernel": "fused_lossless_rank (residual+delta+rank map)",
+                      "achieved": 7.0 * N / (codec_ms["fused_lossless_rank"] * 1e-3) / 1e9, "peak": pk["hbm"],
+                      "unit": "GB/s", "traffic": None,
+                      "lossy_encode_total": {"ms": enc_total, "achieved": 7.0 * N / (enc_total * 1e-3) / 1e9},
+                      "reconstruct": {"ms": codec_ms["reconstruct"],
+                                      "achieved": 7.0 * N / (codec_ms["reconstruct"] * 1e-3) / 1e9},
+                      "ms": codec_ms, "peak_source": pk["src"] + " copy bandwidth"}
+    roofline_codec["frac"] = roofline_codec["achieved"] / pk["hbm"]
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample
+    cpu = None
+    ratio = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import build as obuild
+        from tezip_b200 import container
+        obuild.build()
+        ns = args.cpu_sample_frames
+        t0 = time.perf_counter()
+        r = cpu_port_run(frames_np[:ns], ws, Wn, mode, bound)
+        sample_mb = ns * H * W * C / 1e6
+        cores = torch.get_num_threads()
+        cpu = {"value": sample_mb / r["compress_s"], "unit": "MB/s", "cores": cores, "kind": "port",
+               "sample": "first %d frames (%.2f MB raw), one compress + one decompress, oracle port" % (ns, sample_mb),
+               "decompress_value": sample_mb / r["decompress_s"], "host_cpus": os.cpu_count(),
+               "stages_compress_s": {k: round(v, 4) for k, v in r["stages_c"].items()},
+               "stages_decompress_s": {k: round(v, 4) for k, v in r["stages_d"].items()}}
+        # compression ratio, same sample, same bound: native vs oracle (zstd level 9 like the reference)
+        encs = codec.encode_frames(frames_dev[:ns].contiguous(), net, 0, Wn, None, mode, bound, True)
+        nat = len(container.zstd_compress(encs.payload())) + len(container.zstd_compress(encs.key_plane.cpu().numpy()))
+        orc = len(container.zstd_compress(r["r"]["payload"])) + len(container.zstd_compress(r["r"]["key_plane"]))
+        ratio = {"native": ns * H * W * C / nat, "oracle": ns * H * W * C / orc, "native_over_oracle": orc / nat,
+                 "sample_frames": ns}
+
+    if rank == 0:
+        total_mb = world * raw_bytes / 1e6
+        line = {
+            "metric": "raw_MB_per_s_compress", "value": total_mb / (ms_c * 1e-3), "unit": "MB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_c, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 x f16 -> f32 (PredNet, tcgen05); int16/f64 codec",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": nt, "windows_in_flight": Bk,
+                       "boundary": "packed int16 stream + key plane, before zstd",
+                       "l2": "no explicit flush: one step streams ~%.1f GB (prediction pool + activations) >> 126 MB L2"
+                             % ((enc_keep.pool.numel() * 4 + net.device_bytes()) / 1e9),
+                       "sharding": "by window, %d ranks" % world},
+            "decompress": {"value": total_mb / (ms_d * 1e-3), "unit": "MB/s", "ms_per_step": ms_d,
+                           "e2e": {"value": total_mb / (wall_de * 1e-3), "unit": "MB/s",
+                                   "h2d_bytes_per_step": int(N * 3), "d2h_bytes_per_step": int(N)}},
+            "e2e": {"value": total_mb / (wall_ce * 1e-3), "unit": "MB/s", "h2d_bytes_per_step": int(N),
+                    "d2h_bytes_per_step": int(N * 3)},
+            "gpu_launches": int(launches), "gpu_launches_decompress": int(launches_d),
+            "wall_ms_per_step": wall_c, "clocks": clocks, "max_abs_error_levels": maxerr,
+            "roofline": roofline, "roofline_codec": roofline_codec, "cpu_baseline": cpu, "ratio": ratio,
+            "prednet_gflop_per_frame": net.flops_per_frame() / 1e9,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -87,6 +87,13 @@ int tz_prednet_p0(tz_prednet *h, float *out, void *stream);
  * frames share the batch. */
 int tz_prednet_next(tz_prednet *h, const float *in, float *out, int B, void *stream);
 
+/* Per-kernel view of one tz_prednet_next() for the roofline report: kernel i of tz_prednet_kernel_count()
+ * has a name and an algorithmic FLOP count per frame; tz_prednet_next_timed() runs one next() with CUDA events
+ * between the launches on `stream` and returns the device time of each kernel in ms (synchronous). */
+int tz_prednet_kernel_count(tz_prednet *h);
+int tz_prednet_kernel_info(tz_prednet *h, int i, char *name, int name_len, double *flops_per_frame);
+int tz_prednet_next_timed(tz_prednet *h, const float *in, float *out, int B, void *stream, float *ms, int n_ms);
+
 /* bytes of device memory the handle holds */
 long long tz_prednet_device_bytes(tz_prednet *h);
 /* algorithmic FLOPs per predicted frame */

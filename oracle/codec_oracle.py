@@ -224,7 +224,20 @@ def compress_arrays(frames, predictor, p, window, threshold, mode, bound, entrop
     windows.append((cur_first, cur_preds))                              # :267-268
     T["predict"] = t_pred
 
-    H, W = X_test.shape[2], X_test.shape[3]
+    out = encode_windows(origine_img, windows, PRE, mode, bound, entropy, T)
+    out["key_plane"] = key_frame.ravel()
+    out["keys"] = [f for f in range(nt) if key_frame[0, f].any()]   # what the decoder will see (decompress.py:123-127)
+    out["Hp"], out["Wp"] = X_test_pad.shape[2], X_test_pad.shape[3]
+    return out
+
+
+def encode_windows(origine_img, windows, PRE, mode, bound, entropy=True, timers=None):
+    """compress.py:289-395: residual, error bound, delta, table, rank map and trailer, GIVEN the windows
+    [(first_frame, [prediction f32 [Hp,Wp,C] per frame])] the scheduler produced."""
+    T = timers if timers is not None else {}
+    tic = time.perf_counter
+    X_test_shape = origine_img.shape
+    H, W = X_test_shape[2], X_test_shape[3]
     difference_list = []
     t0 = tic()
     t_eb = 0.0
@@ -271,16 +284,13 @@ def compress_arrays(frames, predictor, p, window, threshold, mode, bound, entrop
         tail += [int(v) for v in table] + [len(table)]                  # :383-385
     else:
         tail += [-1]                                                    # :387
-    tail += [int(v) for v in X_test.shape] + [PRE]                      # :390-392
+    tail += [int(v) for v in X_test_shape] + [PRE]                      # :390-392
     payload = np.concatenate([result.astype(np.int64), np.array(tail, np.int64)]).astype(np.int16)   # :394
     T["pack"] = tic() - t0
 
-    keys = [f for f in range(nt) if key_frame[0, f].any()]   # what the decoder will see (decompress.py:123-127)
     preds_full = np.concatenate([np.stack(w[1]) for w in windows], axis=0)
-    return {"key_plane": key_frame.ravel(), "payload": payload, "keys": keys,
-            "windows": [(w[0], len(w[1])) for w in windows], "preds": preds_full,
-            "x": x, "y": y, "table": table, "shape": X_test.shape, "Hp": X_test_pad.shape[2],
-            "Wp": X_test_pad.shape[3]}
+    return {"payload": payload, "windows": [(w[0], len(w[1])) for w in windows], "preds": preds_full,
+            "x": x, "y": y, "table": table, "shape": tuple(X_test_shape)}
 
 
 # ------------------------------------------------------------------------------------------------ decompress
@@ -299,8 +309,10 @@ def parse_payload(data):
     return data[:table_start], table, shape, warm_up                    # :221
 
 
-def decompress_arrays(key_plane, payload, predictor, timers=None):
-    """decompress.py:94-256,269 on arrays -> frames u8 [nt,H,W,3] (+ info dict)."""
+def decompress_arrays(key_plane, payload, predictor, timers=None, replay_preds=None):
+    """decompress.py:94-256,269 on arrays -> frames u8 [nt,H,W,3] (+ info dict).
+    replay_preds (f32 [nt,Hp,Wp,C]): use these as the regenerated predictions instead of calling the predictor
+    (golden-fixture tests: predictions recorded from the reference run)."""
     T = timers if timers is not None else {}
     tic = time.perf_counter
     body, table, shape, warm_up = parse_payload(payload)
@@ -312,20 +324,28 @@ def decompress_arrays(key_plane, payload, predictor, timers=None):
     t_pred = 0.0
     n_calls = 0
 
+    frame_of_call = []
+
     def pred(x):
         nonlocal t_pred, n_calls
         t0 = tic()
-        out = predictor.predict(x, 10)
+        if replay_preds is not None:
+            f = frame_of_call[-1]
+            out = np.stack([replay_preds[0], replay_preds[f]])[np.newaxis][:, :x.shape[1] if x.shape[1] == 1 else 2]
+        else:
+            out = predictor.predict(x, 10)
         t_pred += tic() - t0
         n_calls += 1
         return out
 
     result_list = []
+    frame_of_call.append(0)
     warm_up_frame = pred(X_test_pad[0, 0][np.newaxis, np.newaxis])      # :141-143 (one time step)
     for _ in range(warm_up):
         result_list.append(warm_up_frame)                               # :144-145
     for idx in range(warm_up, len(key_frame_check[warm_up:]) + warm_up - 1):   # :147
         for predict_idx in range(key_frame_check[idx], key_frame_check[idx + 1]):
+            frame_of_call.append(predict_idx)
             if predict_idx == key_frame_check[idx]:
                 one = X_test_pad[0, predict_idx][np.newaxis, np.newaxis]
                 pred(np.concatenate([one, np.zeros(one.shape)], axis=1))         # :150-154 (discarded)

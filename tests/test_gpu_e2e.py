@@ -52,7 +52,7 @@ def test_lossy_roundtrip_bounded(cuda_lib, mode, bound, maxerr):
         assert err.max() <= np.floor(rng.max() * bound[0]) + 1
     else:
         assert (err <= np.floor(frames.astype(float) * bound[0]) + 1).all()
-    if bound == [0.01]:
+    if mode == "abs" and bound == [0.01]:
         lossless = _roundtrip(net, frames, 0, 4, None, "abs", [0.0])[1]
         assert np.array_equal(payload, lossless)          # abs 0.01 == lossless stream
     net.close()

@@ -1,0 +1,162 @@
+"""Host-side logic of tezip_b200 (no GPU): schedules, payload format, LUTs, container, CLI grammar, C ABI exports."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import codec_oracle as co
+from tezip_b200 import codec, container, ops, dist as tzdist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _ToyNet:
+    """predictor with the oracle's interface whose 'prediction' is a cheap function of the input"""
+    def predict(self, x, batch_size=None):
+        x = np.asarray(x, np.float32)
+        out = np.empty_like(x)
+        out[:, 0] = 0.25
+        if x.shape[1] > 1:
+            out[:, 1] = np.clip(0.9 * x[:, 0] + 0.02, 0, 1)
+        return out
+
+
+@pytest.mark.parametrize("nt,p,window", [(12, 0, 5), (12, 2, 5), (11, 0, 5), (25, 3, 10), (7, 0, 1), (9, 1, 20)])
+def test_swp_schedule_matches_oracle(nt, p, window):
+    frames = np.random.default_rng(0).integers(1, 256, (nt, 8, 8, 3), dtype=np.uint8)
+    r = co.compress_arrays(frames, _ToyNet(), p, window, None, "abs", [0.0], True)
+    keys = codec.swp_keys(nt, p, window)
+    assert keys == r["keys"]
+    plan = codec.plan_from_keys(nt, p, keys)
+    real = [w for w in r["windows"] if not (p and w[0] == 0)]
+    assert plan.windows == real
+    # every non-key frame gets exactly one slot; window starts get -1; warm-up frames 1..p-1 use P0 (slot 0)
+    assert (plan.pred_slot[[w[0] for w in real]] == -1).all()
+    used = plan.pred_slot[plan.pred_slot > 0]
+    assert len(set(used.tolist())) == len(used) == nt - len(keys) and plan.n_slots == len(used) + 1
+    if p > 1:
+        assert (plan.pred_slot[1:p] == 0).all()
+    assert plan.apply_eb.sum() == nt - len(keys)
+    # lock-step: step k advances every window longer than k, from a contiguous prefix
+    for k, (kidx, slot0, B) in enumerate(plan.steps, start=1):
+        assert B == sum(1 for w in real if w[1] > k)
+    with pytest.raises(Exception):
+        codec.swp_keys(p + 1, p, window)
+
+
+def test_payload_pack_parse_matches_oracle():
+    frames = np.random.default_rng(1).integers(1, 256, (9, 8, 8, 3), dtype=np.uint8)
+    for entropy in (True, False):
+        r = co.compress_arrays(frames, _ToyNet(), 1, 4, None, "abs", [1.0], entropy)
+        body, table, shape, p = codec.parse_payload(r["payload"])
+        b2, t2, s2, p2 = co.parse_payload(r["payload"])
+        assert np.array_equal(body, b2) and shape == s2 == (1, 9, 8, 8, 3) and p == p2 == 1
+        assert (table is None) == (t2 is None) == (not entropy)
+        if entropy:
+            assert np.array_equal(table, t2)
+        assert np.array_equal(codec.pack_payload(body, table, shape, p), r["payload"])
+
+
+def test_luts_match_reference_replacing():
+    rng = np.random.default_rng(2)
+    y = rng.integers(-40, 41, 5000).astype(np.int16)
+    s = (1600 - y).astype(np.int16)
+    hist = np.bincount(s, minlength=4096)
+    table = ops.build_table(hist)
+    assert np.array_equal(table, co.build_table(s))
+    enc = ops.encode_lut(table)[s]
+    assert np.array_equal(enc, co.replacing_encode(s, table))
+    dec = ops.decode_lut(table)[enc]
+    assert np.array_equal(dec, co.replacing_decode(enc, table)) and np.array_equal(dec, s)
+    # a colliding table (symbols inside the rank range) goes through the same sequential where() passes
+    t2 = np.array([3, 1, 0, 2], np.int16)
+    arr = np.array([0, 1, 2, 3, 7], np.int16)
+    assert np.array_equal(ops.encode_lut(t2)[arr], co.replacing_encode(arr, t2))
+    assert np.array_equal(ops.decode_lut(t2)[arr], co.replacing_decode(arr, t2))
+
+
+def test_container_roundtrip(tmp_path):
+    rng = np.random.default_rng(3)
+    kp = rng.integers(0, 255, 3000, dtype=np.uint8)
+    payload = rng.integers(-5, 2000, 4000).astype(np.int16)
+    for workers in (0, 2):
+        d = str(tmp_path / ("c%d" % workers))
+        container.write_container(d, ["a.png", "b.png"], True, kp, payload, workers=workers)
+        names, rgb, kp2, pl2 = container.read_container(d)
+        assert names == ["a.png", "b.png"] and rgb and np.array_equal(kp, kp2) and np.array_equal(payload, pl2)
+        # single zstd frame carrying its content size (what python-zstd's one-shot decompress needs)
+        from oracle import refharness as rh
+        raw = open(os.path.join(d, "entropy.dat"), "rb").read()
+        assert rh.zstd_decompress(raw) == payload.tobytes()
+        assert open(os.path.join(d, "filename.txt")).read() == "1\na.png\nb.png\n"
+
+
+def test_shard_ranges_cover_and_align():
+    for nt, p, w, world in ((1000, 0, 10, 8), (105, 2, 10, 4), (37, 0, 5, 2), (12, 1, 5, 8)):
+        rs = tzdist.shard_ranges(nt, p, w, world)
+        assert rs[0][0] == 0 and rs[-1][1] == nt
+        for (a, b), (c, d) in zip(rs, rs[1:]):
+            assert b == c
+        keys = set(codec.swp_keys(nt, p, w))
+        for r, (a, b) in enumerate(rs):
+            if r > 0 and b > a:
+                assert a in keys
+
+
+def _cli(*argv):
+    return subprocess.run([sys.executable, "-m", "tezip_b200.tezip", *argv], cwd=ROOT, capture_output=True, text=True)
+
+
+def test_cli_flag_grammar():
+    r = _cli("-c", "m", "i", "o", "-w", "5", "-m", "abs", "-b", "0")
+    assert "Please specify the -p or --preprocess option!" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-p", "0", "-m", "abs", "-b", "0")
+    assert "Please specify the window size(-w or --window) or MSE threshold(-t or --threshold) option!" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-p", "0", "-w", "5", "-t", "0.1", "-m", "abs", "-b", "0")
+    assert "Please select only one of window size" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-p", "0", "-w", "5", "-m", "xyz", "-b", "0")
+    assert "Please specify the -m or --mode correctly!" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-p", "0", "-w", "5", "-m", "absrel", "-b", "1")
+    assert "enter two in -b or --bound" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-u", "m", "i", "o")
+    assert "Please select only one of learn or compress or uncompress." in r.stdout
+    r = _cli()
+    assert "Please mode select!" in r.stdout
+    r = _cli("-c", "m", "i", "o", "-p", "0", "-w", "5", "-m", "abs", "-b", "0", "-f")
+    assert "not available" in r.stdout and r.returncode != 0
+    h = _cli("-h").stdout
+    for flag in ("-l", "-c", "-u", "-p", "-w", "-t", "-m", "-b", "-f", "-v", "-n"):
+        assert flag in h
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/tezip_b200.h declares; compute
+    entry points fail loudly (no CPU fallback)."""
+    import ctypes
+    from tezip_b200 import build, _lib
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "tezip_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(tz_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, "python binding lacks %s" % name
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.tz_abi_version() == 1
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.tz_device_count() < 0 and b"cuda" in lib.tz_last_error().lower()
+        cfg = _lib.PrednetConfig()
+        cfg.n_layers, cfg.Hp, cfg.Wp, cfg.max_batch = 2, 8, 8, 1
+        cfg.stack_sizes[0] = cfg.stack_sizes[1] = cfg.r_stack_sizes[0] = cfg.r_stack_sizes[1] = 3
+        n = 2 * (6 * 2 - 1)
+        ptrs = (ctypes.c_void_p * n)()
+        sizes = (ctypes.c_longlong * n)()
+        h = ctypes.c_void_p()
+        assert lib.tz_prednet_create(ctypes.byref(cfg), ptrs, sizes, n, ctypes.byref(h)) != 0
+        assert lib.tz_last_error()

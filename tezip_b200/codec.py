@@ -191,11 +191,13 @@ def pool_slots_upper_bound(nt):
 
 
 def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
-                  keep_x=False, has_prev=False, prev_x=0, hist_reduce=None):
+                  keep_x=False, comm=None):
     """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
 
-    hist_reduce: optional callable(hist_int64_device_tensor) -> None that sums the symbol histogram across
-    ranks in place (multi-GPU: every rank must derive the same table)."""
+    comm: optional shard communicator (tezip_b200/dist.py) when `frames` is one rank's window-aligned shard of a
+    longer sequence: comm.exchange_last_x(x_last) -> (has_prev, prev_x) supplies the one-element halo of the 1-D
+    delta (compress.py:75 crosses shard boundaries) and comm.reduce_hist(t) sums the symbol histogram across
+    ranks so that every rank derives the same table."""
     assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4
     nt, H, W, C = frames.shape
     dev = frames.device
@@ -215,11 +217,11 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
     return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
-                            has_prev, prev_x, hist_reduce)
+                            comm)
 
 
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
-                     keep_x=False, has_prev=False, prev_x=0, hist_reduce=None):
+                     keep_x=False, comm=None):
     """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map."""
     nt, H, W, C = frames.shape
     dev = frames.device
@@ -237,6 +239,13 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         if not lossless:
             ops.error_bound(frames, x, torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev), mode,
                             list(bound))                                                 # compress.py:315-319
+    has_prev, prev_x = False, 0
+    if comm is not None:
+        if x is not None:
+            x_last = int(x.view(-1)[-1].item())
+        else:   # lossless: the last residual straight from the last frame
+            x_last = int(ops.residual(frames[-1:], pool, pred_slot[-1:]).view(-1)[-1].item())
+        has_prev, prev_x = comm.exchange_last_x(x_last)
     if entropy:
         hist = torch.zeros(TZ_HIST_BINS, dtype=torch.int64, device=dev)
         ovf = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -245,9 +254,9 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         else:
             ops.encode_lossless(frames, pool, pred_slot, 0, hist=hist, overflow=ovf, has_prev=has_prev,
                                 prev_x=prev_x)
-        if hist_reduce is not None:
-            hist_reduce(hist)
-            hist_reduce(ovf)
+        if comm is not None:
+            comm.reduce_hist(hist)
+            comm.reduce_hist(ovf)
         hist_np = hist.cpu().numpy()
         if int(ovf.item()) != 0:
             raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "

@@ -648,27 +648,34 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   return TZ_OK;
 }
 
-int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st) {
+int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev) {
   TcState *T = h->tc;
   const int L = h->L;
+  int ne = 0;
+  if (ev) cudaEventRecord(ev[ne++], st);
   {
     const int C = h->S[0];
     long long total = (long long)B * h->H[0] * h->W[0] * C;
     e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], T->X[0], total,
                                                                  (long long)h->H[0] * h->W[0] * C, C, T->cx[0]);
     TZ_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[ne++], st);
   }
   for (int l = 0; l < L - 1; l++) {
     int rc = launch_conv(T, &T->aconv[l], B, st);
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[ne++], st);
   }
   for (int l = L - 1; l >= 0; l--) {
     int rc = launch_conv(T, &T->gconv[l], B, st);
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[ne++], st);
   }
   ConvSrc s = {T->r0, h->R[0], 0, 0, (long long)h->H[0] * h->W[0] * h->R[0]};
-  return conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,
-                        h->cfg.pixel_max, st);
+  int rc = conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,
+                          h->cfg.pixel_max, st);
+  if (ev) cudaEventRecord(ev[ne++], st);
+  return rc;
 }
 
 }  // namespace tz

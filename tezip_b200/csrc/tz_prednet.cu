@@ -435,6 +435,54 @@ int tz_prednet_next(tz_prednet *h, const float *in, float *out, int B, void *str
   return TZ_OK;
 }
 
+int tz_prednet_kernel_count(tz_prednet *h) {
+  if (!h) return 0;
+  return h->direct ? 0 : 2 * h->L + 1;   // e0, a_0..a_{L-2}, gates_{L-1}..gates_0, ahat_0
+}
+
+int tz_prednet_kernel_info(tz_prednet *h, int i, char *name, int name_len, double *flops_per_frame) {
+  TZ_REQUIRE(h && name && flops_per_frame && name_len > 0, "tz_prednet_kernel_info: null argument");
+  const int L = h->L, n = 2 * L + 1;
+  TZ_REQUIRE(!h->direct && i >= 0 && i < n, "tz_prednet_kernel_info: no kernel %d", i);
+  double fl = 0.0;
+  if (i == 0) {
+    snprintf(name, name_len, "e0");
+  } else if (i <= L - 1) {
+    int l = i - 1;
+    snprintf(name, name_len, "conv_tc_a%d", l);
+    fl = 2.0 * h->H[l] * h->W[l] * 9.0 * 2 * h->S[l] * h->S[l + 1];
+  } else if (i <= 2 * L - 1) {
+    int l = L - 1 - (i - L);
+    snprintf(name, name_len, "conv_tc_gates%d", l);
+    fl = 2.0 * h->H[l] * h->W[l] * 9.0 * h->cin_g[l] * 4 * h->R[l];
+  } else {
+    snprintf(name, name_len, "conv_direct_ahat0");
+    fl = 2.0 * h->H[0] * h->W[0] * 9.0 * h->R[0] * h->S[0];
+  }
+  *flops_per_frame = fl;
+  return TZ_OK;
+}
+
+int tz_prednet_next_timed(tz_prednet *h, const float *in, float *out, int B, void *stream, float *ms, int n_ms) {
+  TZ_REQUIRE(h && in && out && ms, "tz_prednet_next_timed: null argument");
+  TZ_REQUIRE(!h->direct, "tz_prednet_next_timed: tensor-core path only");
+  TZ_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "tz_prednet_next_timed: bad B");
+  const int n = 2 * h->L + 1;
+  TZ_REQUIRE(n_ms >= n, "tz_prednet_next_timed: need room for %d timings", n);
+  cudaEvent_t ev[2 * TZ_MAX_LAYERS + 2];
+  for (int i = 0; i <= n; i++) TZ_CHECK_CUDA(cudaEventCreate(&ev[i]));
+  int rc = tc_next(h, in, out, B, (cudaStream_t)stream, ev);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (rc == TZ_OK && e == cudaSuccess)
+    for (int i = 0; i < n; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+  for (int i = 0; i <= n; i++) cudaEventDestroy(ev[i]);
+  if (e != cudaSuccess) {
+    set_error("tz_prednet_next_timed: %s", cudaGetErrorString(e));
+    return TZ_ECUDA;
+  }
+  return rc;
+}
+
 long long tz_prednet_device_bytes(tz_prednet *h) { return h ? h->dev_bytes : 0; }
 
 double tz_prednet_flops_per_frame(tz_prednet *h) {

@@ -59,6 +59,6 @@ int lstm_direct(const float *pre, const float *c_prev, float *r_out, float *c_ou
 // tensor-core path (tz_conv_tc.cu)
 int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &w_host);
 void tc_destroy(tz_prednet *h);
-int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st);
+int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev = nullptr);
 
 }  // namespace tz

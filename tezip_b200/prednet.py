@@ -148,6 +148,25 @@ class PredNet:
                    "tz_prednet_next")
         return out
 
+    def kernels(self):
+        """[(name, algorithmic FLOPs per frame)] of the launches inside one next()."""
+        out = []
+        for i in range(self._lib.tz_prednet_kernel_count(self._h)):
+            name = ctypes.create_string_buffer(64)
+            fl = ctypes.c_double()
+            _lib.check(self._lib.tz_prednet_kernel_info(self._h, i, name, 64, ctypes.byref(fl)), "tz_prednet_kernel_info")
+            out.append((name.value.decode(), fl.value))
+        return out
+
+    def next_timed(self, x, out):
+        """One next() with CUDA events between its launches -> per-kernel device ms (synchronous)."""
+        n = self._lib.tz_prednet_kernel_count(self._h)
+        ms = (ctypes.c_float * n)()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.tz_prednet_next_timed(self._h, _lib.ptr(x), _lib.ptr(out), x.shape[0], ctypes.c_void_p(st),
+                                                   ms, n), "tz_prednet_next_timed")
+        return list(ms)
+
     def flops_per_frame(self):
         return float(self._lib.tz_prednet_flops_per_frame(self._h))
 
