@@ -127,18 +127,144 @@ __global__ void __launch_bounds__(256) residual_kernel(const uint8_t *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------ error_bound
-// compress.py:23-70: greedy interval-intersection scan, one thread per (frame, channel) plane, IEEE double
-// with explicit _rn intrinsics so that nothing is contracted into an FMA (NumPy evaluates E, d+E, d-E and
-// (u+l)/2 as separately rounded operations).
-__global__ void __launch_bounds__(32) error_bound_kernel(const uint8_t *__restrict__ frames,
-                                                         int16_t *__restrict__ x,
-                                                         const uint8_t *__restrict__ apply, long long nt, Geo g,
-                                                         int mode, double b0, double b1) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// compress.py:23-70: greedy interval-intersection scan.  The reference walks one plane serially: it keeps the
+// running intersection [l, u] of the intervals [d_i - E_i, d_i + E_i]; when element i would empty it
+// (min(u, Du_i) - max(l, Dl_i) < 0) the open segment [head, i) is flushed with trunc((u+l)/2) and a new segment
+// starts at i.  Here ONE WARP owns a plane and consumes it 32 elements at a time:
+//   A. an inclusive prefix min/max (shuffles), seeded with the carried (u, l), finds where the open segment ends
+//      inside the chunk (or absorbs the whole chunk);
+//   B. every lane s finds, for a segment that would start at s, the first lane that breaks it (forward walk
+//      with shuffles; segments are short, and the walk stops as soon as all lanes are done);
+//   C. lane 0's view chases those links from the first break, closing segments until one stays open.
+// Identical arithmetic to the reference: IEEE double with explicit _rn intrinsics (nothing is contracted into an
+// FMA; NumPy rounds E, d+E, d-E and (u+l)/2 separately).  VAL = int is the exact shortcut for a plane-wide bound
+// (abs / rel / absrel): with d integer, min_i fl(d_i+E) = fl(dmin+E) and max_i fl(d_i-E) = fl(dmax-E), so the
+// emptiness test depends only on the integer gap dmax - dmin; it equals gap > floor(2E) whenever the additions
+// are exact (E a multiple of 2^-36 below 4096) or 2E is at least 1e-6 from an integer (rounding is ~1e-13).
+struct EbInt {   // running (min d, max d)
+  int a, b;
+  __device__ static EbInt empty() { return {2147483647, -2147483647 - 1}; }
+  __device__ static EbInt of(int d, double, bool in) { return in ? EbInt{d, d} : empty(); }
+  __device__ EbInt join(const EbInt &o) const { return {min(a, o.a), max(b, o.b)}; }
+  __device__ bool broken(int G) const { return (long long)b - (long long)a > (long long)G; }
+  __device__ double mid(double E) const {   // (fl(dmin+E) + fl(dmax-E)) / 2, compress.py:61
+    return __dmul_rn(__dadd_rn(__dadd_rn((double)a, E), __dsub_rn((double)b, E)), 0.5);
+  }
+  __device__ EbInt shfl(int src) const { return {__shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src)}; }
+  __device__ EbInt shfl_up(int o) const { return {__shfl_up_sync(0xffffffffu, a, o), __shfl_up_sync(0xffffffffu, b, o)}; }
+};
+struct EbDbl {   // running (u = min Du, l = max Dl)
+  double u, l;
+  __device__ static EbDbl empty() {
+    return {__longlong_as_double(0x7ff0000000000000LL), __longlong_as_double(0xfff0000000000000LL)};
+  }
+  __device__ static EbDbl of(int d, double e, bool in) {
+    return in ? EbDbl{__dadd_rn((double)d, e), __dsub_rn((double)d, e)} : empty();   // compress.py:47-48
+  }
+  __device__ EbDbl join(const EbDbl &o) const { return {(o.u < u) ? o.u : u, (o.l > l) ? o.l : l}; }
+  __device__ bool broken(int) const { return __dsub_rn(u, l) < 0.0; }                 // compress.py:60
+  __device__ double mid(double) const { return __dmul_rn(__dadd_rn(u, l), 0.5); }     // compress.py:61
+  __device__ EbDbl shfl(int src) const { return {__shfl_sync(0xffffffffu, u, src), __shfl_sync(0xffffffffu, l, src)}; }
+  __device__ EbDbl shfl_up(int o) const { return {__shfl_up_sync(0xffffffffu, u, o), __shfl_up_sync(0xffffffffu, l, o)}; }
+};
+
+template <typename VAL>
+__device__ __forceinline__ void eb_plane_warp(const uint8_t *__restrict__ o, int16_t *__restrict__ d, int n, int C,
+                                              bool pwrel, double b0, double E, int G) {
+  const int lane = threadIdx.x & 31;
+  VAL carry = VAL::empty();   // state of the open segment [head, ...)
+  int head = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool in = i < n;
+    const int dv = in ? (int)d[(long long)i * C] : 0;
+    const double e = pwrel ? __dmul_rn((double)(in ? (int)o[(long long)i * C] : 0), b0) : E;   // compress.py:45
+    const VAL mine = VAL::of(dv, e, in);
+    // ---- A: where does the carried segment end?
+    VAL pre = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      VAL t = pre.shfl_up(off);
+      if (lane >= off) pre = pre.join(t);
+    }
+    pre = pre.join(carry);
+    const unsigned m = __ballot_sync(0xffffffffu, in && pre.broken(G));
+    if (m == 0) {   // the whole chunk joins the open segment
+      carry = pre.shfl(31);
+      continue;
+    }
+    const int b = __ffs(m) - 1;
+    {
+      const VAL seg = (b > 0) ? pre.shfl(b - 1) : carry;
+      const int16_t q = (int16_t)(long long)seg.mid(E);               // float -> int64 slice assignment truncates
+      for (int j = head + lane; j < base; j += 32) d[(long long)j * C] = q;   // part of the segment behind this chunk
+      if (lane < b && head <= i) d[(long long)i * C] = q;
+    }
+    // ---- B: for a segment starting at lane s, the first lane that breaks it (32 = still open at chunk end)
+    VAL run = mine;
+    int nb = 32;
+    bool done = !in;
+    for (int k = 1; k < 32; k++) {
+      const int t = lane + k;
+      const VAL vt = mine.shfl(t & 31);
+      const int tin_i = __shfl_sync(0xffffffffu, (int)in, t & 31);   // executed by every lane: no short-circuit
+      const bool tin = (t < 32) && (tin_i != 0);
+      if (!done) {
+        if (!tin) {
+          done = true;
+        } else {
+          const VAL nx = run.join(vt);
+          if (nx.broken(G)) {
+            done = true;
+            nb = t;
+          } else {
+            run = nx;
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+    // ---- C: chase the links from lane b
+    int cur = b;
+    int16_t myq = 0;
+    bool have = false;
+    for (int guard = 0;; guard++) {
+      if (guard > 40) {   // cannot happen (links strictly increase); never hang the GPU on a logic error
+        if (lane == 0) printf("tezip_b200: error_bound link chase did not terminate (base %d cur %d)\n", base, cur);
+        __trap();
+      }
+      const int nxt = __shfl_sync(0xffffffffu, nb, cur);
+      const VAL seg = run.shfl(cur);
+      if (nxt >= 32) {   // stays open: becomes the carried segment
+        carry = seg;
+        head = base + cur;
+        break;
+      }
+      const int16_t q = (int16_t)(long long)seg.mid(E);
+      if (lane >= cur && lane < nxt) {
+        myq = q;
+        have = true;
+      }
+      cur = nxt;
+    }
+    if (have) d[(long long)i * C] = myq;
+  }
+  if (head < n) {   // compress.py:67
+    const int16_t q = (int16_t)(long long)carry.mid(E);
+    for (int j = head + lane; j < n; j += 32) d[(long long)j * C] = q;
+  }
+}
+
+__global__ void __launch_bounds__(128) error_bound_kernel(const uint8_t *__restrict__ frames,
+                                                          int16_t *__restrict__ x,
+                                                          const uint8_t *__restrict__ apply, long long nt, Geo g,
+                                                          int mode, double b0, double b1) {
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per (frame, channel)
   if (t >= nt * g.C) return;
-  long long f = t / g.C;
-  int c = (int)(t - f * g.C);
+  const long long f = t / g.C;
+  const int c = (int)(t - f * g.C);
   if (!apply[f]) return;
+  const int lane = threadIdx.x & 31;
   const int n = g.H * g.W;
   const int C = g.C;
   const uint8_t *o = frames + f * g.frame_elems + c;
@@ -147,11 +273,16 @@ __global__ void __launch_bounds__(32) error_bound_kernel(const uint8_t *__restri
   if (mode == TZ_MODE_ABS) {
     E = fabs(b0);                                                        // :29
   } else if (mode == TZ_MODE_REL || mode == TZ_MODE_ABSREL) {
-    int mx = o[0], mn = o[0];                                            // :31-32 / :36-37
-    for (int i = 1; i < n; i++) {
+    int mx = 0, mn = 255;                                                // :31-32 / :36-37
+    for (int i = lane; i < n; i += 32) {
       int v = o[(long long)i * C];
       mx = max(mx, v);
       mn = min(mn, v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
     }
     if (mode == TZ_MODE_REL) {
       E = __dmul_rn((double)(mx - mn), b0);                              // :33
@@ -160,33 +291,18 @@ __global__ void __launch_bounds__(32) error_bound_kernel(const uint8_t *__restri
       E = (a < r) ? a : r;                                               // :40-43
     }
   }
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  double u = INF, l = -INF;                                              // :55-56
-  int head = 0;
-  for (int i = 0; i < n; i++) {                                          // :58
-    double di = (double)d[(long long)i * C];
-    double e = (mode == TZ_MODE_PWREL) ? __dmul_rn((double)o[(long long)i * C], b0) : E;   // :45
-    double Du = __dadd_rn(di, e);                                        // :47
-    double Dl = __dsub_rn(di, e);                                        // :48
-    double mnu = (Du < u) ? Du : u;
-    double mxl = (Dl > l) ? Dl : l;
-    if (__dsub_rn(mnu, mxl) < 0.0) {                                     // :60
-      if (head < i) {
-        double mid = __dmul_rn(__dadd_rn(u, l), 0.5);                    // :61 (u+l)/2, exact halving
-        int16_t q = (int16_t)(long long)mid;                             // int64 slice assignment truncates
-        for (int j = head; j < i; j++) d[(long long)j * C] = q;
-      }
-      u = INF; l = -INF;                                                 // :62-63
-      head = i;                                                          // :64
+  if (mode != TZ_MODE_PWREL) {
+    const double twoE = E + E;
+    const double sc = E * 68719476736.0;   // 2^36
+    const bool exact = (E < 4096.0) && (sc == floor(sc));
+    const bool clear = fabs(twoE - rint(twoE)) > 1e-6;
+    if (E >= 0.0 && (exact || clear)) {
+      const int G = twoE >= 70000.0 ? 70000 : (int)floor(twoE);
+      eb_plane_warp<EbInt>(o, d, n, C, false, b0, E, G);
+      return;
     }
-    if (Du < u) u = Du;                                                  // :65
-    if (l < Dl) l = Dl;                                                  // :66
   }
-  if (head < n) {
-    double mid = __dmul_rn(__dadd_rn(u, l), 0.5);                        // :67
-    int16_t q = (int16_t)(long long)mid;
-    for (int j = head; j < n; j++) d[(long long)j * C] = q;
-  }
+  eb_plane_warp<EbDbl>(o, d, n, C, mode == TZ_MODE_PWREL, b0, E, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ delta + histogram
@@ -621,8 +737,8 @@ int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long
   if (nt == 0) return TZ_OK;
   Geo g = make_geo(H, W, C, H, W);
   long long planes = nt * C;
-  const int threads = 32;
-  long long blocks = (planes + threads - 1) / threads;
+  const int threads = 128;   // 4 warps = 4 planes per block
+  long long blocks = (planes * 32 + threads - 1) / threads;
   error_bound_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode, b0, b1);
   TZ_CHECK_LAUNCH();
   return TZ_OK;

@@ -126,7 +126,9 @@ struct ConvArgs {
   __half *xe_out;                // X_{l+1}: [B, H/2, W/2, xe_cstride], e written at channels [0, 2*S_next)
   int xe_cstride, S_next;
   // --- R epilogue (LSTM)
-  const float *bm;               // [H, W, 4R]
+  const float *bm;               // [H, W, 4R];  when bm_packed: [H, W, R/8, 4 gates, 8] (one 128-byte line per
+                                 // thread and 8-channel chunk -> eight 16-byte loads of one cache line)
+  int bm_packed;
   const float *c0;               // [H, W, R]
   int R, NC, NCp;                // channels, channels per N tile, gate-block column pitch (NC rounded up to 8)
   __half *xr_out;                // X_{l-1}: [B, 2H, 2W, xr_cstride], r written up-sampled at channel xr_coff
@@ -136,6 +138,12 @@ struct ConvArgs {
 
 __device__ __forceinline__ float hsig(float x) {
   return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.0f), 1.0f);
+}
+// tanh(x) = 1 - 2/(exp(2x)+1) on the SFU (ex2.approx + rcp.approx): absolute error ~1e-7, far below the fp16
+// operand rounding of the convolutions, saturates correctly to +-1, and is deterministic on a given GPU.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -310,17 +318,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_ld_wait();
           if (valid) {
             float r[8];
+            if (P.bm_packed) {
+              const float4 *bp = reinterpret_cast<const float4 *>(P.bm + (pix * (P.R >> 3) + ((nt * P.NC + j0) >> 3)) * 32);
+              const float4 *cp = reinterpret_cast<const float4 *>(c0 + j0);
+              float bq[32], cq[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              if (j0 + j < P.NC) {
-                const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
-                const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
-                const float gc = tanhf(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
-                const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
-                const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
-                r[j] = __fmul_rn(go, tanhf(c));
-              } else {
-                r[j] = 0.0f;
+              for (int q = 0; q < 8; q++) {
+                const float4 t = bp[q];
+                bq[4 * q] = t.x; bq[4 * q + 1] = t.y; bq[4 * q + 2] = t.z; bq[4 * q + 3] = t.w;
+              }
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const float4 t = cp[q];
+                cq[4 * q] = t.x; cq[4 * q + 1] = t.y; cq[4 * q + 2] = t.z; cq[4 * q + 3] = t.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float gi = hsig(__fadd_rn(vi[j], bq[j]));
+                const float gf = hsig(__fadd_rn(vf[j], bq[8 + j]));
+                const float gc = fast_tanh(__fadd_rn(vc[j], bq[16 + j]));
+                const float go = hsig(__fadd_rn(vo[j], bq[24 + j]));
+                const float c = __fadd_rn(__fmul_rn(gf, cq[j]), __fmul_rn(gi, gc));
+                r[j] = __fmul_rn(go, fast_tanh(c));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                if (j0 + j < P.NC) {
+                  const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
+                  const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
+                  const float gc = fast_tanh(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
+                  const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
+                  const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
+                  r[j] = __fmul_rn(go, fast_tanh(c));
+                } else {
+                  r[j] = 0.0f;
+                }
               }
             }
             const int ch0 = nt * P.NC + j0;
@@ -377,6 +410,19 @@ __global__ void __launch_bounds__(256) e0_tc_kernel(const float *__restrict__ in
   x0[pix * cstride + C + c] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
 }
 
+// BM [H*W, 4 gates, R] -> [H*W, R/8, 4 gates, 8]
+__global__ void pack_bm_kernel(const float *__restrict__ src, float *__restrict__ dst, long long npix, int R) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * 4 * R) return;
+  int j = (int)(i & 7);
+  long long t = i >> 3;
+  int g = (int)(t & 3);
+  t >>= 2;
+  int q = (int)(t % (R >> 3));
+  long long pix = t / (R >> 3);
+  dst[i] = src[(pix * 4 + g) * R + q * 8 + j];
+}
+
 __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(src[i]);
@@ -397,6 +443,7 @@ struct TcState {
   int L;
   __half *X[TZ_MAX_LAYERS];   // X_l: [maxB, H_l, W_l, cx[l]] fp16: [e_l | up(r_{l+1}) | zero pad]
   int cx[TZ_MAX_LAYERS];
+  int epad[TZ_MAX_LAYERS];    // channel offset of the up(r_{l+1}) block: 2*S_l rounded up to 8 (16-byte stores)
   float *r0;                  // [maxB, H_0, W_0, R_0] fp32
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
@@ -448,9 +495,12 @@ static void pick_tile(int H, int W, bool pool, int *tw_log, int *th_log, int *tb
     }
 }
 
-static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx, int cin_real /*channels read*/,
-                     const std::vector<float> &wsrc /*fp32 [3][3][cin_w][cout_w]*/, int cin_w, int cin_ofs, int cout_w,
+// cmap[i] = input-channel row of the fp32 kernel that multiplies channel i of the activation buffer X (-1: none,
+// the packed weight is zero).  The conv reads channels [0, round_up(cmap.size(), 16)) of X.
+static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx, const std::vector<int> &cmap,
+                     const std::vector<float> &wsrc /*fp32 [3][3][cin_w][cout_w]*/, int cin_w, int cout_w,
                      int n_real /*output channels or R*/) {
+  const int cin_real = (int)cmap.size();
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -506,7 +556,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       float *dst = wp.data() + (size_t)(nt * A.n_tile + r) * Ktot;
       for (int tap = 0; tap < 9; tap++)
         for (int ci = 0; ci < cin_real; ci++)
-          dst[tap * A.cin_pad + ci] = wsrc[((size_t)tap * cin_w + cin_ofs + ci) * cout_w + src_col];
+          if (cmap[ci] >= 0) dst[tap * A.cin_pad + ci] = wsrc[((size_t)tap * cin_w + cmap[ci]) * cout_w + src_col];
     }
   float *tmp = nullptr;
   TZ_CHECK_CUDA(cudaMalloc(&tmp, wp.size() * sizeof(float)));
@@ -583,7 +633,8 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   const int mb = h->cfg.max_batch;
   for (int l = 0; l < L; l++) {
     TZ_REQUIRE(h->H[l] % 2 == 0 || l == L - 1, "tensor-core path: odd layer height");
-    T->cx[l] = round_up(2 * h->S[l] + (l < L - 1 ? h->R[l + 1] : 0), 16);
+    T->epad[l] = round_up(2 * h->S[l], 8);
+    T->cx[l] = round_up(T->epad[l] + (l < L - 1 ? h->R[l + 1] : 0), 16);
     size_t bytes = (size_t)mb * h->H[l] * h->W[l] * T->cx[l] * sizeof(__half);
     T->X[l] = (__half *)dev_alloc(h, bytes);
     if (!T->X[l]) return TZ_ENOMEM;
@@ -596,17 +647,31 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
 
   for (int l = 0; l < L; l++) {
     // gate conv: reads all of X_l = [e_l | up(r_{l+1})]; the r_{t-1} slice of the kernel is hoisted into BM_l
-    const int cin_real = 2 * h->S[l] + (l < L - 1 ? h->R[l + 1] : 0);
-    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], cin_real, wg_host[l], h->cin_g[l], h->R[l],
-                       4 * h->R[l], h->R[l]);
+    std::vector<int> gmap(T->epad[l] + (l < L - 1 ? h->R[l + 1] : 0), -1);
+    for (int i = 0; i < 2 * h->S[l]; i++) gmap[i] = h->R[l] + i;                                  // e_l
+    if (l < L - 1)
+      for (int i = 0; i < h->R[l + 1]; i++) gmap[T->epad[l] + i] = h->R[l] + 2 * h->S[l] + i;    // up(r_{l+1})
+    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l],
+                       h->R[l]);
     if (rc) return rc;
     ConvArgs &G = T->gconv[l].args;
     G.bm = h->BM[l];
+    G.bm_packed = 0;
     G.c0 = h->C0[l];
+    if (G.NC % 8 == 0 && h->R[l] % 8 == 0) {
+      const long long npix = (long long)h->H[l] * h->W[l];
+      float *bp = (float *)dev_alloc(h, (size_t)npix * 4 * h->R[l] * sizeof(float));
+      if (!bp) return TZ_ENOMEM;
+      const long long n = npix * 4 * h->R[l];
+      pack_bm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(h->BM[l], bp, npix, h->R[l]);
+      TZ_CHECK_CUDA(cudaDeviceSynchronize());
+      G.bm = bp;
+      G.bm_packed = 1;
+    }
     if (l > 0) {
       G.xr_out = T->X[l - 1];
       G.xr_cstride = T->cx[l - 1];
-      G.xr_coff = 2 * h->S[l - 1];
+      G.xr_coff = T->epad[l - 1];
     } else {
       G.xr_out = nullptr;
       G.r0_out = T->r0;
@@ -615,8 +680,9 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       // a conv: reads channels [0, 2S_l) of X_l
       std::vector<float> wa((size_t)9 * 2 * h->S[l] * h->S[l + 1]);
       TZ_CHECK_CUDA(cudaMemcpy(wa.data(), h->w_a[l], wa.size() * sizeof(float), cudaMemcpyDeviceToHost));
-      rc = make_conv(h, &T->aconv[l], 0, l, T->X[l], T->cx[l], 2 * h->S[l], wa, 2 * h->S[l], 0, h->S[l + 1],
-                     h->S[l + 1]);
+      std::vector<int> amap(2 * h->S[l]);
+      for (int i = 0; i < 2 * h->S[l]; i++) amap[i] = i;
+      rc = make_conv(h, &T->aconv[l], 0, l, T->X[l], T->cx[l], amap, wa, 2 * h->S[l], h->S[l + 1], h->S[l + 1]);
       if (rc) return rc;
       ConvArgs &Aa = T->aconv[l].args;
       Aa.bias = h->b_a[l];
