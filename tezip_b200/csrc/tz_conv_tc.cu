@@ -3,13 +3,14 @@
 // One persistent, warp-specialised kernel serves every 3x3 convolution of `next()` (prednet.py:255-258,290):
 //   M = 128 output pixels (a TB x TH x TW patch of the NHWC activation tensor), N = up to 256 output channels,
 //   K = 9 taps x Cin, walked tap-major in blocks of KC channels.
-//   warp 4  : TMA producer.  The A operand of tap (dy,dx) is the SAME 4-D box of the fp16 activation tensor
+//   warp 0  : TMA producer.  The A operand of tap (dy,dx) is the SAME 4-D box of the fp16 activation tensor
 //             shifted by (dy-1, dx-1); TMA zero-fills out-of-bounds rows/columns, which is exactly Keras'
 //             'same' padding, so no im2col buffer exists anywhere.  The B operand is a [N_tile x KC] box of the
 //             pre-packed K-major weight matrix.  Both land in 128B/64B/32B-swizzled shared memory.
-//   warp 5  : allocates TMEM and issues tcgen05.mma (M128 x N x K16, fp16 x fp16 -> fp32 in TMEM) from one
+//   warp 1  : allocates TMEM and issues tcgen05.mma (M128 x N x K16, fp16 x fp16 -> fp32 in TMEM) from one
 //             elected lane; tcgen05.commit releases smem stages / publishes the accumulator.
-//   warps 0-3: epilogue.  tcgen05.ld the accumulator rows (one pixel per thread) and finish the layer in
+//   warps 4..: epilogue (4, 8 or 12 warps; warp w reads TMEM lane quadrant w % 4 and every (EW/4)-th 8-channel
+//             chunk).  tcgen05.ld the accumulator rows (one pixel per thread) and finish the layer in
 //             registers: bias + relu + 2x2 max-pool + error units (A path, prednet.py:274-277,290-291), or
 //             bias-map + hard-sigmoid/tanh LSTM cell (R path, prednet.py:255-259) with the nearest-neighbour
 //             up-sampling (prednet.py:263-264) folded into the store.  Two TMEM accumulator stages overlap the
@@ -19,6 +20,7 @@
 #include "tz_prednet.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace tz {
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float v[8]) {
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernel arguments
-constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_THREADS = 512;   // 4 role warps (producer, MMA, 2 idle) + up to 12 epilogue warps
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
 constexpr int TC_TMEM_COLS = 512;
@@ -117,6 +119,9 @@ struct ConvArgs {
   int KC, cin_pad;               // channels per K block, kchunks*KC
   int n_tile;                    // MMA N (multiple of 16)
   int stages;
+  int epi_warps;                 // 4, 8 or 12
+  int halo;                      // 1: halo + stationary-weights mode (see conv_tc_kernel)
+  uint32_t b_block, b_region;    // halo mode: bytes of one [n_tile x 64] weight block; bytes of all 9*kchunks blocks
   uint32_t a_stride, stage_stride, tx_bytes;
   uint32_t desc_hi;              // upper half of the smem matrix descriptor (SBO, version, swizzle)
   uint32_t idesc;
@@ -148,10 +153,10 @@ __device__ __forceinline__ float fast_tanh(float x) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int EPI>  // 0: A path (pool + E), 1: R path (LSTM)
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -161,6 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
   const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+  const uint32_t bfull = smem_u32(&bars[2 * TC_MAX_STAGES + 4]);   // halo mode: all weights have landed
 
   const int tiles_img = P.tiles_w * P.tiles_h;
   const int tiles_b = (P.B + (1 << P.tb_log) - 1) >> P.tb_log;
@@ -174,12 +180,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
+      mbar_init(tempty0 + 8 * a, (uint32_t)P.epi_warps);
     }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
@@ -190,9 +197,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 4) {
+  if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && P.halo) {
+      // Halo mode.  The whole weight matrix of this CTA's N tile stays resident in shared memory (loaded once);
+      // per tile and 64-channel chunk ONE box of (TH+2) x 16 pixels is fetched and all nine taps read it through
+      // shifted UMMA descriptors, instead of nine shifted boxes: ~4x less activation traffic, no weight re-reads.
+      if ((int)blockIdx.x < n_tiles) {
+        const int n0 = ((int)blockIdx.x % P.n_tiles_n) * P.n_tile;
+        mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * 128u);
+        for (int kb = 0; kb < kblocks; kb++)   // block kb = tap * kchunks + chunk
+          tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * 64, n0);
+      }
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int mt = t / P.n_tiles_n;
+        const int twi = mt % P.tiles_w;
+        mt /= P.tiles_w;
+        const int thi = mt % P.tiles_h;
+        const int tbi = mt / P.tiles_h;
+        const int w0 = twi << P.tw_log, h0 = thi << P.th_log, b0 = tbi << P.tb_log;
+        for (int ch = 0; ch < P.kchunks; ch++, it++) {
+          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t full = full0 + 8 * s;
+          mbar_expect_tx(full, P.tx_bytes);
+          tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, ch * 64, w0 - 1, h0 - 1, b0);
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int nt = t % P.n_tiles_n;
@@ -217,9 +250,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && P.halo) {
+      uint32_t it = 0, tc = 0;
+      if ((int)blockIdx.x < n_tiles) mbar_wait(bfull, 0);
+      tc_fence_after();
+      const uint64_t bhi = (uint64_t)P.desc_hi << 32;                       // weights: SBO = 1024, aligned blocks
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+        const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+        mbar_wait(tempty0 + 8 * a, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * TC_ACC_STRIDE;
+        for (int ch = 0; ch < P.kchunks; ch++, it++) {
+          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;      // halo tile: rows of 128 B, 16 per image row
+#pragma unroll 1
+          for (int tap = 0; tap < 9; tap++) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            // rows (th, tw) of the M tile = halo rows (th+dy)*16 + (tw+dx): 8-row groups 2048 B apart (SBO).  The
+            // start is 128*(16dy+dx) bytes past a 1024-aligned base; the 128B swizzle is a function of the absolute
+            // shared-memory address bits (what TMA wrote), so the descriptor base_offset stays 0 -- measured on
+            // B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
+            const uint32_t astart = sa + (uint32_t)(dy * 16 + dx) * 128u;
+            const uint64_t ahi = (uint64_t)((2048u >> 4) | (1u << 14) | (2u << 29)) << 32;
+            const uint64_t adesc = ahi | (uint64_t)(((astart >> 4) & 0x3FFFu) | (1u << 16));
+            const uint32_t sb = smem0 + (uint32_t)(tap * P.kchunks + ch) * P.b_block;
+            const uint64_t bdesc = bhi | (uint64_t)(((sb >> 4) & 0x3FFFu) | (1u << 16));
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (ch | tap | k) != 0);
+          }
+          tc_commit(empty0 + 8 * s);   // halo slot free once its 36 MMAs retire
+        }
+        tc_commit(tfull0 + 8 * a);
+      }
+    } else if (lane == 0) {
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
         const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
@@ -242,9 +310,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else {
-    // ===================================================================== epilogue (warps 0..3)
-    const int m = warp * 32 + lane;  // accumulator row == pixel inside the tile
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (warps 4 .. 4+epi_warps-1)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int part = (warp - 4) >> 2;          // which share of the 8-channel chunks
+    const int nparts = P.epi_warps >> 2;
+    const int m = quad * 32 + lane;            // accumulator row == pixel inside the tile
     const int tw = m & ((1 << P.tw_log) - 1);
     const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
     const int tb = m >> (P.tw_log + P.th_log);
@@ -261,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * TC_ACC_STRIDE;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * TC_ACC_STRIDE;
       if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
@@ -270,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float *ah = P.ahat_next + ((long long)(h >> 1) * Wo + (w >> 1)) * P.S_next;
         __half *dst = P.xe_out + opix * P.xe_cstride;
         const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
-        for (int j0 = 0; j0 < n_real; j0 += 8) {
+        for (int j0 = 8 * part; j0 < n_real; j0 += 8 * nparts) {
           float v[8];
           tc_ld8(trow + j0, v);
           tc_ld_wait();
@@ -309,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long pix = (long long)h * P.W + w;
         const float *bm = P.bm + pix * 4 * P.R + nt * P.NC;
         const float *c0 = P.c0 + pix * P.R + nt * P.NC;
-        for (int j0 = 0; j0 < P.NC; j0 += 8) {
+        for (int j0 = 8 * part; j0 < P.NC; j0 += 8 * nparts) {
           float vi[8], vf[8], vc[8], vo[8];
           tc_ld8(trow + 0 * P.NCp + j0, vi);
           tc_ld8(trow + 1 * P.NCp + j0, vf);
@@ -388,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
@@ -523,17 +594,52 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   A.kchunks = A.cin_pad / A.KC;
   A.ksteps = A.KC / 16;
   int rows_total;
+  int n_unit = 0;   // output channels (A path) or R channels (R path) per N tile
   if (epi == 1) {
     A.R = n_real;
-    A.NC = largest_divisor_le(n_real, 64);
+    n_unit = largest_divisor_le(n_real, 64);
+  } else {
+    n_unit = largest_divisor_le(n_real, 256);
+  }
+  // ---- halo + stationary-weights mode: small weight matrices only (they must fit in shared memory next to the
+  // halo tiles), image width a multiple of the 8-pixel tile width.
+  {
+    const char *env = getenv("TZ_HALO");
+    const bool want = !(env && env[0] == '0');
+    const int cin64 = round_up(cin_real, 64);
+    const uint32_t budget = 112u * 1024u;
+    if (want && cin64 <= cx && (A.W % 8) == 0) {
+      for (int split = 1; split <= 2; split++) {
+        if (n_real % split) continue;
+        const int unit = n_real / split;
+        if (epi == 1 && unit > 64) continue;
+        if (epi == 0 && split > 1 && (unit % 16) != 0) continue;
+        const int ntile = (epi == 1) ? round_up(4 * round_up(unit, 8), 16) : round_up(unit, 16);
+        if ((uint32_t)ntile * 9u * (uint32_t)cin64 * 2u > budget || ntile > 256) continue;
+        A.halo = 1;
+        n_unit = unit;
+        A.cin_pad = cin64;
+        A.KC = 64;
+        A.kchunks = cin64 / 64;
+        A.ksteps = 4;
+        A.tw_log = 3;
+        A.th_log = 4;
+        A.tb_log = 0;
+        A.tiles_w = (A.W + 7) >> 3;
+        A.tiles_h = (A.H + 15) >> 4;
+        break;
+      }
+    }
+  }
+  if (epi == 1) {
+    A.NC = n_unit;
     A.NCp = round_up(A.NC, 8);
     A.n_tile = round_up(4 * A.NCp, 16);
     A.n_tiles_n = n_real / A.NC;
   } else {
-    int nt = largest_divisor_le(n_real, 256);
-    A.n_tile = round_up(nt, 16);
-    A.n_tiles_n = n_real / nt;
-    if (A.n_tiles_n > 1 && (nt % 16) != 0) {
+    A.n_tile = round_up(n_unit, 16);
+    A.n_tiles_n = n_real / n_unit;
+    if (A.n_tiles_n > 1 && (n_unit % 16) != 0) {
       set_error("unsupported channel count %d for the tensor-core path", n_real);
       return TZ_EINVAL;
     }
@@ -587,6 +693,25 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   }
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
+  if (A.halo) {
+    A.b_block = (uint32_t)A.n_tile * 128u;
+    A.b_region = 9u * (uint32_t)A.kchunks * A.b_block;
+    A.a_stride = 0;
+    A.stage_stride = 16u * 18u * 128u;   // one halo tile: 18 image rows x 16 pixels x 64 channels (fp16)
+    A.tx_bytes = A.stage_stride;
+    stages = (int)((204u * 1024u - A.b_region) / A.stage_stride);
+    if (stages > 4) stages = 4;
+    if (stages < 2) {
+      set_error("internal: halo mode does not fit (weights %u bytes)", A.b_region);
+      return TZ_EINVAL;
+    }
+    A.stages = stages;
+    c->smem_bytes = A.b_region + (uint32_t)stages * A.stage_stride + 1024u;
+  }
+  {
+    const int nchunks = (epi == 1) ? (A.NC + 7) / 8 : (A.n_tile + 7) / 8;
+    A.epi_warps = nchunks >= 3 ? 12 : nchunks >= 2 ? 8 : 4;
+  }
   // ---- descriptors
   const CUtensorMapSwizzle swz = A.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : A.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -598,6 +723,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
     cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
     cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
+    if (A.halo) {   // (TH+2) rows of 16 pixels: pitch 16 keeps the 8-row groups 2048 B apart (swizzle-phase neutral)
+      box[1] = 16;
+      box[2] = 18;
+      box[3] = 1;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -706,10 +836,11 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   const int tiles_b = (B + (1 << A.tb_log) - 1) >> A.tb_log;
   long long n_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b * A.n_tiles_n;
   int grid = n_tiles < T->sm_count ? (int)n_tiles : T->sm_count;
+  if (A.halo) grid = grid / A.n_tiles_n * A.n_tiles_n;   // a CTA keeps one N tile: its weights stay in shared memory
   if (c->epi == 0)
-    conv_tc_kernel<0><<<grid, TC_THREADS, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    conv_tc_kernel<0><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   else
-    conv_tc_kernel<1><<<grid, TC_THREADS, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    conv_tc_kernel<1><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   TZ_CHECK_LAUNCH();
   return TZ_OK;
 }
