@@ -1,0 +1,70 @@
+"""Sharding on one GPU: encoding a sequence as window-aligned shards with the halo / histogram exchange
+(tezip_b200/dist.py protocol, emulated in-process) gives the same stream as encoding it in one piece, and every
+shard decodes independently."""
+import numpy as np
+import pytest
+
+from helpers import TINY, oracle_net, gpu_net
+from tezip_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+class _FakeComm:
+    """Runs the ranks one after the other: pass 1 records last_x / histograms, pass 2 replays the reductions."""
+    def __init__(self, world):
+        self.world, self.rank, self.phase = world, 0, 0
+        self.last_x = [0] * world
+        self.hists = {}
+        self.calls = 0
+
+    def exchange_last_x(self, x_last):
+        if self.phase == 0:
+            self.last_x[self.rank] = int(x_last)
+        return (self.rank > 0), (self.last_x[self.rank - 1] if self.rank > 0 else 0)
+
+    def reduce_hist(self, t):
+        key = self.calls
+        self.calls += 1
+        if self.phase == 0:
+            self.hists.setdefault(key, []).append(t.clone())
+        else:
+            t.copy_(sum(self.hists[key]))
+
+
+@pytest.mark.parametrize("mode,bound", [("abs", [0.0]), ("abs", [2.0])])
+def test_sharded_encode_equals_unsharded(cuda_lib, mode, bound):
+    import torch
+    from tezip_b200 import codec
+    from tezip_b200.dist import shard_ranges
+    stack, H, W, nt, Wn, world = TINY, 24, 40, 23, 4, 3
+    _o, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, 24, 40, max_batch=8)
+    frames = synth.make_frames(nt, H, W, 3, seed=31)
+    dev = torch.device("cuda", 0)
+    fr = torch.from_numpy(frames).to(dev)
+    whole = codec.encode_frames(fr, net, 0, Wn, None, mode, bound, True)
+    ranges = shard_ranges(nt, 0, Wn, world)
+    comm = _FakeComm(world)
+    encs = None
+    for phase in (0, 1):
+        comm.phase = phase
+        encs = []
+        for r, (a, b) in enumerate(ranges):
+            comm.rank, comm.calls = r, 0
+            encs.append(codec.encode_frames(fr[a:b].contiguous(), net, 0, Wn, None, mode, bound, True, comm=comm))
+    body = torch.cat([e.body for e in encs]).cpu().numpy()
+    assert all(np.array_equal(e.table, whole.table) for e in encs)
+    assert np.array_equal(body, whole.body.cpu().numpy())
+    assert np.array_equal(torch.cat([e.key_plane for e in encs]).cpu().numpy(), whole.key_plane.cpu().numpy())
+    # every shard decodes on its own: x restarts at 0 at its first (key) frame
+    outs = []
+    for r, ((a, b), e) in enumerate(zip(ranges, encs)):
+        out, _ = codec.decode_arrays(e.key_plane, e.body, e.table, e.shape, 0, net,
+                                     first_mode=0 if r == 0 else 1, first_x=0)
+        outs.append(out)
+    dec = torch.cat(outs).cpu().numpy()
+    if bound == [0.0]:
+        assert np.array_equal(dec, frames)
+    else:
+        assert np.abs(dec.astype(int) - frames.astype(int)).max() <= 2
