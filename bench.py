@@ -135,6 +135,7 @@ def run_reference(args):
         return
     from oracle import build as obuild
     obuild.build()
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     n = args.cpu_sample_frames
     ws = synth.make_weights(STACK, bias="uniform", seed=7)
     frames = synth.make_frames(n, H, W, C, seed=1)
@@ -343,6 +344,7 @@ def run_native(args):
         from oracle import build as obuild
         from tezip_b200 import container
         obuild.build()
+        torch.set_num_threads(os.cpu_count() or 1)
         ns = args.cpu_sample_frames
         t0 = time.perf_counter()
         r = cpu_port_run(frames_np[:ns], ws, Wn, mode, bound)

@@ -108,7 +108,7 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // ------------------------------------------------------------------------------------------------ kernel arguments
 constexpr int TC_MAX_THREADS = 512;   // 4 role warps (producer, MMA, 2 idle) + up to 12 epilogue warps
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
+constexpr int TC_MAX_ACC = 8;       // TMEM accumulator stages (2 for wide tiles, up to 8 for narrow ones)
 constexpr int TC_TMEM_COLS = 512;
 
 struct ConvArgs {
@@ -120,6 +120,10 @@ struct ConvArgs {
   int n_tile;                    // MMA N (multiple of 16)
   int stages;
   int epi_warps;                 // 4, 8 or 12
+  int epi_groups;                // 1: every epilogue warp works on every tile (8-channel chunks are shared out);
+                                 // G > 1: narrow tiles -- warp group g (4 warps) owns the tiles with index % G == g,
+                                 // so G epilogues are in flight and their latency overlaps
+  int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
   int halo;                      // 1: halo + stationary-weights mode (see conv_tc_kernel)
   uint32_t b_block, b_region;    // halo mode: bytes of one [n_tile x 64] weight block; bytes of all 9*kchunks blocks
   uint32_t a_stride, stage_stride, tx_bytes;
@@ -151,12 +155,35 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+// Halo mode: the 9 x KSTEPS MMAs of one channel chunk, fully unrolled.  One thread issues every tcgen05.mma of the
+// CTA, so for narrow tiles (N <= 64, where an MMA lasts only ~30-100 cycles) the issue loop itself is the
+// critical path: descriptors are formed with one 32-bit add each, no loop-carried integer division.
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+template <int KSTEPS>
+__device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t row16 /*row bytes >> 4*/,
+                                                 uint32_t b_tap_stride16, uint32_t idesc, bool first_chunk) {
+#pragma unroll
+  for (int tap = 0; tap < 9; tap++) {
+    const uint32_t al = a_lo + (uint32_t)((tap / 3) * 16 + (tap % 3)) * row16;
+    const uint32_t bl = b_lo + (uint32_t)tap * b_tap_stride16;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; k++)
+      tc_mma_f16(d_tmem, make_desc(al + 2 * k, a_hi), make_desc(bl + 2 * k, b_hi), idesc,
+                 (tap | k) != 0 || !first_chunk);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int EPI>  // 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 5];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -165,8 +192,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t full0 = smem_u32(&bars[0]);
   const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
-  const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
-  const uint32_t bfull = smem_u32(&bars[2 * TC_MAX_STAGES + 4]);   // halo mode: all weights have landed
+  const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + TC_MAX_ACC]);
+  const uint32_t bfull = smem_u32(&bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC]);   // halo mode: all weights have landed
 
   const int tiles_img = P.tiles_w * P.tiles_h;
   const int tiles_b = (P.B + (1 << P.tb_log) - 1) >> P.tb_log;
@@ -178,9 +205,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    for (int a = 0; a < 2; a++) {
+    for (int a = 0; a < P.acc_stages; a++) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, (uint32_t)P.epi_warps);
+      mbar_init(tempty0 + 8 * a, (uint32_t)(P.epi_groups > 1 ? 4 : P.epi_warps));
     }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,9 +232,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // shifted UMMA descriptors, instead of nine shifted boxes: ~4x less activation traffic, no weight re-reads.
       if ((int)blockIdx.x < n_tiles) {
         const int n0 = ((int)blockIdx.x % P.n_tiles_n) * P.n_tile;
-        mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * 128u);
+        mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * (uint32_t)(2 * P.KC));
         for (int kb = 0; kb < kblocks; kb++)   // block kb = tap * kchunks + chunk
-          tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * 64, n0);
+          tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * P.KC, n0);
       }
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -222,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const uint32_t full = full0 + 8 * s;
           mbar_expect_tx(full, P.tx_bytes);
-          tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, ch * 64, w0 - 1, h0 - 1, b0);
+          tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, ch * P.KC, w0 - 1, h0 - 1, b0);
         }
       }
     } else if (lane == 0) {
@@ -256,33 +283,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t it = 0, tc = 0;
       if ((int)blockIdx.x < n_tiles) mbar_wait(bfull, 0);
       tc_fence_after();
-      const uint64_t bhi = (uint64_t)P.desc_hi << 32;                       // weights: SBO = 1024, aligned blocks
+      const uint32_t rowb = 2u * (uint32_t)P.KC;                            // bytes per pixel row of a chunk
+      // halo tile: 16 pixels per image row -> the 8-row groups (one image row of the 8-wide tile) are 16*rowb apart;
+      // weights: dense 8-row groups in aligned blocks (P.desc_hi as is)
+      const uint32_t ahi32 = (((16u * rowb) >> 4) & 0x3FFFu) | (P.desc_hi & 0xFFFFC000u);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
-        const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+        const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * TC_ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
         for (int ch = 0; ch < P.kchunks; ch++, it++) {
           const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;      // halo tile: rows of 128 B, 16 per image row
-#pragma unroll 1
-          for (int tap = 0; tap < 9; tap++) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            // rows (th, tw) of the M tile = halo rows (th+dy)*16 + (tw+dx): 8-row groups 2048 B apart (SBO).  The
-            // start is 128*(16dy+dx) bytes past a 1024-aligned base; the 128B swizzle is a function of the absolute
-            // shared-memory address bits (what TMA wrote), so the descriptor base_offset stays 0 -- measured on
-            // B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
-            const uint32_t astart = sa + (uint32_t)(dy * 16 + dx) * 128u;
-            const uint64_t ahi = (uint64_t)((2048u >> 4) | (1u << 14) | (2u << 29)) << 32;
-            const uint64_t adesc = ahi | (uint64_t)(((astart >> 4) & 0x3FFFu) | (1u << 16));
-            const uint32_t sb = smem0 + (uint32_t)(tap * P.kchunks + ch) * P.b_block;
-            const uint64_t bdesc = bhi | (uint64_t)(((sb >> 4) & 0x3FFFu) | (1u << 16));
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (ch | tap | k) != 0);
-          }
+          const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
+          // rows (th, tw) of the M tile = halo rows (th+dy)*16 + (tw+dx): 8-row groups 16*rowb apart (SBO).  The
+          // tap's start is rowb*(16dy+dx) bytes past a 1024-aligned base; the swizzle is a function of the absolute
+          // shared-memory address bits (what TMA wrote), so the descriptor base_offset stays 0 -- measured on
+          // B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
+          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t b_lo = (((smem0 + (uint32_t)ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // block kb = tap * kchunks + chunk
+          if (P.ksteps == 4)
+            issue_halo_chunk<4>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
+          else if (P.ksteps == 2)
+            issue_halo_chunk<2>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
+          else
+            issue_halo_chunk<1>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
           tc_commit(empty0 + 8 * s);   // halo slot free once its 36 MMAs retire
         }
         tc_commit(tfull0 + 8 * a);
@@ -290,10 +317,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (lane == 0) {
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
-        const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+        const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * TC_ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
         for (int kb = 0; kb < kblocks; kb++, it++) {
           const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
           mbar_wait(full0 + 8 * s, ph);
@@ -302,8 +329,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t hi = (uint64_t)P.desc_hi << 32;
           const uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFFu) | (1u << 16));
           const uint64_t bdesc = hi | (uint64_t)((((sa + P.a_stride) >> 4) & 0x3FFFu) | (1u << 16));
-          for (int k = 0; k < P.ksteps; k++)  // advance 32 bytes (16 fp16 of K) inside the swizzled row
-            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+          // advance 32 bytes (16 fp16 of K) inside the swizzled row
+          if (P.ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+          } else {
+            for (int k = 0; k < P.ksteps; k++)
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+          }
           tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
         }
         tc_commit(tfull0 + 8 * a);    // accumulator complete
@@ -313,14 +347,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================================================================== epilogue (warps 4 .. 4+epi_warps-1)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int part = (warp - 4) >> 2;          // which share of the 8-channel chunks
-    const int nparts = P.epi_warps >> 2;
+    const int group = (warp - 4) >> 2;
+    const int part = P.epi_groups > 1 ? 0 : group;          // which share of the 8-channel chunks
+    const int nparts = P.epi_groups > 1 ? 1 : (P.epi_warps >> 2);
     const int m = quad * 32 + lane;            // accumulator row == pixel inside the tile
     const int tw = m & ((1 << P.tw_log) - 1);
     const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
     const int tb = m >> (P.tw_log + P.th_log);
     uint32_t tc = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+      if (P.epi_groups > 1 && (int)(tc % (uint32_t)P.epi_groups) != group) continue;   // another group's tile
       const int nt = t % P.n_tiles_n;
       int mt = t / P.n_tiles_n;
       const int twi = mt % P.tiles_w;
@@ -329,10 +365,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tbi = mt / P.tiles_h;
       const int w = (twi << P.tw_log) + tw, h = (thi << P.th_log) + th, b = (tbi << P.tb_log) + tb;
       const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
-      const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
+      const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * TC_ACC_STRIDE;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride;
       if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
@@ -606,7 +642,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   {
     const char *env = getenv("TZ_HALO");
     const bool want = !(env && env[0] == '0');
-    const int cin64 = round_up(cin_real, 64);
+    const int cin64 = A.cin_pad;            // channels read: cin rounded up to 16, walked in chunks of KC
     const uint32_t budget = 112u * 1024u;
     if (want && cin64 <= cx && (A.W % 8) == 0) {
       for (int split = 1; split <= 2; split++) {
@@ -618,10 +654,6 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         if ((uint32_t)ntile * 9u * (uint32_t)cin64 * 2u > budget || ntile > 256) continue;
         A.halo = 1;
         n_unit = unit;
-        A.cin_pad = cin64;
-        A.KC = 64;
-        A.kchunks = cin64 / 64;
-        A.ksteps = 4;
         A.tw_log = 3;
         A.th_log = 4;
         A.tb_log = 0;
@@ -694,11 +726,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
   if (A.halo) {
-    A.b_block = (uint32_t)A.n_tile * 128u;
+    A.b_block = ((uint32_t)A.n_tile * row_bytes + 1023u) & ~1023u;
     A.b_region = 9u * (uint32_t)A.kchunks * A.b_block;
     A.a_stride = 0;
-    A.stage_stride = 16u * 18u * 128u;   // one halo tile: 18 image rows x 16 pixels x 64 channels (fp16)
-    A.tx_bytes = A.stage_stride;
+    A.stage_stride = (16u * 18u * row_bytes + 1023u) & ~1023u;   // one halo tile: 18 image rows x 16 pixels x KC channels
+    A.tx_bytes = 16u * 18u * row_bytes;
     stages = (int)((204u * 1024u - A.b_region) / A.stage_stride);
     if (stages > 4) stages = 4;
     if (stages < 2) {
@@ -711,6 +743,15 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   {
     const int nchunks = (epi == 1) ? (A.NC + 7) / 8 : (A.n_tile + 7) / 8;
     A.epi_warps = nchunks >= 3 ? 12 : nchunks >= 2 ? 8 : 4;
+    A.epi_groups = 1;
+    A.acc_stages = 2;
+    A.acc_stride = 256;
+    if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
+      A.epi_warps = 12;
+      A.epi_groups = 3;
+      A.acc_stages = 6;
+      A.acc_stride = 64;
+    }
   }
   // ---- descriptors
   const CUtensorMapSwizzle swz = A.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
