@@ -42,7 +42,8 @@ def test_direct_matches_oracle(cuda_lib, stack, H, W, bias):
     net.close()
 
 
-@pytest.mark.parametrize("stack,H,W", [(TINY, 20, 28), (TINY, 32, 64), (FULL, 32, 48), (FULL, 128, 160)])
+@pytest.mark.parametrize("stack,H,W", [(TINY, 20, 28), (TINY, 32, 64), (TINY, 128, 128), (FULL, 32, 48),
+                                       (FULL, 128, 160)])
 def test_tc_matches_oracle(cuda_lib, stack, H, W):
     import torch
     Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8

@@ -124,7 +124,9 @@ struct ConvArgs {
                                  // G > 1: narrow tiles -- warp group g (4 warps) owns the tiles with index % G == g,
                                  // so G epilogues are in flight and their latency overlaps
   int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
-  int halo;                      // 1: halo + stationary-weights mode (see conv_tc_kernel)
+  int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
+  int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
+  uint32_t a_slot, a_tx;         // pair mode: bytes of one halo slot (1024-aligned) and of the TMA box
   uint32_t b_block, b_region;    // halo mode: bytes of one [n_tile x 64] weight block; bytes of all 9*kchunks blocks
   uint32_t a_stride, stage_stride, tx_bytes;
   uint32_t desc_hi;              // upper half of the smem matrix descriptor (SBO, version, swizzle)
@@ -183,7 +185,7 @@ template <int EPI>  // 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1 + 4];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -194,6 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
   const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + TC_MAX_ACC]);
   const uint32_t bfull = smem_u32(&bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC]);   // halo mode: all weights have landed
+  const uint32_t afull0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1]);   // pair mode: 2 halo slots
+  const uint32_t aempty0 = afull0 + 16;
 
   const int tiles_img = P.tiles_w * P.tiles_h;
   const int tiles_b = (P.B + (1 << P.tb_log) - 1) >> P.tb_log;
@@ -210,6 +214,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tempty0 + 8 * a, (uint32_t)(P.epi_groups > 1 ? 4 : P.epi_warps));
     }
     mbar_init(bfull, 1);
+    for (int a = 0; a < 2; a++) {
+      mbar_init(afull0 + 8 * a, 1);
+      mbar_init(aempty0 + 8 * a, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -226,7 +234,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0 && P.halo) {
+    if (lane == 0 && P.halo == 2) {
+      // Halo pair mode (large weight matrices): per 64-channel chunk ONE halo box of 34 image rows x 16 pixels
+      // feeds two vertically adjacent 8x16 M tiles for all nine taps (shifted descriptors), and every streamed
+      // [N_tile x 64] weight block is used by both M tiles before it is released: ~2.5x less L2->SM traffic than
+      // nine im2col boxes + one weight block per M tile.
+      uint32_t ita = 0, itb = 0;
+      const uint32_t bbase = smem0 + 2 * P.a_slot;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nt = t % P.n_tiles_n;
+        int mt = t / P.n_tiles_n;
+        const int twi = mt % P.tiles_w;
+        mt /= P.tiles_w;
+        const int thi = mt % P.tiles_h;
+        const int tbi = mt / P.tiles_h;
+        const int w0 = twi << P.tw_log, h0 = thi * P.tile_h, b0 = tbi;
+        const int n0 = nt * P.n_tile;
+        for (int ch = 0; ch < P.kchunks; ch++, ita++) {
+          const uint32_t sl = ita & 1u, pha = (ita >> 1) & 1u;
+          mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
+          mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
+          tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, ch * 64, w0 - 1, h0 - 1, b0);
+          for (int tap = 0; tap < 9; tap++, itb++) {
+            const uint32_t s = itb % P.stages, ph = (itb / P.stages) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
+            tma_load_2d(bbase + s * P.stage_stride, &tmB, full0 + 8 * s, tap * P.cin_pad + ch * 64, n0);
+          }
+        }
+      }
+    } else if (lane == 0 && P.halo) {
       // Halo mode.  The whole weight matrix of this CTA's N tile stays resident in shared memory (loaded once);
       // per tile and 64-channel chunk ONE box of (TH+2) x 16 pixels is fetched and all nine taps read it through
       // shifted UMMA descriptors, instead of nine shifted boxes: ~4x less activation traffic, no weight re-reads.
@@ -279,7 +316,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && P.halo) {
+    if (lane == 0 && P.halo == 2) {
+      uint32_t ita = 0, itb = 0, tc = 0;
+      const uint32_t bbase = smem0 + 2 * P.a_slot;
+      const uint32_t ahi32 = ((2048u >> 4) & 0x3FFFu) | (P.desc_hi & 0xFFFFC000u);   // image rows 16 px * 128 B apart
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+        mbar_wait(tempty0, (tc & 1u) ^ 1u);   // one accumulator set (two M tiles fill TMEM)
+        tc_fence_after();
+        for (int ch = 0; ch < P.kchunks; ch++, ita++) {
+          const uint32_t sl = ita & 1u, pha = (ita >> 1) & 1u;
+          mbar_wait(afull0 + 8 * sl, pha);
+          tc_fence_after();
+          const uint32_t sa = smem0 + sl * P.a_slot;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; tap++, itb++) {
+            const uint32_t s = itb % P.stages, ph = (itb / P.stages) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_lo = (((sa + (uint32_t)(dy * 16 + dx) * 128u) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t b_lo = (((bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+            for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 32768 bytes further down the halo
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                tc_mma_f16(tmem_base + sub * 256, make_desc(a_lo + sub * 2048 + 2 * k, ahi32),
+                           make_desc(b_lo + 2 * k, P.desc_hi), P.idesc, (ch | tap | k) != 0);
+            tc_commit(empty0 + 8 * s);
+          }
+          tc_commit(aempty0 + 8 * sl);
+        }
+        tc_commit(tfull0);
+      }
+    } else if (lane == 0 && P.halo) {
       uint32_t it = 0, tc = 0;
       if ((int)blockIdx.x < n_tiles) mbar_wait(bfull, 0);
       tc_fence_after();
@@ -363,12 +432,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mt /= P.tiles_w;
       const int thi = mt % P.tiles_h;
       const int tbi = mt / P.tiles_h;
-      const int w = (twi << P.tw_log) + tw, h = (thi << P.th_log) + th, b = (tbi << P.tb_log) + tb;
-      const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
+      const int w = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
       const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride;
+      for (int sub = 0; sub < P.sub_tiles; sub++) {
+      const int h = thi * P.tile_h + (sub << P.th_log) + th;
+      const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride + sub * 256;
       if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
@@ -488,6 +559,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }   // sub tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
@@ -663,6 +735,31 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       }
     }
   }
+  // ---- halo pair mode: large weight matrices, two stacked M tiles share every streamed weight block
+  if (!A.halo) {
+    // Measured on B200 (round 1): correct, but slower than the im2col path for the (3,48,96,192) net (gates1
+    // 0.38 -> 0.46 ms at B=100: one accumulator set, only three weight stages fit beside two 68 KB halo slots), so
+    // it is opt-in (TZ_HALO=3) until the pipeline is rebalanced.
+    const char *env = getenv("TZ_HALO");
+    const bool want = env && env[0] == '3';
+    const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
+    const uint32_t bst = ((uint32_t)ntile_c * 128u + 1023u) & ~1023u;
+    const uint32_t aslot = 16u * 34u * 128u;
+    if (want && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 32) == 0 && ntile_c <= 256 &&
+        2u * aslot + 3u * bst + 1024u <= 226u * 1024u) {
+      A.halo = 2;
+      A.KC = 64;
+      A.kchunks = A.cin_pad / 64;
+      A.ksteps = 4;
+      A.tw_log = 3;
+      A.th_log = 4;
+      A.tb_log = 0;
+      A.tiles_w = (A.W + 7) >> 3;
+      A.tiles_h = A.H / 32;
+    }
+  }
+  A.sub_tiles = (A.halo == 2) ? 2 : 1;
+  A.tile_h = (1 << A.th_log) * A.sub_tiles;
   if (epi == 1) {
     A.NC = n_unit;
     A.NCp = round_up(A.NC, 8);
@@ -725,7 +822,17 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   }
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
-  if (A.halo) {
+  if (A.halo == 2) {
+    A.a_slot = 16u * 34u * 128u;   // 34 image rows x 16 pixels x 64 channels fp16 (multiple of 1024)
+    A.a_tx = A.a_slot;
+    A.a_stride = 0;
+    A.stage_stride = (b_bytes + 1023u) & ~1023u;
+    A.tx_bytes = b_bytes;
+    stages = (int)((226u * 1024u - 1024u - 2u * A.a_slot) / A.stage_stride);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    A.stages = stages;
+    c->smem_bytes = 2u * A.a_slot + (uint32_t)stages * A.stage_stride + 1024u;
+  } else if (A.halo) {
     A.b_block = ((uint32_t)A.n_tile * row_bytes + 1023u) & ~1023u;
     A.b_region = 9u * (uint32_t)A.kchunks * A.b_block;
     A.a_stride = 0;
@@ -746,7 +853,10 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.epi_groups = 1;
     A.acc_stages = 2;
     A.acc_stride = 256;
-    if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
+    if (A.halo == 2) {
+      A.acc_stages = 1;     // the two M tiles of a pair occupy TMEM columns [0, N) and [256, 256 + N)
+      A.acc_stride = 0;
+    } else if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
       A.epi_warps = 12;
       A.epi_groups = 3;
       A.acc_stages = 6;
@@ -764,9 +874,9 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
     cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
     cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
-    if (A.halo) {   // (TH+2) rows of 16 pixels: pitch 16 keeps the 8-row groups 2048 B apart (swizzle-phase neutral)
+    if (A.halo) {   // (tile height + 2) image rows of 16 pixels each (8-wide tile + halo, padded to a 16-pixel pitch)
       box[1] = 16;
-      box[2] = 18;
+      box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
@@ -813,8 +923,8 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   }
   T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
   if (!T->r0) return TZ_ENOMEM;
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
   for (int l = 0; l < L; l++) {
     // gate conv: reads all of X_l = [e_l | up(r_{l+1})]; the r_{t-1} slice of the kernel is hoisted into BM_l
@@ -877,7 +987,7 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   const int tiles_b = (B + (1 << A.tb_log) - 1) >> A.tb_log;
   long long n_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b * A.n_tiles_n;
   int grid = n_tiles < T->sm_count ? (int)n_tiles : T->sm_count;
-  if (A.halo) grid = grid / A.n_tiles_n * A.n_tiles_n;   // a CTA keeps one N tile: its weights stay in shared memory
+  if (A.halo == 1) grid = grid / A.n_tiles_n * A.n_tiles_n;   // a CTA keeps one N tile: its weights stay in shared memory
   if (c->epi == 0)
     conv_tc_kernel<0><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   else
