@@ -46,6 +46,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // after ~4 s of waiting the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;   // fast path: already complete
   uint64_t t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
@@ -232,65 +240,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  // Ring state is kept incrementally (stage index + phase bit) and descriptors are formed with 32-bit adds: ONE
+  // thread issues every TMA and ONE thread every tcgen05.mma of the CTA, so the instruction count of these two
+  // loops bounds the tensor pipe (a microbenchmark reaches N/2 cycles per M128 MMA only with straight-line issue;
+  // runtime divisions and 64-bit descriptor arithmetic per MMA cost more than the MMA itself).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0 && P.halo == 2) {
-      // Halo pair mode (large weight matrices): per 64-channel chunk ONE halo box of 34 image rows x 16 pixels
-      // feeds two vertically adjacent 8x16 M tiles for all nine taps (shifted descriptors), and every streamed
-      // [N_tile x 64] weight block is used by both M tiles before it is released: ~2.5x less L2->SM traffic than
-      // nine im2col boxes + one weight block per M tile.
-      uint32_t ita = 0, itb = 0;
-      const uint32_t bbase = smem0 + 2 * P.a_slot;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int nt = t % P.n_tiles_n;
-        int mt = t / P.n_tiles_n;
-        const int twi = mt % P.tiles_w;
-        mt /= P.tiles_w;
-        const int thi = mt % P.tiles_h;
-        const int tbi = mt / P.tiles_h;
-        const int w0 = twi << P.tw_log, h0 = thi * P.tile_h, b0 = tbi;
-        const int n0 = nt * P.n_tile;
-        for (int ch = 0; ch < P.kchunks; ch++, ita++) {
-          const uint32_t sl = ita & 1u, pha = (ita >> 1) & 1u;
-          mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
-          mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
-          tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, ch * 64, w0 - 1, h0 - 1, b0);
-          for (int tap = 0; tap < 9; tap++, itb++) {
-            const uint32_t s = itb % P.stages, ph = (itb / P.stages) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
-            tma_load_2d(bbase + s * P.stage_stride, &tmB, full0 + 8 * s, tap * P.cin_pad + ch * 64, n0);
-          }
-        }
-      }
-    } else if (lane == 0 && P.halo) {
-      // Halo mode.  The whole weight matrix of this CTA's N tile stays resident in shared memory (loaded once);
-      // per tile and 64-channel chunk ONE box of (TH+2) x 16 pixels is fetched and all nine taps read it through
-      // shifted UMMA descriptors, instead of nine shifted boxes: ~4x less activation traffic, no weight re-reads.
-      if ((int)blockIdx.x < n_tiles) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;      // main ring (im2col: A+B stages; halo: halo slots; pair: weight stages)
+      uint32_t sl = 0, pha = 0;    // pair mode: halo slot ring
+      if (P.halo == 1 && (int)blockIdx.x < n_tiles) {
+        // Halo mode: the whole weight matrix of this CTA's N tile stays resident in shared memory (loaded once)
         const int n0 = ((int)blockIdx.x % P.n_tiles_n) * P.n_tile;
         mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * (uint32_t)(2 * P.KC));
         for (int kb = 0; kb < kblocks; kb++)   // block kb = tap * kchunks + chunk
           tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * P.KC, n0);
       }
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int mt = t / P.n_tiles_n;
-        const int twi = mt % P.tiles_w;
-        mt /= P.tiles_w;
-        const int thi = mt % P.tiles_h;
-        const int tbi = mt / P.tiles_h;
-        const int w0 = twi << P.tw_log, h0 = thi << P.th_log, b0 = tbi << P.tb_log;
-        for (int ch = 0; ch < P.kchunks; ch++, it++) {
-          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          const uint32_t full = full0 + 8 * s;
-          mbar_expect_tx(full, P.tx_bytes);
-          tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, ch * P.KC, w0 - 1, h0 - 1, b0);
-        }
-      }
-    } else if (lane == 0) {
-      uint32_t it = 0;
+      const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int nt = t % P.n_tiles_n;
         int mt = t / P.n_tiles_n;
@@ -298,118 +264,145 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mt /= P.tiles_w;
         const int thi = mt % P.tiles_h;
         const int tbi = mt / P.tiles_h;
-        const int w0 = twi << P.tw_log, h0 = thi << P.th_log, b0 = tbi << P.tb_log;
+        const int w0 = twi << P.tw_log, h0 = thi * P.tile_h, b0 = tbi << P.tb_log;
         const int n0 = nt * P.n_tile;
-        for (int kb = 0; kb < kblocks; kb++, it++) {
-          const int tap = kb / P.kchunks, ch = kb - tap * P.kchunks;
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          const uint32_t full = full0 + 8 * s;
-          mbar_expect_tx(full, P.tx_bytes);
-          const uint32_t sa = smem0 + s * P.stage_stride;
-          tma_load_4d(sa, &tmA, full, ch * P.KC, w0 + dx - 1, h0 + dy - 1, b0);
-          tma_load_2d(sa + P.a_stride, &tmB, full, tap * P.cin_pad + ch * P.KC, n0);
+        if (P.halo == 0) {
+          // im2col mode: per (tap, chunk) one shifted activation box + one weight box
+          int kcoord = 0;
+          for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++)
+              for (int c = 0; c < P.cin_pad; c += P.KC) {
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t full = full0 + 8 * s;
+                mbar_expect_tx(full, P.tx_bytes);
+                const uint32_t sa = smem0 + s * P.stage_stride;
+                tma_load_4d(sa, &tmA, full, c, w0 + dx, h0 + dy, b0);
+                tma_load_2d(sa + P.a_stride, &tmB, full, kcoord, n0);
+                kcoord += P.KC;
+                if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+              }
+        } else if (P.halo == 1) {
+          // halo mode: per chunk ONE box of (TH+2) x 16 pixels; the nine taps read it through shifted descriptors
+          for (int c = 0; c < P.cin_pad; c += P.KC) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t full = full0 + 8 * s;
+            mbar_expect_tx(full, P.tx_bytes);
+            tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+          }
+        } else {
+          // halo pair mode (large weight matrices): per 64-channel chunk ONE halo box of 34 image rows x 10 pixels
+          // feeds two stacked 8x16 M tiles for all nine taps, and every streamed [N_tile x 64] weight block is
+          // used by both M tiles before it is released
+          int kc = 0;
+          for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
+            mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
+            mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
+            tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            sl ^= 1u;
+            pha ^= (sl == 0);
+            int kcoord = kc;
+            for (int tap = 0; tap < 9; tap++, kcoord += P.cin_pad) {
+              mbar_wait(empty0 + 8 * s, ph ^ 1u);
+              mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
+              tma_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, n0);
+              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            }
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && P.halo == 2) {
-      uint32_t ita = 0, itb = 0, tc = 0;
-      const uint32_t bbase = smem0 + 2 * P.a_slot;
-      const uint32_t ahi32 = ((2048u >> 4) & 0x3FFFu) | (P.desc_hi & 0xFFFFC000u);   // image rows 16 px * 128 B apart
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
-        mbar_wait(tempty0, (tc & 1u) ^ 1u);   // one accumulator set (two M tiles fill TMEM)
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, sl = 0, pha = 0;
+      uint32_t a = 0, aph = 0;   // accumulator ring
+      const uint32_t hi = P.desc_hi;
+      const uint32_t idesc = P.idesc;
+      if (P.halo == 1 && (int)blockIdx.x < n_tiles) {
+        mbar_wait(bfull, 0);
         tc_fence_after();
-        for (int ch = 0; ch < P.kchunks; ch++, ita++) {
-          const uint32_t sl = ita & 1u, pha = (ita >> 1) & 1u;
-          mbar_wait(afull0 + 8 * sl, pha);
-          tc_fence_after();
-          const uint32_t sa = smem0 + sl * P.a_slot;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; tap++, itb++) {
-            const uint32_t s = itb % P.stages, ph = (itb / P.stages) & 1u;
+      }
+      const uint32_t rowb = 2u * (uint32_t)P.KC;   // bytes per pixel row of a chunk
+      // halo tiles: 16 pixels per image row -> the 8-row groups (one image row of the 8-wide tile) are 16*rowb apart
+      // (pair mode: 10 pixels of 128 B).  Neither needs to be a multiple of the swizzle period: the swizzle is a
+      // function of the absolute shared-memory address bits (what TMA wrote), and the descriptor base_offset stays 0
+      // -- measured on B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
+      const uint32_t ahi_halo = (((16u * rowb) >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
+      const uint32_t ahi_pair = ((1280u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
+      const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // halo mode: block kb = tap * kchunks + chunk
+      const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(tempty0 + 8 * a, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
+        if (P.halo == 0) {
+          uint32_t acc = 0;
+          for (int kb = 0; kb < kblocks; kb++) {
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_lo = (((sa + (uint32_t)(dy * 16 + dx) * 128u) >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t b_lo = (((bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
-#pragma unroll
-            for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 32768 bytes further down the halo
+            const uint32_t sa = smem0 + s * P.stage_stride;
+            const uint32_t alo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t blo = (((sa + P.a_stride) >> 4) & 0x3FFFu) | (1u << 16);
+            // advance 32 bytes (16 fp16 of K) inside the swizzled row per MMA
+            if (P.ksteps == 4) {
 #pragma unroll
               for (int k = 0; k < 4; k++)
-                tc_mma_f16(tmem_base + sub * 256, make_desc(a_lo + sub * 2048 + 2 * k, ahi32),
-                           make_desc(b_lo + 2 * k, P.desc_hi), P.idesc, (ch | tap | k) != 0);
-            tc_commit(empty0 + 8 * s);
+                tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
+            } else {
+              for (int k = 0; k < P.ksteps; k++)
+                tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
+            }
+            acc = 1;
+            tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
           }
-          tc_commit(aempty0 + 8 * sl);
-        }
-        tc_commit(tfull0);
-      }
-    } else if (lane == 0 && P.halo) {
-      uint32_t it = 0, tc = 0;
-      if ((int)blockIdx.x < n_tiles) mbar_wait(bfull, 0);
-      tc_fence_after();
-      const uint32_t rowb = 2u * (uint32_t)P.KC;                            // bytes per pixel row of a chunk
-      // halo tile: 16 pixels per image row -> the 8-row groups (one image row of the 8-wide tile) are 16*rowb apart;
-      // weights: dense 8-row groups in aligned blocks (P.desc_hi as is)
-      const uint32_t ahi32 = (((16u * rowb) >> 4) & 0x3FFFu) | (P.desc_hi & 0xFFFFC000u);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
-        const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
-        mbar_wait(tempty0 + 8 * a, aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
-        for (int ch = 0; ch < P.kchunks; ch++, it++) {
-          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
-          // rows (th, tw) of the M tile = halo rows (th+dy)*16 + (tw+dx): 8-row groups 16*rowb apart (SBO).  The
-          // tap's start is rowb*(16dy+dx) bytes past a 1024-aligned base; the swizzle is a function of the absolute
-          // shared-memory address bits (what TMA wrote), so the descriptor base_offset stays 0 -- measured on
-          // B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
-          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
-          const uint32_t b_lo = (((smem0 + (uint32_t)ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-          const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // block kb = tap * kchunks + chunk
-          if (P.ksteps == 4)
-            issue_halo_chunk<4>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
-          else if (P.ksteps == 2)
-            issue_halo_chunk<2>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
-          else
-            issue_halo_chunk<1>(d_tmem, a_lo, ahi32, b_lo, P.desc_hi, rowb >> 4, btap16, P.idesc, ch == 0);
-          tc_commit(empty0 + 8 * s);   // halo slot free once its 36 MMAs retire
-        }
-        tc_commit(tfull0 + 8 * a);
-      }
-    } else if (lane == 0) {
-      uint32_t it = 0, tc = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
-        const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
-        mbar_wait(tempty0 + 8 * a, aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
-        for (int kb = 0; kb < kblocks; kb++, it++) {
-          const uint32_t s = it % P.stages, ph = (it / P.stages) & 1u;
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = smem0 + s * P.stage_stride;
-          const uint64_t hi = (uint64_t)P.desc_hi << 32;
-          const uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFFu) | (1u << 16));
-          const uint64_t bdesc = hi | (uint64_t)((((sa + P.a_stride) >> 4) & 0x3FFFu) | (1u << 16));
-          // advance 32 bytes (16 fp16 of K) inside the swizzled row
-          if (P.ksteps == 4) {
+        } else if (P.halo == 1) {
+          for (int ch = 0; ch < P.kchunks; ch++) {
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
+            const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t b_lo = (((smem0 + (uint32_t)ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
+            if (P.ksteps == 4)
+              issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+            else if (P.ksteps == 2)
+              issue_halo_chunk<2>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+            else
+              issue_halo_chunk<1>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+            tc_commit(empty0 + 8 * s);   // halo slot free once its MMAs retire
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+          }
+        } else {
+          uint32_t acc = 0;
+          for (int ch = 0; ch < P.kchunks; ch++) {
+            mbar_wait(afull0 + 8 * sl, pha);
+            tc_fence_after();
+            const uint32_t a_base = (((smem0 + sl * P.a_slot) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
-          } else {
-            for (int k = 0; k < P.ksteps; k++)
-              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+            for (int tap = 0; tap < 9; tap++) {
+              mbar_wait(full0 + 8 * s, ph);
+              tc_fence_after();
+              const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;   // 128 B per halo pixel
+              const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+              for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 20480 bytes further down the halo
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  tc_mma_f16(tmem_base + sub * 256, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
+                             make_desc(b_lo + 2 * k, hi), idesc, acc | (uint32_t)(tap | k));
+              tc_commit(empty0 + 8 * s);
+              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            }
+            acc = 1;
+            tc_commit(aempty0 + 8 * sl);
+            sl ^= 1u;
+            pha ^= (sl == 0);
           }
-          tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
         }
         tc_commit(tfull0 + 8 * a);    // accumulator complete
+        if (++a == (uint32_t)P.acc_stages) { a = 0; aph ^= 1u; }
       }
     }
     __syncwarp();
@@ -602,6 +595,47 @@ __global__ void pack_bm_kernel(const float *__restrict__ src, float *__restrict_
   dst[i] = src[(pix * 4 + g) * R + q * 8 + j];
 }
 
+// prednet.py:268-271 at layer 0: prediction = min(relu(conv3x3(r_0) + b), pixel_max), C -> C channels (C = 1 or 3).
+// 16x16 output pixels per block; the 18x18xC input patch and the 9*C*C weights sit in shared memory.
+template <int C>
+__global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0, const float *__restrict__ wt,
+                                                    const float *__restrict__ bias, float *__restrict__ out, int H,
+                                                    int W, float clip) {
+  __shared__ float tile[18][18 * C + 1];
+  __shared__ float ws[9 * C * C];
+  __shared__ float bs[C];
+  const int b = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+  const float *src = r0 + (long long)b * H * W * C;
+  for (int i = threadIdx.x; i < 18 * 18 * C; i += 256) {
+    const int yy = i / (18 * C), rem = i - yy * (18 * C);
+    const int xx = rem / C, c = rem - xx * C;
+    const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+    tile[yy][rem] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? src[((long long)gy * W + gx) * C + c] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < 9 * C * C; i += 256) ws[i] = wt[i];
+  if (threadIdx.x < C) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  float acc[C];
+#pragma unroll
+  for (int co = 0; co < C; co++) acc[co] = 0.0f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+      for (int ci = 0; ci < C; ci++) {
+        const float v = tile[ty + ky][(tx + kx) * C + ci];
+#pragma unroll
+        for (int co = 0; co < C; co++) acc[co] = fmaf(v, ws[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
+      }
+  float *dst = out + (((long long)b * H + y) * W + x) * C;
+#pragma unroll
+  for (int co = 0; co < C; co++) dst[co] = fminf(fmaxf(acc[co] + bs[co], 0.0f), clip);
+}
+
 __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(src[i]);
@@ -744,7 +778,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     const bool want = env && env[0] == '3';
     const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
     const uint32_t bst = ((uint32_t)ntile_c * 128u + 1023u) & ~1023u;
-    const uint32_t aslot = 16u * 34u * 128u;
+    const uint32_t aslot = (10u * 34u * 128u + 1023u) & ~1023u;
     if (want && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 32) == 0 && ntile_c <= 256 &&
         2u * aslot + 3u * bst + 1024u <= 226u * 1024u) {
       A.halo = 2;
@@ -823,8 +857,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
   if (A.halo == 2) {
-    A.a_slot = 16u * 34u * 128u;   // 34 image rows x 16 pixels x 64 channels fp16 (multiple of 1024)
-    A.a_tx = A.a_slot;
+    A.a_tx = 10u * 34u * 128u;     // 34 image rows x 10 pixels x 64 channels fp16
+    A.a_slot = (A.a_tx + 1023u) & ~1023u;
     A.a_stride = 0;
     A.stage_stride = (b_bytes + 1023u) & ~1023u;
     A.tx_bytes = b_bytes;
@@ -875,7 +909,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
     cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
     if (A.halo) {   // (tile height + 2) image rows of 16 pixels each (8-wide tile + halo, padded to a 16-pixel pitch)
-      box[1] = 16;
+      box[1] = (A.halo == 2) ? 10 : 16;
       box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
     }
@@ -1019,9 +1053,19 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[ne++], st);
   }
-  ConvSrc s = {T->r0, h->R[0], 0, 0, (long long)h->H[0] * h->W[0] * h->R[0]};
-  int rc = conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,
-                          h->cfg.pixel_max, st);
+  int rc = TZ_OK;
+  if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
+    dim3 grid((h->W[0] + 15) / 16, (h->H[0] + 15) / 16, B);
+    if (h->S[0] == 3)
+      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max);
+    else
+      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max);
+    TZ_CHECK_LAUNCH();
+  } else {
+    ConvSrc s = {T->r0, h->R[0], 0, 0, (long long)h->H[0] * h->W[0] * h->R[0]};
+    rc = conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,
+                        h->cfg.pixel_max, st);
+  }
   if (ev) cudaEventRecord(ev[ne++], st);
   return rc;
 }

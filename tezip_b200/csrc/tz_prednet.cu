@@ -456,7 +456,7 @@ int tz_prednet_kernel_info(tz_prednet *h, int i, char *name, int name_len, doubl
     snprintf(name, name_len, "conv_tc_gates%d", l);
     fl = 2.0 * h->H[l] * h->W[l] * 9.0 * h->cin_g[l] * 4 * h->R[l];
   } else {
-    snprintf(name, name_len, "conv_direct_ahat0");
+    snprintf(name, name_len, "ahat0");
     fl = 2.0 * h->H[0] * h->W[0] * 9.0 * h->R[0] * h->S[0];
   }
   *flops_per_frame = fl;
