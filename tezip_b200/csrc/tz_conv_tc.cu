@@ -111,6 +111,13 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float v[8]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+// 256-bit read-only global load (sm_100): one request per thread instead of two 128-bit ones -- the epilogue reads
+// one private 128-byte line per thread and chunk, so its cost is the number of load wavefronts, not the bytes.
+__device__ __forceinline__ void ldg256(const float *p, float v[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernel arguments
@@ -134,6 +141,7 @@ struct ConvArgs {
   int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
   int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
   int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
+  int sub_stride;                // TMEM columns between the accumulators of the two M tiles of a pair
   uint32_t a_slot, a_tx;         // pair mode: bytes of one halo slot (1024-aligned) and of the TMA box
   uint32_t b_block, b_region;    // halo mode: bytes of one [n_tile x 64] weight block; bytes of all 9*kchunks blocks
   uint32_t a_stride, stage_stride, tx_bytes;
@@ -153,6 +161,7 @@ struct ConvArgs {
   __half *xr_out;                // X_{l-1}: [B, 2H, 2W, xr_cstride], r written up-sampled at channel xr_coff
   int xr_cstride, xr_coff;
   float *r0_out;                 // layer 0: r as fp32 [B, H, W, R] (xr_out == nullptr)
+  long long *dbg;                // optional [gridDim][8]: MMA-thread cycle breakdown (TZ_CONV_DEBUG), else nullptr
 };
 
 __device__ __forceinline__ float hsig(float x) {
@@ -333,14 +342,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ahi_pair = ((1280u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
       const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // halo mode: block kb = tap * kchunks + chunk
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
+      long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
+      const bool dbg = P.dbg != nullptr;
+      if (dbg) t_start = clock64();
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (dbg) c0 = clock64();
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
+        if (dbg) w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
         if (P.halo == 0) {
           uint32_t acc = 0;
           for (int kb = 0; kb < kblocks; kb++) {
+            if (dbg) c0 = clock64();
             mbar_wait(full0 + 8 * s, ph);
+            if (dbg) w_full += clock64() - c0;
             tc_fence_after();
             const uint32_t sa = smem0 + s * P.stage_stride;
             const uint32_t alo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
@@ -377,12 +393,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           uint32_t acc = 0;
           for (int ch = 0; ch < P.kchunks; ch++) {
+            if (dbg) c0 = clock64();
             mbar_wait(afull0 + 8 * sl, pha);
+            if (dbg) w_afull += clock64() - c0;
             tc_fence_after();
             const uint32_t a_base = (((smem0 + sl * P.a_slot) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
             for (int tap = 0; tap < 9; tap++) {
+              if (dbg) c0 = clock64();
               mbar_wait(full0 + 8 * s, ph);
+              if (dbg) w_full += clock64() - c0;
               tc_fence_after();
               const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;   // 128 B per halo pixel
               const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
@@ -390,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 20480 bytes further down the halo
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                  tc_mma_f16(tmem_base + sub * 256, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
+                  tc_mma_f16(d_tmem + sub * (uint32_t)P.sub_stride, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
                              make_desc(b_lo + 2 * k, hi), idesc, acc | (uint32_t)(tap | k));
               tc_commit(empty0 + 8 * s);
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
@@ -403,6 +423,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_commit(tfull0 + 8 * a);    // accumulator complete
         if (++a == (uint32_t)P.acc_stages) { a = 0; aph ^= 1u; }
+      }
+      if (dbg) {
+        long long *o = P.dbg + 8 * blockIdx.x;
+        o[0] = clock64() - t_start;
+        o[1] = w_tempty;
+        o[2] = w_full;
+        o[3] = w_afull;
       }
     }
     __syncwarp();
@@ -432,7 +459,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int sub = 0; sub < P.sub_tiles; sub++) {
       const int h = thi * P.tile_h + (sub << P.th_log) + th;
       const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride + sub * 256;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride +
+                            sub * (uint32_t)P.sub_stride;
       if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
@@ -441,7 +469,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float *ah = P.ahat_next + ((long long)(h >> 1) * Wo + (w >> 1)) * P.S_next;
         __half *dst = P.xe_out + opix * P.xe_cstride;
         const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
-        for (int j0 = 8 * part; j0 < n_real; j0 += 8 * nparts) {
+        // The error units need Ahat0 of the pooled pixel (one private 32-byte piece per writer lane and chunk).  All
+        // of this warp's chunks are requested up front, so their L2 latency is paid once per tile, not per chunk.
+        constexpr int PF = 6;
+        const bool vec_ok = ((P.S_next | P.xe_cstride) & 7) == 0;
+        float ahp[PF][8];
+#pragma unroll
+        for (int c = 0; c < PF; c++) {
+          const int j0 = 8 * (part + c * nparts);
+          const int ch0 = nt * P.n_tile + j0;
+          if (writer && vec_ok && j0 < n_real && ch0 + 8 <= P.S_next) ldg256(ah + ch0, ahp[c]);
+        }
+        auto chunk = [&](int j0, const float *ahv) {
           float v[8];
           tc_ld8(trow + j0, v);
           tc_ld_wait();
@@ -455,14 +494,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (writer) {
             const int ch0 = nt * P.n_tile + j0;
-            if (ch0 + 8 <= P.S_next && ((P.S_next | P.xe_cstride) & 7) == 0) {
-              float4 a0 = *reinterpret_cast<const float4 *>(ah + ch0), a1 = *reinterpret_cast<const float4 *>(ah + ch0 + 4);
-              const float ahv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (ch0 + 8 <= P.S_next && vec_ok) {
+              float al[8];
+              if (!ahv) ldg256(ah + ch0, al);
               __align__(16) __half up[8], dn[8];
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                up[j] = __float2half_rn(fmaxf(__fsub_rn(ahv[j], v[j]), 0.0f));
-                dn[j] = __float2half_rn(fmaxf(__fsub_rn(v[j], ahv[j]), 0.0f));
+                const float a_ = ahv ? ahv[j] : al[j];
+                up[j] = __float2half_rn(fmaxf(__fsub_rn(a_, v[j]), 0.0f));
+                dn[j] = __float2half_rn(fmaxf(__fsub_rn(v[j], a_), 0.0f));
               }
               *reinterpret_cast<uint4 *>(dst + ch0) = *reinterpret_cast<const uint4 *>(up);
               *reinterpret_cast<uint4 *>(dst + P.S_next + ch0) = *reinterpret_cast<const uint4 *>(dn);
@@ -474,7 +514,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+        };
+#pragma unroll
+        for (int c = 0; c < PF; c++) {
+          const int j0 = 8 * (part + c * nparts);
+          if (j0 < n_real) chunk(j0, ahp[c]);
         }
+        for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) chunk(j0, nullptr);
       } else {
         // LSTM cell: columns [g*NCp + j], g = i,f,c,o.  c = f*C0 + i*tanh(.), r = o*tanh(c)
         const long long pix = (long long)h * P.W + w;
@@ -490,19 +536,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (valid) {
             float r[8];
             if (P.bm_packed) {
-              const float4 *bp = reinterpret_cast<const float4 *>(P.bm + (pix * (P.R >> 3) + ((nt * P.NC + j0) >> 3)) * 32);
-              const float4 *cp = reinterpret_cast<const float4 *>(c0 + j0);
+              const float *bp = P.bm + (pix * (P.R >> 3) + ((nt * P.NC + j0) >> 3)) * 32;
               float bq[32], cq[8];
-#pragma unroll
-              for (int q = 0; q < 8; q++) {
-                const float4 t = bp[q];
-                bq[4 * q] = t.x; bq[4 * q + 1] = t.y; bq[4 * q + 2] = t.z; bq[4 * q + 3] = t.w;
-              }
-#pragma unroll
-              for (int q = 0; q < 2; q++) {
-                const float4 t = cp[q];
-                cq[4 * q] = t.x; cq[4 * q + 1] = t.y; cq[4 * q + 2] = t.z; cq[4 * q + 3] = t.w;
-              }
+              ldg256(bp, bq);
+              ldg256(bp + 8, bq + 8);
+              ldg256(bp + 16, bq + 16);
+              ldg256(bp + 24, bq + 24);
+              ldg256(c0 + j0, cq);
 #pragma unroll
               for (int j = 0; j < 8; j++) {
                 const float gi = hsig(__fadd_rn(vi[j], bq[j]));
@@ -771,17 +811,23 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   }
   // ---- halo pair mode: large weight matrices, two stacked M tiles share every streamed weight block
   if (!A.halo) {
-    // Measured on B200 (round 1): correct, but slower than the im2col path for the (3,48,96,192) net (gates1
-    // 0.38 -> 0.46 ms at B=100: one accumulator set, only three weight stages fit beside two 68 KB halo slots), so
-    // it is opt-in (TZ_HALO=3) until the pipeline is rebalanced.
+    // Measured on B200 (round 1, (3,48,96,192) net, B=100): with N tiles of <= 128 columns and two accumulator
+    // stages gates2 0.32 -> 0.28 ms, gates1 0.35 -> 0.34 ms vs the im2col path (TZ_HALO=1 selects the latter).
     const char *env = getenv("TZ_HALO");
-    const bool want = env && env[0] == '3';
-    const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
+    const bool want = !(env && (env[0] == '0' || env[0] == '1'));
+    // N tiles of at most 128 columns: the two M tiles of a pair then use 256 TMEM columns, which leaves room for a
+    // second accumulator stage (epilogue of pair i overlaps the MMAs of pair i+1)
+    int unit_p = n_unit;
+    if (epi == 1) unit_p = largest_divisor_le(n_real, 32);
+    else for (unit_p = 128; unit_p >= 16; unit_p -= 16) if (n_real % unit_p == 0) break;
+    if (unit_p < 16 && epi == 0) unit_p = n_unit;
+    const int ntile_c = (epi == 1) ? round_up(4 * round_up(unit_p, 8), 16) : round_up(unit_p, 16);
     const uint32_t bst = ((uint32_t)ntile_c * 128u + 1023u) & ~1023u;
     const uint32_t aslot = (10u * 34u * 128u + 1023u) & ~1023u;
     if (want && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 32) == 0 && ntile_c <= 256 &&
         2u * aslot + 3u * bst + 1024u <= 226u * 1024u) {
       A.halo = 2;
+      n_unit = unit_p;
       A.KC = 64;
       A.kchunks = A.cin_pad / 64;
       A.ksteps = 4;
@@ -887,9 +933,17 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.epi_groups = 1;
     A.acc_stages = 2;
     A.acc_stride = 256;
+    A.sub_stride = 0;
     if (A.halo == 2) {
-      A.acc_stages = 1;     // the two M tiles of a pair occupy TMEM columns [0, N) and [256, 256 + N)
-      A.acc_stride = 0;
+      if (A.n_tile <= 128) {   // pair = columns [0, N) and [128, 128 + N) of a 256-column stage; two stages
+        A.acc_stages = 2;
+        A.acc_stride = 256;
+        A.sub_stride = 128;
+      } else {                 // the two M tiles of a pair occupy TMEM columns [0, N) and [256, 256 + N)
+        A.acc_stages = 1;
+        A.acc_stride = 0;
+        A.sub_stride = 256;
+      }
     } else if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
       A.epi_warps = 12;
       A.epi_groups = 3;
@@ -1018,6 +1072,10 @@ void tc_destroy(tz_prednet *h) {
 static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   ConvArgs A = c->args;
   A.B = B;
+  static long long *dbg_buf = nullptr;
+  static const bool dbg_on = getenv("TZ_CONV_DEBUG") != nullptr;
+  if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long));
+  A.dbg = dbg_on ? dbg_buf : nullptr;
   const int tiles_b = (B + (1 << A.tb_log) - 1) >> A.tb_log;
   long long n_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b * A.n_tiles_n;
   int grid = n_tiles < T->sm_count ? (int)n_tiles : T->sm_count;
@@ -1027,6 +1085,14 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   else
     conv_tc_kernel<1><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   TZ_CHECK_LAUNCH();
+  if (dbg_on) {   // diagnostics only: synchronous
+    long long hbuf[256 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tz conv] epi %d halo %d H %d N %d kchunks %d: mma-thread cycles total %lld, wait tempty %lld, "
+            "wait full %lld, wait afull %lld (CTA 0; tiles/CTA ~%lld)\n", c->epi, A.halo, A.H, A.n_tile, A.kchunks,
+            hbuf[0], hbuf[1], hbuf[2], hbuf[3], (n_tiles + grid - 1) / grid);
+  }
   return TZ_OK;
 }
 
