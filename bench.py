@@ -285,8 +285,20 @@ def run_native(args):
     dom = max(range(len(kern)), key=lambda i: kern[i]["ms"] if kern[i]["kernel"].startswith("conv_tc") else -1)
     total_ms = float(acc.sum())
     achieved = kern[dom]["tflops"]
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same B, same shape)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if Bk == 100 and nt == 1000:
+            traffic = tj["per_launch_dram_bytes"].get(kern[dom]["kernel"])
+    except Exception:
+        traffic = None
+    # executed (not algorithmic) MMA FLOPs: the r_{t-1} slice of every gate kernel is hoisted into the bias maps
     roofline = {"bound": "tensor", "kernel": kern[dom]["kernel"], "achieved": achieved, "peak": pk["tf_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+                "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r1_ncu_full.md)",
+                "flops_convention": "algorithmic FLOPs of SURVEY.md 8(d): full concatenated K for the gate convs; the "
+                                    "kernels execute less (the r(t-1) K-slice is hoisted into per-pixel bias maps)",
                 "peak_source": "%s bf16 dense sustained (kernel timed inside a 9-launch step); fp16 operands" % pk["src"],
                 "launch_ms": kern[dom]["ms"], "share_of_next": kern[dom]["ms"] / total_ms,
                 "next_step": {"ms": total_ms, "tflops": net.flops_per_frame() * Bk / (total_ms * 1e-3) / 1e12,
