@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -374,6 +374,40 @@ def run_native(args):
         ratio = {"native": ns * H * W * C / nat, "oracle": ns * H * W * C / orc, "native_over_oracle": orc / nat,
                  "sample_frames": ns}
 
+    # ---- BASELINE config 5: decompress-only throughput for windows 5 / 10 / 20 (device-resident, same frames)
+    sweep = {}
+    for wn in (5, 20):
+        nwin = -(-nt // wn)
+        if nwin > net.max_batch:
+            net_w = PredNet(STACK, STACK, weights=ws, input_hw=(H, W), max_batch=min(nwin, 256), device=local)
+        else:
+            net_w = net
+        enc_w = codec.encode_frames(frames_dev, net_w, 0, wn, None, mode, bound, True, comm=comm)
+
+        def dec_w():
+            return codec.decode_arrays(enc_w.key_plane, enc_w.body, enc_w.table, enc_w.shape, 0, net_w,
+                                       first_mode=first_mode, first_x=first_x)[0]
+        ms_w, _w, _l = timed(dec_w, max(2, args.steps // 2), 1)
+        sweep["w%d" % wn] = {"decompress_MB_per_s": world * raw_bytes / 1e6 / (ms_w * 1e-3), "ms": ms_w}
+        if net_w is not net:
+            net_w.close()
+    sweep["w%d" % Wn] = {"decompress_MB_per_s": world * raw_bytes / 1e6 / (ms_d * 1e-3), "ms": ms_d}
+
+    # ---- the container stage that follows the hot path: zstd level 9, one frame, all host cores
+    cont = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tezip_b200 import container as tzc
+        payload = enc0.payload()
+        kp_np = enc0.key_plane.cpu().numpy()
+        nw = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        zb = tzc.zstd_compress(payload, 9, workers=nw)
+        zk = tzc.zstd_compress(kp_np, 9, workers=nw)
+        tz_s = time.perf_counter() - t0
+        cont = {"zstd_level": 9, "workers": nw, "seconds": tz_s, "raw_MB_per_s": raw_bytes / 1e6 / tz_s,
+                "ratio": raw_bytes / float(len(zb) + len(zk)),
+                "note": "single zstd frame with content size (what the reference decoder needs); not part of value/e2e"}
+
     if rank == 0:
         total_mb = world * raw_bytes / 1e6
         line = {
@@ -394,6 +428,7 @@ def run_native(args):
             "gpu_launches": int(launches), "gpu_launches_decompress": int(launches_d),
             "wall_ms_per_step": wall_c, "clocks": clocks, "max_abs_error_levels": maxerr,
             "roofline": roofline, "roofline_codec": roofline_codec, "cpu_baseline": cpu, "ratio": ratio,
+            "decompress_sweep": sweep, "container": cont,
             "prednet_gflop_per_frame": net.flops_per_frame() / 1e9,
         }
         print(json.dumps(line))
