@@ -120,6 +120,50 @@ __device__ __forceinline__ void ldg256(const float *p, float v[8]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster run ONE M256 MMA per instruction; each holds its own
+// 128 rows of A and half of the B tile, the leader (rank 0) issues, barriers are signalled across the pair.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta_rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_bar), "r"(cta_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-parity bit: the address then names the leader's smem
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {   // arrives on the same barrier offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ kernel arguments
 constexpr int TC_MAX_THREADS = 512;   // 4 role warps (producer, MMA, 2 idle) + up to 12 epilogue warps
 constexpr int TC_MAX_STAGES = 8;
@@ -198,7 +242,9 @@ __device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int EPI>  // 0: A path (pool + E), 1: R path (LSTM)
+// TWO = CTA-pair instantiation (launched as clusters of 2): kernels that contain cta_group::2 instructions can only
+// be launched with a matching cluster size, so the one-CTA modes use the TWO = false instantiation.
+template <int EPI, bool TWO>  // EPI 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,9 +262,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t afull0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1]);   // pair mode: 2 halo slots
   const uint32_t aempty0 = afull0 + 16;
 
+  constexpr bool two = TWO;                               // CTA-pair mode (launched as clusters of 2)
+  uint32_t crank = 0;                                     // 0 = leader (issues the MMAs)
+  if constexpr (TWO) crank = cluster_ctarank();
   const int tiles_img = P.tiles_w * P.tiles_h;
   const int tiles_b = (P.B + (1 << P.tb_log) - 1) >> P.tb_log;
-  const int n_tiles = tiles_img * tiles_b * P.n_tiles_n;
+  // scheduled units: (M tile, N tile) per CTA, or (pair of M tiles, N tile) per cluster; unit index steps by the
+  // number of CTAs / clusters.  m_of(t) is the M tile this CTA owns inside unit t.
+  const int n_tiles = two ? ((tiles_img * tiles_b + 1) >> 1) * P.n_tiles_n : tiles_img * tiles_b * P.n_tiles_n;
+  const int t_first = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kblocks = 9 * P.kchunks;
 
   if (threadIdx.x == 0) {
@@ -228,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < P.acc_stages; a++) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, (uint32_t)(P.epi_groups > 1 ? 4 : P.epi_warps));
+      mbar_init(tempty0 + 8 * a, (uint32_t)(two ? 2 * P.epi_warps : (P.epi_groups > 1 ? 4 : P.epi_warps)));
     }
     mbar_init(bfull, 1);
     for (int a = 0; a < 2; a++) {
@@ -239,13 +292,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"((uint32_t)TC_TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                   "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                   "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -266,15 +326,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * P.KC, n0);
       }
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = t_first; t < n_tiles; t += t_step) {
         const int nt = t % P.n_tiles_n;
         int mt = t / P.n_tiles_n;
+        if (two) mt = 2 * mt + (int)crank;
         const int twi = mt % P.tiles_w;
         mt /= P.tiles_w;
         const int thi = mt % P.tiles_h;
         const int tbi = mt / P.tiles_h;
         const int w0 = twi << P.tw_log, h0 = thi * P.tile_h, b0 = tbi << P.tb_log;
         const int n0 = nt * P.n_tile;
+        if constexpr (TWO) {
+          // CTA-pair mode: this CTA fetches the halo box of ITS M tile and ITS half of every weight block; all
+          // transaction bytes of the pair are counted on the leader's barriers (the leader alone waits on them).
+          int kc = 0;
+          const int nb0 = n0 + (int)crank * (P.n_tile >> 1);
+          for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
+            mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
+            if (crank == 0) mbar_expect_tx(afull0 + 8 * sl, 2 * P.a_tx);
+            tma2_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            sl ^= 1u;
+            pha ^= (sl == 0);
+            int kcoord = kc;
+            for (int tap = 0; tap < 9; tap++, kcoord += P.cin_pad) {
+              mbar_wait(empty0 + 8 * s, ph ^ 1u);
+              if (crank == 0) mbar_expect_tx(full0 + 8 * s, 2 * P.tx_bytes);
+              tma2_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, nb0);
+              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        } else {
         if (P.halo == 0) {
           // im2col mode: per (tap, chunk) one shifted activation box + one weight box
           int kcoord = 0;
@@ -319,12 +400,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        }   // one-CTA modes
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && crank == 0) {
       uint32_t s = 0, ph = 0, sl = 0, pha = 0;
       uint32_t a = 0, aph = 0;   // accumulator ring
       const uint32_t hi = P.desc_hi;
@@ -345,12 +427,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
       const bool dbg = P.dbg != nullptr;
       if (dbg) t_start = clock64();
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = t_first; t < n_tiles; t += t_step) {
         if (dbg) c0 = clock64();
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
         if (dbg) w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
+        if constexpr (TWO) {
+          // one M256 MMA per instruction: rows 0..127 from this CTA's halo box, rows 128..255 from the peer's (same
+          // smem offsets), B rows [0, N/2) from this CTA's stage, [N/2, N) from the peer's
+          uint32_t acc = 0;
+          for (int ch = 0; ch < P.kchunks; ch++) {
+            if (dbg) c0 = clock64();
+            mbar_wait(afull0 + 8 * sl, pha);
+            if (dbg) w_afull += clock64() - c0;
+            tc_fence_after();
+            const uint32_t a_base = (((smem0 + sl * P.a_slot) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+              if (dbg) c0 = clock64();
+              mbar_wait(full0 + 8 * s, ph);
+              if (dbg) w_full += clock64() - c0;
+              tc_fence_after();
+              const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;
+              const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                            acc | (uint32_t)(tap | k));
+              tc2_commit(empty0 + 8 * s);
+              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            }
+            acc = 1;
+            tc2_commit(aempty0 + 8 * sl);
+            sl ^= 1u;
+            pha ^= (sl == 0);
+          }
+          tc2_commit(tfull0 + 8 * a);
+          if (++a == (uint32_t)P.acc_stages) { a = 0; aph ^= 1u; }
+          continue;
+        }
         if (P.halo == 0) {
           uint32_t acc = 0;
           for (int kb = 0; kb < kblocks; kb++) {
@@ -444,10 +560,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
     const int tb = m >> (P.tw_log + P.th_log);
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tc++) {
+    for (int t = t_first; t < n_tiles; t += t_step, tc++) {
       if (P.epi_groups > 1 && (int)(tc % (uint32_t)P.epi_groups) != group) continue;   // another group's tile
       const int nt = t % P.n_tiles_n;
       int mt = t / P.n_tiles_n;
+      if (two) mt = 2 * mt + (int)crank;
       const int twi = mt % P.tiles_w;
       mt /= P.tiles_w;
       const int thi = mt % P.tiles_h;
@@ -595,15 +712,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }   // sub tiles
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(tempty0 + 8 * a, 0);   // the leader waits for both CTAs' epilogues
+        else mbar_arrive(tempty0 + 8 * a);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
-                 : "memory");
+    if constexpr (TWO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -809,6 +933,26 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       }
     }
   }
+  // ---- CTA-pair mode (cta_group::2): large weight matrices.  Clusters of two CTAs run M256 MMAs: each CTA holds the
+  // halo box of its own 8x16 M tile and HALF of every streamed weight block, so per SM both the TMA fill and the
+  // tensor core's shared-memory reads of B are halved (shared-memory bandwidth is what bounds the one-CTA modes).
+  if (!A.halo) {
+    const char *env = getenv("TZ_HALO");
+    const bool want2 = !(env && (env[0] == '0' || env[0] == '1' || env[0] == '3'));   // default; TZ_HALO=3: one-CTA pair mode
+    const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
+    if (want2 && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
+        (ntile_c % 16) == 0) {
+      A.halo = 4;
+      A.KC = 64;
+      A.kchunks = A.cin_pad / 64;
+      A.ksteps = 4;
+      A.tw_log = 3;
+      A.th_log = 4;
+      A.tb_log = 0;
+      A.tiles_w = (A.W + 7) >> 3;
+      A.tiles_h = (A.H + 15) >> 4;
+    }
+  }
   // ---- halo pair mode: large weight matrices, two stacked M tiles share every streamed weight block
   if (!A.halo) {
     // Measured on B200 (round 1, (3,48,96,192) net, B=100): with N tiles of <= 128 columns and two accumulator
@@ -902,7 +1046,17 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   }
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
-  if (A.halo == 2) {
+  if (A.halo == 4) {
+    A.a_tx = 10u * 18u * 128u;     // 18 image rows x 10 pixels x 64 channels fp16 (this CTA's M tile + halo)
+    A.a_slot = (A.a_tx + 1023u) & ~1023u;
+    A.a_stride = 0;
+    A.tx_bytes = (uint32_t)(A.n_tile / 2) * 128u;   // this CTA's half of a weight block
+    A.stage_stride = (A.tx_bytes + 1023u) & ~1023u;
+    stages = (int)((226u * 1024u - 1024u - 2u * A.a_slot) / A.stage_stride);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    A.stages = stages;
+    c->smem_bytes = 2u * A.a_slot + (uint32_t)stages * A.stage_stride + 1024u;
+  } else if (A.halo == 2) {
     A.a_tx = 10u * 34u * 128u;     // 34 image rows x 10 pixels x 64 channels fp16
     A.a_slot = (A.a_tx + 1023u) & ~1023u;
     A.a_stride = 0;
@@ -934,7 +1088,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.acc_stages = 2;
     A.acc_stride = 256;
     A.sub_stride = 0;
-    if (A.halo == 2) {
+    if (A.halo == 4) {
+      A.epi_groups = 1;
+      A.acc_stages = 2;
+      A.acc_stride = 256;
+    } else if (A.halo == 2) {
       if (A.n_tile <= 128) {   // pair = columns [0, N) and [128, 128 + N) of a 256-column stage; two stages
         A.acc_stages = 2;
         A.acc_stride = 256;
@@ -957,13 +1115,13 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   const uint32_t layout_type = A.KC == 64 ? 2u : A.KC == 32 ? 4u : 6u;   // UMMA SWIZZLE_128B / 64B / 32B
   const uint32_t sbo = 8u * row_bytes;                                   // 8-row core-matrix group stride
   A.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
-  A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | ((128u >> 4) << 24);   // f32 acc, f16 x f16, K-major
+  A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | (((A.halo == 4 ? 256u : 128u) >> 4) << 24);   // f32 acc, f16 x f16, K-major
   {
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
     cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
     cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
     if (A.halo) {   // (tile height + 2) image rows of 16 pixels each (8-wide tile + halo, padded to a 16-pixel pitch)
-      box[1] = (A.halo == 2) ? 10 : 16;
+      box[1] = (A.halo == 2 || A.halo == 4) ? 10 : 16;
       box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
     }
@@ -979,7 +1137,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows_total};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)A.KC, (cuuint32_t)A.n_tile};
+    cuuint32_t box[2] = {(cuuint32_t)A.KC, (cuuint32_t)(A.halo == 4 ? A.n_tile / 2 : A.n_tile)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&c->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->wpack, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1011,8 +1169,10 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   }
   T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
   if (!T->r0) return TZ_ENOMEM;
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
   for (int l = 0; l < L; l++) {
     // gate conv: reads all of X_l = [e_l | up(r_{l+1})]; the r_{t-1} slice of the kernel is hoisted into BM_l
@@ -1080,18 +1240,45 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   long long n_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b * A.n_tiles_n;
   int grid = n_tiles < T->sm_count ? (int)n_tiles : T->sm_count;
   if (A.halo == 1) grid = grid / A.n_tiles_n * A.n_tiles_n;   // a CTA keeps one N tile: its weights stay in shared memory
-  if (c->epi == 0)
-    conv_tc_kernel<0><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  if (A.halo == 4) {
+    // clusters of two CTAs; one (pair of M tiles, N tile) unit per cluster and iteration
+    long long m_tiles = (long long)A.tiles_w * A.tiles_h * tiles_b;
+    n_tiles = ((m_tiles + 1) / 2) * A.n_tiles_n;
+    int clusters = T->sm_count / 2;
+    if (n_tiles < clusters) clusters = (int)n_tiles;
+    grid = 2 * clusters;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128 + 32 * A.epi_warps);
+    cfg.dynamicSmemBytes = c->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, A)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, A);
+    if (e != cudaSuccess) {
+      set_error("cluster launch failed: %s", cudaGetErrorString(e));
+      return TZ_ECUDA;
+    }
+  } else if (c->epi == 0)
+    conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   else
-    conv_tc_kernel<1><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   TZ_CHECK_LAUNCH();
   if (dbg_on) {   // diagnostics only: synchronous
     long long hbuf[256 * 8];
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    const int issuers = A.halo == 4 ? grid / 2 : grid;
     fprintf(stderr, "[tz conv] epi %d halo %d H %d N %d kchunks %d: mma-thread cycles total %lld, wait tempty %lld, "
-            "wait full %lld, wait afull %lld (CTA 0; tiles/CTA ~%lld)\n", c->epi, A.halo, A.H, A.n_tile, A.kchunks,
-            hbuf[0], hbuf[1], hbuf[2], hbuf[3], (n_tiles + grid - 1) / grid);
+            "wait full %lld, wait afull %lld (CTA 0; units per issuing CTA ~%lld)\n", c->epi, A.halo, A.H, A.n_tile,
+            A.kchunks, hbuf[0], hbuf[1], hbuf[2], hbuf[3], (n_tiles + issuers - 1) / issuers);
   }
   return TZ_OK;
 }
