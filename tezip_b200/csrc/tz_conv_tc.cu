@@ -907,9 +907,27 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   } else {
     n_unit = largest_divisor_le(n_real, 256);
   }
+  // ---- experiment (TZ_HALO=5): CTA-pair mode also for the small-weight convs (channels rounded up to 64)
+  {
+    const char *env = getenv("TZ_HALO");
+    const int c64 = round_up(cin_real, 64);
+    const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
+    if (env && env[0] == '5' && c64 <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 && (ntile_c % 16) == 0) {
+      A.halo = 4;
+      A.cin_pad = c64;
+      A.KC = 64;
+      A.kchunks = c64 / 64;
+      A.ksteps = 4;
+      A.tw_log = 3;
+      A.th_log = 4;
+      A.tb_log = 0;
+      A.tiles_w = (A.W + 7) >> 3;
+      A.tiles_h = (A.H + 15) >> 4;
+    }
+  }
   // ---- halo + stationary-weights mode: small weight matrices only (they must fit in shared memory next to the
   // halo tiles), image width a multiple of the 8-pixel tile width.
-  {
+  if (!A.halo) {
     const char *env = getenv("TZ_HALO");
     const bool want = !(env && env[0] == '0');
     const int cin64 = A.cin_pad;            // channels read: cin rounded up to 16, walked in chunks of KC
