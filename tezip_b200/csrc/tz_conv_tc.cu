@@ -166,7 +166,7 @@ __device__ __forceinline__ void tc2_commit(uint32_t bar) {   // arrives on the s
 
 // ------------------------------------------------------------------------------------------------ kernel arguments
 constexpr int TC_MAX_THREADS = 512;   // 4 role warps (producer, MMA, 2 idle) + up to 12 epilogue warps
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_ACC = 8;       // TMEM accumulator stages (2 for wide tiles, up to 8 for narrow ones)
 constexpr int TC_TMEM_COLS = 512;
 
@@ -348,10 +348,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sl ^= 1u;
             pha ^= (sl == 0);
             int kcoord = kc;
-            for (int tap = 0; tap < 9; tap++, kcoord += P.cin_pad) {
+            for (int tg = 0; tg < 3; tg++) {   // one weight stage = the three taps of one filter row
               mbar_wait(empty0 + 8 * s, ph ^ 1u);
               if (crank == 0) mbar_expect_tx(full0 + 8 * s, 2 * P.tx_bytes);
-              tma2_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, nb0);
+              const uint32_t sb = pair_bbase + s * P.stage_stride;
+#pragma unroll
+              for (int j = 0; j < 3; j++, kcoord += P.cin_pad)
+                tma2_load_2d(sb + (uint32_t)j * P.b_block, &tmB, full0 + 8 * s, kcoord, nb0);
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
           }
@@ -444,17 +447,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t a_base = (((smem0 + sl * P.a_slot) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
-            for (int tap = 0; tap < 9; tap++) {
+            for (int tg = 0; tg < 3; tg++) {   // filter row tg: three taps per weight stage
               if (dbg) c0 = clock64();
               mbar_wait(full0 + 8 * s, ph);
               if (dbg) w_full += clock64() - c0;
               tc_fence_after();
-              const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;
-              const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+              const uint32_t b_base = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
-                            acc | (uint32_t)(tap | k));
+              for (int j = 0; j < 3; j++) {
+                const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                              acc | (uint32_t)(tg | j | k));
+              }
               tc2_commit(empty0 + 8 * s);
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
@@ -1068,8 +1075,9 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.a_tx = 10u * 18u * 128u;     // 18 image rows x 10 pixels x 64 channels fp16 (this CTA's M tile + halo)
     A.a_slot = (A.a_tx + 1023u) & ~1023u;
     A.a_stride = 0;
-    A.tx_bytes = (uint32_t)(A.n_tile / 2) * 128u;   // this CTA's half of a weight block
-    A.stage_stride = (A.tx_bytes + 1023u) & ~1023u;
+    A.b_block = (((uint32_t)(A.n_tile / 2) * 128u) + 1023u) & ~1023u;   // this CTA's half of one tap's weight block
+    A.tx_bytes = 3u * (uint32_t)(A.n_tile / 2) * 128u;                  // a stage holds one filter row (3 taps)
+    A.stage_stride = 3u * A.b_block;
     stages = (int)((226u * 1024u - 1024u - 2u * A.a_slot) / A.stage_stride);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     A.stages = stages;
