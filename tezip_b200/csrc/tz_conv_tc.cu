@@ -650,68 +650,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long pix = (long long)h * P.W + w;
         const float *bm = P.bm + pix * 4 * P.R + nt * P.NC;
         const float *c0 = P.c0 + pix * P.R + nt * P.NC;
-        for (int j0 = 8 * part; j0 < P.NC; j0 += 8 * nparts) {
+        // r for channels j0..j0+7 of this N tile -> fp16 into hv (or straight to the fp32 r_0 buffer at layer 0)
+        auto lstm_chunk = [&](int j0, __half *hv) {
           float vi[8], vf[8], vc[8], vo[8];
           tc_ld8(trow + 0 * P.NCp + j0, vi);
           tc_ld8(trow + 1 * P.NCp + j0, vf);
           tc_ld8(trow + 2 * P.NCp + j0, vc);
           tc_ld8(trow + 3 * P.NCp + j0, vo);
           tc_ld_wait();
-          if (valid) {
-            float r[8];
-            if (P.bm_packed) {
-              const float *bp = P.bm + (pix * (P.R >> 3) + ((nt * P.NC + j0) >> 3)) * 32;
-              float bq[32], cq[8];
-              ldg256(bp, bq);
-              ldg256(bp + 8, bq + 8);
-              ldg256(bp + 16, bq + 16);
-              ldg256(bp + 24, bq + 24);
-              ldg256(c0 + j0, cq);
+          if (!valid) return;
+          float r[8];
+          if (P.bm_packed) {
+            const float *bp = P.bm + (pix * (P.R >> 3) + ((nt * P.NC + j0) >> 3)) * 32;
+            float bq[32], cq[8];
+            ldg256(bp, bq);
+            ldg256(bp + 8, bq + 8);
+            ldg256(bp + 16, bq + 16);
+            ldg256(bp + 24, bq + 24);
+            ldg256(c0 + j0, cq);
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const float gi = hsig(__fadd_rn(vi[j], bq[j]));
-                const float gf = hsig(__fadd_rn(vf[j], bq[8 + j]));
-                const float gc = fast_tanh(__fadd_rn(vc[j], bq[16 + j]));
-                const float go = hsig(__fadd_rn(vo[j], bq[24 + j]));
-                const float c = __fadd_rn(__fmul_rn(gf, cq[j]), __fmul_rn(gi, gc));
+            for (int j = 0; j < 8; j++) {
+              const float gi = hsig(__fadd_rn(vi[j], bq[j]));
+              const float gf = hsig(__fadd_rn(vf[j], bq[8 + j]));
+              const float gc = fast_tanh(__fadd_rn(vc[j], bq[16 + j]));
+              const float go = hsig(__fadd_rn(vo[j], bq[24 + j]));
+              const float c = __fadd_rn(__fmul_rn(gf, cq[j]), __fmul_rn(gi, gc));
+              r[j] = __fmul_rn(go, fast_tanh(c));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              if (j0 + j < P.NC) {
+                const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
+                const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
+                const float gc = fast_tanh(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
+                const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
+                const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
                 r[j] = __fmul_rn(go, fast_tanh(c));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                if (j0 + j < P.NC) {
-                  const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
-                  const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
-                  const float gc = fast_tanh(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
-                  const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
-                  const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
-                  r[j] = __fmul_rn(go, fast_tanh(c));
-                } else {
-                  r[j] = 0.0f;
-                }
+              } else {
+                r[j] = 0.0f;
               }
             }
-            const int ch0 = nt * P.NC + j0;
-            if (P.xr_out) {
-              // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
-              const int H2 = P.H * 2, W2 = P.W * 2;
-              const bool vec = (j0 + 8 <= P.NC) && (((P.xr_coff + ch0) | P.xr_cstride) & 7) == 0;
-              __align__(16) __half hv[8];
+          }
+          if (P.xr_out) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) hv[j] = __float2half_rn(r[j]);
+            for (int j = 0; j < 8; j++) hv[j] = __float2half_rn(r[j]);
+          } else {
+            float *dst = P.r0_out + ((long long)b * P.H * P.W + pix) * P.R + nt * P.NC + j0;
+            for (int j = 0; j < 8 && j0 + j < P.NC; j++) dst[j] = r[j];
+          }
+        };
+        // two adjacent 8-channel chunks per pass, so that the up-sampled store is 32 bytes wide where alignment allows
+        for (int jp = 16 * part; jp < P.NC; jp += 16 * nparts) {
+          __align__(32) __half hv[16];
+          const bool second = jp + 8 < P.NC;
+          lstm_chunk(jp, hv);
+          if (second) lstm_chunk(jp + 8, hv + 8);
+          if (valid && P.xr_out) {
+            // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
+            const int H2 = P.H * 2, W2 = P.W * 2;
+            const int ch0 = nt * P.NC + jp;
+            const bool v32 = (jp + 16 <= P.NC) && (((P.xr_coff + ch0) | P.xr_cstride) & 15) == 0;
+            const bool v16a = (jp + 8 <= P.NC) && (((P.xr_coff + ch0) | P.xr_cstride) & 7) == 0;
+            const bool v16b = (jp + 16 <= P.NC) && (((P.xr_coff + ch0 + 8) | P.xr_cstride) & 7) == 0;
 #pragma unroll
-              for (int q = 0; q < 4; q++) {
-                __half *dst = P.xr_out + (((long long)b * H2 + 2 * h + (q >> 1)) * W2 + 2 * w + (q & 1)) * P.xr_cstride +
-                              P.xr_coff + ch0;
-                if (vec) {
-                  *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hv);
-                } else {
-                  for (int j = 0; j < 8 && j0 + j < P.NC; j++) dst[j] = hv[j];
+            for (int q = 0; q < 4; q++) {
+              __half *dst = P.xr_out + (((long long)b * H2 + 2 * h + (q >> 1)) * W2 + 2 * w + (q & 1)) * P.xr_cstride +
+                            P.xr_coff + ch0;
+              if (v32) {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(hv), hi4 = *reinterpret_cast<const uint4 *>(hv + 8);
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y),
+                             "r"(lo.z), "r"(lo.w), "r"(hi4.x), "r"(hi4.y), "r"(hi4.z), "r"(hi4.w)
+                             : "memory");
+              } else {
+                if (v16a) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hv);
+                else for (int j = 0; j < 8 && jp + j < P.NC; j++) dst[j] = hv[j];
+                if (second) {
+                  if (v16b) *reinterpret_cast<uint4 *>(dst + 8) = *reinterpret_cast<const uint4 *>(hv + 8);
+                  else for (int j = 8; j < 16 && jp + j < P.NC; j++) dst[j] = hv[j];
                 }
               }
-            } else {
-              float *dst = P.r0_out + ((long long)b * P.H * P.W + pix) * P.R + ch0;
-              for (int j = 0; j < 8 && j0 + j < P.NC; j++) dst[j] = r[j];
             }
           }
         }
@@ -827,7 +845,7 @@ struct TcState {
   int L;
   __half *X[TZ_MAX_LAYERS];   // X_l: [maxB, H_l, W_l, cx[l]] fp16: [e_l | up(r_{l+1}) | zero pad]
   int cx[TZ_MAX_LAYERS];
-  int epad[TZ_MAX_LAYERS];    // channel offset of the up(r_{l+1}) block: 2*S_l rounded up to 8 (16-byte stores)
+  int epad[TZ_MAX_LAYERS];    // channel offset of the up(r_{l+1}) block: 2*S_l rounded up to 16 (32-byte stores)
   float *r0;                  // [maxB, H_0, W_0, R_0] fp32
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
@@ -1108,7 +1126,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     c->smem_bytes = A.b_region + (uint32_t)stages * A.stage_stride + 1024u;
   }
   {
-    const int nchunks = (epi == 1) ? (A.NC + 7) / 8 : (A.n_tile + 7) / 8;
+    // work items per tile that the epilogue warps share out: 8-channel chunks (A path) / 16-channel pairs (R path)
+    const int nchunks = (epi == 1) ? (A.NC + 15) / 16 : (A.n_tile + 7) / 8;
     A.epi_warps = nchunks >= 3 ? 12 : nchunks >= 2 ? 8 : 4;
     A.epi_groups = 1;
     A.acc_stages = 2;
@@ -1186,7 +1205,7 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   const int mb = h->cfg.max_batch;
   for (int l = 0; l < L; l++) {
     TZ_REQUIRE(h->H[l] % 2 == 0 || l == L - 1, "tensor-core path: odd layer height");
-    T->epad[l] = round_up(2 * h->S[l], 8);
+    T->epad[l] = round_up(2 * h->S[l], 16);   // 32-byte aligned r_up block
     T->cx[l] = round_up(T->epad[l] + (l < L - 1 ? h->R[l + 1] : 0), 16);
     size_t bytes = (size_t)mb * h->H[l] * h->W[l] * T->cx[l] * sizeof(__half);
     T->X[l] = (__half *)dev_alloc(h, bytes);
