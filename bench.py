@@ -209,10 +209,8 @@ def run_native(args):
         return codec.encode_frames(frames_dev, net, 0, Wn, None, mode, bound, True, comm=comm)
 
     def compress_e2e():
-        fd = frames_host.to(dev, non_blocking=True)
-        enc = codec.encode_frames(fd, net, 0, Wn, None, mode, bound, True, comm=comm)
-        body_host.copy_(enc.body, non_blocking=True)
-        keyp_host.copy_(enc.key_plane, non_blocking=True)
+        enc = codec.encode_frames_host(frames_host, net, 0, Wn, None, mode, bound, keyp_host, body_host, True,
+                                       comm=comm)
         if comm is not None:
             comm.stream_offsets(enc.body.numel())
         torch.cuda.synchronize(dev)
@@ -226,10 +224,8 @@ def run_native(args):
                                    first_x=first_x)[0]
 
     def decompress_e2e():
-        kp = keyp_host.to(dev, non_blocking=True)
-        bd = body_host.to(dev, non_blocking=True)
-        out = codec.decode_arrays(kp, bd, enc0.table, enc0.shape, 0, net, first_mode=first_mode, first_x=first_x)[0]
-        out_host.copy_(out, non_blocking=True)
+        out, _plan = codec.decode_arrays_host(keyp_host, body_host, enc0.table, enc0.shape, 0, net, out_host,
+                                              first_mode=first_mode, first_x=first_x)
         torch.cuda.synchronize(dev)
         return out
 

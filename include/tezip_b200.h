@@ -120,8 +120,8 @@ int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long
                    int C, int mode, double b0, double b1, void *stream);
 
 /* finding_difference (compress.py:73-77) fused with the symbol histogram (compress.py:348-355):
- * y[i] = x[i-1] - x[i]; y[0] = x[0] if has_prev == 0 else prev_x - x[0] (prev_x = last x of the previous
- * shard).  hist[s] += 1 for s = 1600 - y.  hist: device u64[TZ_HIST_BINS], caller-zeroed.
+ * y[i] = x[i-1] - x[i]; y[0] = x[0] if has_prev == 0; prev_x - x[0] if has_prev == 1 (prev_x = last x of the
+ * previous shard); x[-1] - x[0] if has_prev == 2 (x points into a longer device stream: chunked calls).  hist[s] += 1 for s = 1600 - y.  hist: device u64[TZ_HIST_BINS], caller-zeroed.
  * overflow: device u64[1], caller-zeroed, counts symbols outside [0, TZ_HIST_BINS). */
 int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsigned long long *hist,
                   unsigned long long *overflow, void *stream);

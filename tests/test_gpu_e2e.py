@@ -133,3 +133,30 @@ def test_ratio_vs_oracle_full_net(cuda_lib):
         b = len(container.zstd_compress(r["payload"])) + len(container.zstd_compress(r["key_plane"]))
         assert a <= b / 0.95, (a, b)
     net.close()
+
+
+def test_host_buffer_api_matches_device_api(cuda_lib):
+    """encode_frames_host / decode_arrays_host (pinned host buffers, pipelined copies, chunked rank map) give the
+    same stream and frames as the device-resident API."""
+    import torch
+    from tezip_b200 import codec
+    stack, H, W, nt = TINY, 24, 40, 17
+    _o, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, 24, 40, max_batch=8)
+    frames = synth.make_frames(nt, H, W, 3, seed=41)
+    fh = torch.from_numpy(frames).pin_memory()
+    for mode, bound in (("abs", [0.0]), ("abs", [2.0])):
+        ref = codec.encode_frames(fh.cuda(), net, 1, 4, None, mode, bound, True)
+        key_host = torch.empty_like(fh).pin_memory()
+        body_host = torch.empty(frames.size, dtype=torch.int16).pin_memory()
+        enc = codec.encode_frames_host(fh, net, 1, 4, None, mode, bound, key_host, body_host, True, chunks=3)
+        torch.cuda.synchronize()
+        assert np.array_equal(body_host.numpy(), ref.body.cpu().numpy())
+        assert np.array_equal(key_host.numpy(), ref.key_plane.cpu().numpy())
+        assert np.array_equal(enc.table, ref.table)
+        out_host = torch.empty_like(fh).pin_memory()
+        codec.decode_arrays_host(key_host, body_host, enc.table, enc.shape, 1, net, out_host)
+        torch.cuda.synchronize()
+        err = np.abs(out_host.numpy().astype(int) - frames.astype(int)).max()
+        assert err <= (0 if bound == [0.0] else 2)
+    net.close()

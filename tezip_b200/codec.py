@@ -181,6 +181,44 @@ def pack_payload(body, table, shape, p):
     return np.concatenate([np.asarray(body, np.int16), np.array(tail, np.int64).astype(np.int16)])  # :394
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device):
+    """One cached copy stream per device (creating streams per call costs more than the copies it hides)."""
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+class HostSink:
+    """Streams the results of an encode to pinned host buffers while the GPU keeps working: the key plane as soon as
+    the schedule is known (before any PredNet step), the int16 stream in chunks as the rank-map kernel produces them.
+    Copies run on a side stream; `finish()` makes the current stream wait for them."""
+
+    def __init__(self, key_host, body_host, device, chunks=4):
+        self.key_host, self.body_host, self.chunks = key_host, body_host, max(1, int(chunks))
+        self.device = device
+        self.stream = side_stream(device)
+
+    def _after_current(self):
+        self.stream.wait_event(torch.cuda.current_stream(self.device).record_event())
+
+    def key_plane(self, t):
+        self._after_current()
+        with torch.cuda.stream(self.stream):
+            self.key_host.view(-1).copy_(t.view(-1), non_blocking=True)
+
+    def body_chunk(self, t, a, b):
+        self._after_current()
+        with torch.cuda.stream(self.stream):
+            self.body_host[a:b].copy_(t[a:b], non_blocking=True)
+
+    def finish(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def is_lossless(mode, bound):
     """compress.py:24,35: BOUND_VALUE[0] == 0 (or absrel with BOUND_VALUE[1] == 0) leaves diff untouched."""
     return float(bound[0]) == 0.0 or (mode == "absrel" and float(bound[1]) == 0.0)
@@ -191,7 +229,7 @@ def pool_slots_upper_bound(nt):
 
 
 def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
-                  keep_x=False, comm=None):
+                  keep_x=False, comm=None, sink=None):
     """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
 
     comm: optional shard communicator (tezip_b200/dist.py) when `frames` is one rank's window-aligned shard of a
@@ -217,11 +255,11 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
     return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
-                            comm)
+                            comm, sink)
 
 
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
-                     keep_x=False, comm=None):
+                     keep_x=False, comm=None, sink=None):
     """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map."""
     nt, H, W, C = frames.shape
     dev = frames.device
@@ -229,6 +267,8 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
     is_key = np.zeros(nt, np.uint8)
     is_key[list(keys)] = 1
     key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))                  # compress.py:183-263
+    if sink is not None:
+        sink.key_plane(key_plane)
     N = nt * H * W * C
     body = torch.empty(N, dtype=torch.int16, device=dev)
     table = None
@@ -265,10 +305,26 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         lut = torch.from_numpy(ops.encode_lut(table)).to(dev)
     else:
         lut = None
-    if x is not None:
-        ops.finding_difference_rank(x, lut, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
+    if x is not None and sink is not None and sink.chunks > 1:
+        # rank map in chunks so that the device->host copy of chunk i overlaps the kernel of chunk i+1
+        xf = x.view(-1)
+        step = -(-N // sink.chunks) // 8 * 8 + 8
+        for a in range(0, N, step):
+            b = min(N, a + step)
+            if a == 0:
+                ops.finding_difference_rank(xf[a:b], lut, out=body[a:b], has_prev=has_prev, prev_x=prev_x)
+            else:
+                ops.finding_difference_rank(xf[a:b], lut, out=body[a:b], has_prev=2)      # y[a] = x[a-1] - x[a]
+            sink.body_chunk(body, a, b)
     else:
-        ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut, out=body, has_prev=has_prev, prev_x=prev_x)
+        if x is not None:
+            ops.finding_difference_rank(x, lut, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
+        else:
+            ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut, out=body, has_prev=has_prev, prev_x=prev_x)
+        if sink is not None:
+            sink.body_chunk(body, 0, N)
+    if sink is not None:
+        sink.finish()
     return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),
                    pool if keep_pool else None, x if keep_x else None)
 
@@ -291,8 +347,10 @@ def parse_payload(data):
     return data[:table_start], data[table_start:-1].copy(), shape, p
 
 
-def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0):
-    """decompress.py:115-256,269 on device tensors: key_plane u8 [nt,H,W,C], body int16 [N] -> u8 frames."""
+def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0, body_event=None):
+    """decompress.py:115-256,269 on device tensors: key_plane u8 [nt,H,W,C], body int16 [N] -> u8 frames.
+    body_event: optional CUDA event after which `body` is valid (its host->device copy may still be in flight on
+    another stream while the predictions are replayed; only the final reconstruct needs it)."""
     _one, nt, H, W, C = shape
     dev = key_plane.device
     Hp, Wp = padding_size(H), padding_size(W)
@@ -312,5 +370,36 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
         tl = len(table)
     else:
         lut, tl = None, -1
+    if body_event is not None:
+        torch.cuda.current_stream(dev).wait_event(body_event)
     return ops.reconstruct(body, (nt, H, W, C), Hp, Wp, tl, lut, pool, pred_slot, key_plane, first_mode, first_x,
                            want_x=want_x), plan
+
+
+def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_host, body_host, entropy=True,
+                       dwp_chains=1, comm=None, chunks=4):
+    """Host-buffer API: frames_host u8 [nt,H,W,C] (pinned) -> key_host u8 (pinned, same shape), body_host int16 [N]
+    (pinned).  The H2D copy, the kernels and the D2H copies are pipelined; returns the Encoded record (table, keys)
+    after the copies have been ordered on the current stream (synchronise before reading the host buffers)."""
+    dev = net.device
+    frames = frames_host.to(dev, non_blocking=True)
+    sink = HostSink(key_host, body_host, dev, chunks)
+    return encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink)
+
+
+def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, first_mode=0, first_x=0):
+    """Host-buffer API of the decoder: the key plane goes first (the prediction replay needs it), the int16 stream
+    follows on a side stream while PredNet runs, the frames come back at the end."""
+    dev = net.device
+    main = torch.cuda.current_stream(dev)
+    key_plane = key_host.to(dev, non_blocking=True)
+    body = torch.empty(body_host.numel(), dtype=torch.int16, device=dev)   # allocated on the main stream's pool
+    side = side_stream(dev)
+    side.wait_event(main.record_event())      # after the key plane copy (same copy engine) and any earlier use of `body`
+    with torch.cuda.stream(side):
+        body.copy_(body_host, non_blocking=True)
+        ev = side.record_event()
+    out, plan = decode_arrays(key_plane, body, table, shape, p, net, first_mode=first_mode, first_x=first_x,
+                              body_event=ev)
+    out_host.copy_(out, non_blocking=True)
+    return out, plan

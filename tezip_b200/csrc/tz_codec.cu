@@ -312,10 +312,10 @@ __global__ void __launch_bounds__(128) error_bound_kernel(const uint8_t *__restr
 template <int SRC>
 __device__ __forceinline__ void fetch8(const int16_t *__restrict__ x, const uint8_t *__restrict__ frames,
                                        const float *__restrict__ pool, const int32_t *__restrict__ slot,
-                                       const Geo &g, long long i0, long long n, int v[8], int &prev) {
+                                       const Geo &g, long long i0, long long n, int v[8], int &prev, int has_prev) {
   if (SRC == 0) {
     load8_i16(x, i0, n, v);
-    prev = (i0 > 0) ? (int)x[i0 - 1] : 0;
+    prev = (i0 > 0 || has_prev == 2) ? (int)x[i0 - 1] : 0;   // has_prev == 2: x points into a longer stream
   } else {
     resid8<SRC == 2>(frames, pool, slot, g, i0, n, v);
     prev = (i0 > 0) ? resid_at(frames, pool, slot, g, i0 - 1) : 0;
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restri
        gi += (long long)gridDim.x * blockDim.x) {
     long long i0 = gi * 8;
     int v[8], y[8], prev;
-    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev);
-    if (i0 == 0 && has_prev) prev = prev_x;
+    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
+    if (i0 == 0 && has_prev == 1) prev = prev_x;
     delta8(v, prev, i0 == 0 && !has_prev, y);
     int cur = -1, cnt = 0;
 #pragma unroll
@@ -391,8 +391,8 @@ __global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restri
        gi += (long long)gridDim.x * blockDim.x) {
     long long i0 = gi * 8;
     int v[8], y[8], prev;
-    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev);
-    if (i0 == 0 && has_prev) prev = prev_x;
+    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
+    if (i0 == 0 && has_prev == 1) prev = prev_x;
     delta8(v, prev, i0 == 0 && !has_prev, y);
     if (lut) {
 #pragma unroll

@@ -69,6 +69,8 @@ def finding_difference_rank(x, lut, out=None, has_prev=False, prev_x=0):
     """compress.py:73-77 + replacing_based_on_frequency (:84-90); lut None -> the raw delta stream."""
     if out is None:
         out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+    if out is not None and out.numel() != x.numel():
+        raise ValueError("out must have as many elements as x")
     check(_lib.load().tz_delta_rank(ptr(x), x.numel(), int(has_prev), int(prev_x), ptr(lut), ptr(out),
                                     _st(x.device)), "tz_delta_rank")
     return out
