@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--bound", type=float, nargs="*", default=[2.0])
     ap.add_argument("--cpu-sample-frames", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dwp", action="store_true",
+                    help="BASELINE config 3: dynamic windows (-t T, T calibrated as SURVEY 8(d)) instead of -w; "
+                         "--chains sub-ranges per GPU run as a batch, each starting with a forced key frame")
+    ap.add_argument("--chains", type=int, default=100)
     return ap.parse_args()
 
 
@@ -205,12 +209,22 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    thr, chains, win = None, 1, Wn
+    if args.dwp:
+        # T = mean cumulative window MSE at step Wn of an unbounded window (first 2*Wn frames), SURVEY 8(d)
+        pool_c = torch.empty((2 * Wn + 2, H, W, C), dtype=torch.float32, device=dev)
+        _k, slot_c, _a, _n = codec.run_dwp(net, frames_dev[:2 * Wn].contiguous(), 0, 1e30, pool_c, 1)
+        idx = torch.arange(1, Wn + 1, dtype=torch.int32, device=dev)
+        sse = ops.window_sse(frames_dev, idx, pool_c[torch.from_numpy(slot_c[1:Wn + 1].astype(np.int64)).to(dev)])
+        thr = float(sse.sum().item() / (Wn * H * W * C))
+        chains, win = args.chains, None
+
     def compress_dev():
-        return codec.encode_frames(frames_dev, net, 0, Wn, None, mode, bound, True, comm=comm)
+        return codec.encode_frames(frames_dev, net, 0, win, thr, mode, bound, True, dwp_chains=chains, comm=comm)
 
     def compress_e2e():
-        enc = codec.encode_frames_host(frames_host, net, 0, Wn, None, mode, bound, keyp_host, body_host, True,
-                                       comm=comm)
+        enc = codec.encode_frames_host(frames_host, net, 0, win, thr, mode, bound, keyp_host, body_host, True,
+                                       dwp_chains=chains, comm=comm)
         if comm is not None:
             comm.stream_offsets(enc.body.numel())
         torch.cuda.synchronize(dev)
@@ -411,7 +425,10 @@ def run_native(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_c, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 x f16 -> f32 (PredNet, tcgen05); int16/f64 codec",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": nt, "windows_in_flight": Bk,
+            "config": {"workload": WORKLOAD if not args.dwp else WORKLOAD.replace(
+                           "SWP window 10", "DWP threshold %.6g (calibrated), %d chains per GPU, %d key frames" %
+                           (thr, chains, len(enc0.keys))),
+                       "frames_per_gpu": nt, "windows_in_flight": Bk,
                        "boundary": "packed int16 stream + key plane, before zstd",
                        "l2": "no explicit flush: one step streams ~%.1f GB (prediction pool + activations) >> 126 MB L2"
                              % ((enc_keep.pool.numel() * 4 + net.device_bytes()) / 1e9),
