@@ -86,6 +86,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
       : "memory");
 }
 
+// one lane of a converged warp (elect.sync): the canonical way to issue single-thread tcgen05 / TMA instructions from
+// warp-uniform code -- descriptors computed by all lanes stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -409,7 +420,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && crank == 0) {
+    // The whole warp walks the loop (waits, ring state, descriptors are warp-uniform); one elected lane issues.
+    if (crank == 0) {
       uint32_t s = 0, ph = 0, sl = 0, pha = 0;
       uint32_t a = 0, aph = 0;   // accumulator ring
       const uint32_t hi = P.desc_hi;
@@ -428,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // halo mode: block kb = tap * kchunks + chunk
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
-      const bool dbg = P.dbg != nullptr;
+      const bool dbg = P.dbg != nullptr && lane == 0;
       if (dbg) t_start = clock64();
       for (int t = t_first; t < n_tiles; t += t_step) {
         if (dbg) c0 = clock64();
@@ -453,24 +465,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (dbg) w_full += clock64() - c0;
               tc_fence_after();
               const uint32_t b_base = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 3; j++) {
-                const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
-                const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+                for (int j = 0; j < 3; j++) {
+                  const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                  const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                  tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
-                              acc | (uint32_t)(tg | j | k));
+                  for (int k = 0; k < 4; k++)
+                    tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                                acc | (uint32_t)(tg | j | k));
+                }
+                tc2_commit(empty0 + 8 * s);
               }
-              tc2_commit(empty0 + 8 * s);
+              __syncwarp();
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
             acc = 1;
-            tc2_commit(aempty0 + 8 * sl);
+            if (elect_one()) tc2_commit(aempty0 + 8 * sl);
+            __syncwarp();
             sl ^= 1u;
             pha ^= (sl == 0);
           }
-          tc2_commit(tfull0 + 8 * a);
+          if (elect_one()) tc2_commit(tfull0 + 8 * a);
+          __syncwarp();
           if (++a == (uint32_t)P.acc_stages) { a = 0; aph ^= 1u; }
           continue;
         }
@@ -485,16 +502,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t alo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t blo = (((sa + P.a_stride) >> 4) & 0x3FFFu) | (1u << 16);
             // advance 32 bytes (16 fp16 of K) inside the swizzled row per MMA
-            if (P.ksteps == 4) {
+            if (elect_one()) {
+              if (P.ksteps == 4) {
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
-            } else {
-              for (int k = 0; k < P.ksteps; k++)
-                tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
+                for (int k = 0; k < 4; k++)
+                  tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
+              } else {
+                for (int k = 0; k < P.ksteps; k++)
+                  tc_mma_f16(d_tmem, make_desc(alo + 2 * k, hi), make_desc(blo + 2 * k, hi), idesc, acc | (uint32_t)k);
+              }
+              tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
             }
+            __syncwarp();
             acc = 1;
-            tc_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
           }
         } else if (P.halo == 1) {
@@ -504,13 +524,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
             const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t b_lo = (((smem0 + (uint32_t)ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-            if (P.ksteps == 4)
-              issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-            else if (P.ksteps == 2)
-              issue_halo_chunk<2>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-            else
-              issue_halo_chunk<1>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-            tc_commit(empty0 + 8 * s);   // halo slot free once its MMAs retire
+            if (elect_one()) {
+              if (P.ksteps == 4)
+                issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+              else if (P.ksteps == 2)
+                issue_halo_chunk<2>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+              else
+                issue_halo_chunk<1>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+              tc_commit(empty0 + 8 * s);   // halo slot free once its MMAs retire
+            }
+            __syncwarp();
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
           }
         } else {
@@ -529,22 +552,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_fence_after();
               const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;   // 128 B per halo pixel
               const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
+              if (elect_one()) {
 #pragma unroll
-              for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 20480 bytes further down the halo
+                for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 20480 bytes further down the halo
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                  tc_mma_f16(d_tmem + sub * (uint32_t)P.sub_stride, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
-                             make_desc(b_lo + 2 * k, hi), idesc, acc | (uint32_t)(tap | k));
-              tc_commit(empty0 + 8 * s);
+                  for (int k = 0; k < 4; k++)
+                    tc_mma_f16(d_tmem + sub * (uint32_t)P.sub_stride, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
+                               make_desc(b_lo + 2 * k, hi), idesc, acc | (uint32_t)(tap | k));
+                tc_commit(empty0 + 8 * s);
+              }
+              __syncwarp();
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
             acc = 1;
-            tc_commit(aempty0 + 8 * sl);
+            if (elect_one()) tc_commit(aempty0 + 8 * sl);
+            __syncwarp();
             sl ^= 1u;
             pha ^= (sl == 0);
           }
         }
-        tc_commit(tfull0 + 8 * a);    // accumulator complete
+        if (elect_one()) tc_commit(tfull0 + 8 * a);    // accumulator complete
+        __syncwarp();
         if (++a == (uint32_t)P.acc_stages) { a = 0; aph ^= 1u; }
       }
       if (dbg) {
