@@ -326,15 +326,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // runtime divisions and 64-bit descriptor arithmetic per MMA cost more than the MMA itself).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // (whole warp walks the loop with warp-uniform state; one elected lane issues the TMA instructions)
+    {
       uint32_t s = 0, ph = 0;      // main ring (im2col: A+B stages; halo: halo slots; pair: weight stages)
       uint32_t sl = 0, pha = 0;    // pair mode: halo slot ring
       if (P.halo == 1 && (int)blockIdx.x < n_tiles) {
         // Halo mode: the whole weight matrix of this CTA's N tile stays resident in shared memory (loaded once)
         const int n0 = ((int)blockIdx.x % P.n_tiles_n) * P.n_tile;
-        mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * (uint32_t)(2 * P.KC));
-        for (int kb = 0; kb < kblocks; kb++)   // block kb = tap * kchunks + chunk
-          tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * P.KC, n0);
+        if (elect_one()) {
+          mbar_expect_tx(bfull, (uint32_t)kblocks * (uint32_t)P.n_tile * (uint32_t)(2 * P.KC));
+          for (int kb = 0; kb < kblocks; kb++)   // block kb = tap * kchunks + chunk
+            tma_load_2d(smem0 + kb * P.b_block, &tmB, bfull, kb * P.KC, n0);
+        }
+        __syncwarp();
       }
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       for (int t = t_first; t < n_tiles; t += t_step) {
@@ -354,18 +358,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nb0 = n0 + (int)crank * (P.n_tile >> 1);
           for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
             mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
-            if (crank == 0) mbar_expect_tx(afull0 + 8 * sl, 2 * P.a_tx);
-            tma2_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            if (elect_one()) {
+              if (crank == 0) mbar_expect_tx(afull0 + 8 * sl, 2 * P.a_tx);
+              tma2_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            }
+            __syncwarp();
             sl ^= 1u;
             pha ^= (sl == 0);
             int kcoord = kc;
             for (int tg = 0; tg < 3; tg++) {   // one weight stage = the three taps of one filter row
               mbar_wait(empty0 + 8 * s, ph ^ 1u);
-              if (crank == 0) mbar_expect_tx(full0 + 8 * s, 2 * P.tx_bytes);
-              const uint32_t sb = pair_bbase + s * P.stage_stride;
+              if (elect_one()) {
+                if (crank == 0) mbar_expect_tx(full0 + 8 * s, 2 * P.tx_bytes);
+                const uint32_t sb = pair_bbase + s * P.stage_stride;
 #pragma unroll
-              for (int j = 0; j < 3; j++, kcoord += P.cin_pad)
-                tma2_load_2d(sb + (uint32_t)j * P.b_block, &tmB, full0 + 8 * s, kcoord, nb0);
+                for (int j = 0; j < 3; j++)
+                  tma2_load_2d(sb + (uint32_t)j * P.b_block, &tmB, full0 + 8 * s, kcoord + j * P.cin_pad, nb0);
+              }
+              __syncwarp();
+              kcoord += 3 * P.cin_pad;
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
           }
@@ -377,11 +388,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int dx = -1; dx <= 1; dx++)
               for (int c = 0; c < P.cin_pad; c += P.KC) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const uint32_t full = full0 + 8 * s;
-                mbar_expect_tx(full, P.tx_bytes);
-                const uint32_t sa = smem0 + s * P.stage_stride;
-                tma_load_4d(sa, &tmA, full, c, w0 + dx, h0 + dy, b0);
-                tma_load_2d(sa + P.a_stride, &tmB, full, kcoord, n0);
+                if (elect_one()) {
+                  const uint32_t full = full0 + 8 * s;
+                  mbar_expect_tx(full, P.tx_bytes);
+                  const uint32_t sa = smem0 + s * P.stage_stride;
+                  tma_load_4d(sa, &tmA, full, c, w0 + dx, h0 + dy, b0);
+                  tma_load_2d(sa + P.a_stride, &tmB, full, kcoord, n0);
+                }
+                __syncwarp();
                 kcoord += P.KC;
                 if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
               }
@@ -389,9 +403,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // halo mode: per chunk ONE box of (TH+2) x 16 pixels; the nine taps read it through shifted descriptors
           for (int c = 0; c < P.cin_pad; c += P.KC) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            const uint32_t full = full0 + 8 * s;
-            mbar_expect_tx(full, P.tx_bytes);
-            tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
+            if (elect_one()) {
+              const uint32_t full = full0 + 8 * s;
+              mbar_expect_tx(full, P.tx_bytes);
+              tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
+            }
+            __syncwarp();
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
           }
         } else {
@@ -401,15 +418,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int kc = 0;
           for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
             mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
-            mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
-            tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            if (elect_one()) {
+              mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
+              tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
+            }
+            __syncwarp();
             sl ^= 1u;
             pha ^= (sl == 0);
             int kcoord = kc;
             for (int tap = 0; tap < 9; tap++, kcoord += P.cin_pad) {
               mbar_wait(empty0 + 8 * s, ph ^ 1u);
-              mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
-              tma_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, n0);
+              if (elect_one()) {
+                mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
+                tma_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, n0);
+              }
+              __syncwarp();
               if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
           }
