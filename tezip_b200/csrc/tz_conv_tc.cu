@@ -542,7 +542,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if (P.halo == 1) {
           for (int ch = 0; ch < P.kchunks; ch++) {
+            if (dbg) c0 = clock64();
             mbar_wait(full0 + 8 * s, ph);
+            if (dbg) w_full += clock64() - c0;
             tc_fence_after();
             const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
             const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
