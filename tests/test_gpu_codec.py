@@ -95,6 +95,56 @@ def test_error_bound_random_planes(cuda_lib):
         assert np.array_equal(x.cpu().numpy().astype(np.int64), ref), (mode, bound)
 
 
+@pytest.mark.parametrize("hw", [(1, 1), (3, 11), (64, 32), (41, 50), (70, 93), (128, 160)],
+                         ids=lambda hw: "%dx%d" % hw)
+def test_error_bound_tiled_planes(cuda_lib, hw):
+    """The tiled error-bound kernel (2048-element tiles, 32-element chunks) vs the C oracle on planes that span
+    zero, one and many tiles, with short segments (noise), long segments (flat + spikes, random walks: segments
+    crossing chunk and tile boundaries), constant planes and the int16 extremes."""
+    import torch
+    from oracle import codec_oracle as co
+    from tezip_b200 import ops
+    H, W = hw
+    C, nt = 3, 7
+    rng = np.random.default_rng(H * 1000 + W)
+    frames = rng.integers(0, 256, size=(nt, H, W, C), dtype=np.uint8)
+    dev = torch.device("cuda", 0)
+    n = H * W
+
+    def planes(kind):
+        if kind == "noise":
+            return rng.integers(-3, 4, size=(nt, H, W, C))
+        if kind == "wide":
+            return rng.integers(-300, 301, size=(nt, H, W, C))
+        if kind == "flat":
+            d = np.zeros((nt, n, C), np.int64)
+            for f in range(nt):
+                for c in range(C):
+                    k = max(1, n // 700)
+                    d[f, rng.integers(0, n, size=k), c] = rng.integers(-30, 31, size=k)
+            return d.reshape(nt, H, W, C)
+        if kind == "walk":
+            return np.cumsum(rng.integers(-1, 2, size=(nt, n, C)), axis=1).reshape(nt, H, W, C)
+        if kind == "const":
+            return np.full((nt, H, W, C), 5)
+        if kind == "extremes":
+            return rng.choice(np.array([-32768, -32767, -1, 0, 1, 32766, 32767]), size=(nt, H, W, C))
+        raise ValueError(kind)
+
+    for kind in ("noise", "wide", "flat", "walk", "const", "extremes"):
+        for mode, bound in (("abs", [2.0]), ("abs", [0.5]), ("abs", [2.55]), ("abs", [40000.0]), ("rel", [0.013]),
+                            ("absrel", [4.0, 0.02])):
+            d = planes(kind).astype(np.int64)
+            ref = d.copy()
+            co.error_bound_frames(frames.astype(np.int64), ref, mode, bound)
+            x = torch.from_numpy(d.astype(np.int16)).to(dev)
+            apply = np.ones(nt, np.uint8)
+            apply[0] = 0
+            ops.error_bound(torch.from_numpy(frames).to(dev), x, torch.from_numpy(apply).to(dev), mode, bound)
+            got = x.cpu().numpy().astype(np.int64)
+            assert np.array_equal(got, ref.astype(np.int16).astype(np.int64)), (kind, mode, bound)
+
+
 def test_window_sse_matches_numpy(cuda_lib):
     import torch
     from tezip_b200 import ops

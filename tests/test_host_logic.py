@@ -76,6 +76,14 @@ def test_luts_match_reference_replacing():
     arr = np.array([0, 1, 2, 3, 7], np.int16)
     assert np.array_equal(ops.encode_lut(t2)[arr], co.replacing_encode(arr, t2))
     assert np.array_equal(ops.decode_lut(t2)[arr], co.replacing_decode(arr, t2))
+    # random tables full of value/index collisions, over the whole symbol domain
+    dom = np.arange(4096, dtype=np.int16)
+    for trial in range(60):
+        n = int(rng.integers(1, 300))
+        hi = int(rng.choice([n, 2 * n, 4096]))
+        t3 = rng.choice(hi, size=min(n, hi), replace=False).astype(np.int16)
+        assert np.array_equal(ops.encode_lut(t3), co.replacing_encode(dom, t3)), trial
+        assert np.array_equal(ops.decode_lut(t3), co.replacing_decode(dom, t3)), trial
 
 
 def test_container_roundtrip(tmp_path):

@@ -246,29 +246,44 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         raise TezipError("unknown mode %r" % (mode,))
     if any(float(b) < 0 for b in bound) and mode != "abs":
         raise TezipError("error bounds must be non-negative")
+    staged = None
     if threshold is None:
         plan = plan_from_keys(nt, p, swp_keys(nt, p, window))
         pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
-        run_plan(net, frames, plan, pool)
         keys, pred_slot_np, apply_np = plan.keys, plan.pred_slot, plan.apply_eb
+        # the schedule is static: upload it and emit the key plane before the first PredNet step is queued, so that
+        # nothing on the host waits behind the predictions and the key plane's D2H copy runs under them
+        staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink)
+        run_plan(net, frames, plan, pool)
     else:
         pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
     return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
-                            comm, sink)
+                            comm, sink, staged)
+
+
+def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
+    """Device copies of the schedule (pred_slot int32 [nt], apply u8 [nt]) and the key plane (compress.py:183-263)."""
+    dev = frames.device
+    nt = frames.shape[0]
+    pred_slot = torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)).to(dev)
+    apply = torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev)
+    is_key = np.zeros(nt, np.uint8)
+    is_key[list(keys)] = 1
+    key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))
+    if sink is not None:
+        sink.key_plane(key_plane)
+    return pred_slot, apply, key_plane
 
 
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
-                     keep_x=False, comm=None, sink=None):
-    """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map."""
+                     keep_x=False, comm=None, sink=None, staged=None):
+    """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map.
+    staged: the result of stage_plan() when the caller already ran it (before the predictions)."""
     nt, H, W, C = frames.shape
     dev = frames.device
-    pred_slot = torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)).to(dev)
-    is_key = np.zeros(nt, np.uint8)
-    is_key[list(keys)] = 1
-    key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))                  # compress.py:183-263
-    if sink is not None:
-        sink.key_plane(key_plane)
+    pred_slot, apply_dev, key_plane = staged if staged is not None else stage_plan(frames, keys, pred_slot_np,
+                                                                                   apply_np, sink)
     N = nt * H * W * C
     body = torch.empty(N, dtype=torch.int16, device=dev)
     table = None
@@ -277,8 +292,7 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
     if not lossless or keep_x:
         x = ops.residual(frames, pool, pred_slot)                                        # compress.py:293-314
         if not lossless:
-            ops.error_bound(frames, x, torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev), mode,
-                            list(bound))                                                 # compress.py:315-319
+            ops.error_bound(frames, x, apply_dev, mode, list(bound))                    # compress.py:315-319
     has_prev, prev_x = False, 0
     if comm is not None:
         if x is not None:
@@ -287,18 +301,18 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
             x_last = int(ops.residual(frames[-1:], pool, pred_slot[-1:]).view(-1)[-1].item())
         has_prev, prev_x = comm.exchange_last_x(x_last)
     if entropy:
-        hist = torch.zeros(TZ_HIST_BINS, dtype=torch.int64, device=dev)
-        ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+        hist_ovf = torch.zeros(TZ_HIST_BINS + 1, dtype=torch.int64, device=dev)   # one buffer: one D2H, one reduce
+        hist, ovf = hist_ovf[:TZ_HIST_BINS], hist_ovf[TZ_HIST_BINS:]
         if x is not None:
             ops.finding_difference_hist(x, hist, ovf, has_prev, prev_x)                  # :339-340,348-355
         else:
             ops.encode_lossless(frames, pool, pred_slot, 0, hist=hist, overflow=ovf, has_prev=has_prev,
                                 prev_x=prev_x)
         if comm is not None:
-            comm.reduce_hist(hist)
-            comm.reduce_hist(ovf)
-        hist_np = hist.cpu().numpy()
-        if int(ovf.item()) != 0:
+            comm.reduce_hist(hist_ovf)
+        hist_ovf_np = hist_ovf.cpu().numpy()
+        hist_np = hist_ovf_np[:TZ_HIST_BINS]
+        if int(hist_ovf_np[TZ_HIST_BINS]) != 0:
             raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
                              "cannot represent this bound" % TZ_HIST_BINS)
         table = ops.build_table(hist_np)                                                 # :352-361
@@ -363,13 +377,13 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
     keys = [int(i) for i in np.nonzero(nz)[0]]
     plan = plan_from_keys(nt, p, keys)
     pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
-    run_plan(net, key_plane, plan, pool)                                                 # decompress.py:138-189
     pred_slot = torch.from_numpy(plan.pred_slot).to(dev)
     if table is not None:
         lut = torch.from_numpy(ops.decode_lut(table)).to(dev)
         tl = len(table)
     else:
         lut, tl = None, -1
+    run_plan(net, key_plane, plan, pool)                                                 # decompress.py:138-189
     if body_event is not None:
         torch.cuda.current_stream(dev).wait_event(body_event)
     return ops.reconstruct(body, (nt, H, W, C), Hp, Wp, tl, lut, pool, pred_slot, key_plane, first_mode, first_x,

@@ -305,6 +305,265 @@ __global__ void __launch_bounds__(128) error_bound_kernel(const uint8_t *__restr
   eb_plane_warp<EbDbl>(o, d, n, C, mode == TZ_MODE_PWREL, b0, E, 0);
 }
 
+// ---- tiled variant for plane-wide bounds (abs / rel / absrel): one CTA per plane ---------------------------------
+// The warp-serial kernel above is bound by the latency of its dependent chain (one chunk after another, one
+// segment after another inside a chunk); with short segments (noisy residuals) that chain is ~7k cycles per 32
+// elements.  Here everything that does not depend on where the previous segment ended is done in parallel, for
+// EVERY element as if a segment started there, and the serial part shrinks to one ballot per 32-element chunk:
+//   S1 (all warps, one chunk of 32 elements per warp pass)
+//        pre[j]   inclusive in-chunk prefix state (min d, max d)                       -- 5 shuffle rounds
+//        nb[j]    first in-chunk element that breaks a segment started at j, or 32      -- sparse table + binary lifting
+//        run[j]   state of [j, nb[j])                                                   --   (5 + 5 shuffles)
+//        last[j]  last start inside the chunk of the chain j -> nb[j] -> nb[nb[j]] ...  -- 5 pointer-jumping rounds
+//   S2 (warp 0) walks the chunks with the open segment's state X: ballot(broken(join(X, pre[j]))) gives the break
+//        b; the orbit then enters the chunk at b, leaves it at last[b] with X = run[last[b]].
+//   S3 (all warps) marks the starts inside each chunk from its entry (reachability doubling with a warp OR),
+//        picks every element's segment state and writes trunc((u+l)/2).
+// A segment still open at the end of a tile is written when it closes (or at the end of the plane).
+// State is packed as two int16: lo = min d, hi = ~(max d), so that join is ONE __vmins2 (VIMNMX.S16X2) and
+// (min - max + G + 1) is ONE __dp2a_lo; ~ maps int16 onto int16, so every int16 residual is representable.
+// scripts/eb_tile_emulate.py is a lane-level numpy emulation of this kernel checked against the oracle.
+constexpr int EB_T = 1024;          // elements per tile
+constexpr int EB_NCH = EB_T / 32;   // chunks per tile
+constexpr int EB_THREADS = 128;
+constexpr int EB_WARPS = EB_THREADS / 32;
+constexpr uint32_t EBP_ID = 0x7fff7fffu;   // identity of join: (min = 32767, max = -32768)
+
+__device__ __forceinline__ uint32_t ebp_pack(int d) { return ((uint32_t)d & 0xffffu) | ((uint32_t)(~d) << 16); }
+__device__ __forceinline__ uint32_t ebp_join(uint32_t p, uint32_t q) { return __vmins2(p, q); }
+// max - min > G  <=>  min + ~max + 1 + G < 0
+__device__ __forceinline__ bool ebp_broken(uint32_t p, int G1) { return __dp2a_lo((int)p, 0x0101, G1) < 0; }
+// compress.py:61 as EbInt::mid.  EXACT: E is a multiple of 2^-36 below 4096, so fl(a+E), fl(b-E) and their sum are
+// exact and trunc(((a+E)+(b-E))/2) is the truncating integer division (a+b)/2.
+template <bool EXACT>
+__device__ __forceinline__ int16_t ebp_mid(uint32_t p, double E) {
+  const int a = (int)(int16_t)(p & 0xffffu);
+  const int b = ~(int)(int16_t)(p >> 16);
+  if (EXACT) return (int16_t)((a + b) / 2);
+  return (int16_t)(long long)__dmul_rn(__dadd_rn(__dadd_rn((double)a, E), __dsub_rn((double)b, E)), 0.5);
+}
+
+struct EbTileSmem {
+  uint32_t pre[EB_T];      // S1 -> S2: inclusive in-chunk prefix state
+  uint32_t run[EB_T];      // S1 -> S3: state of the in-chunk segment [j, nb[j])
+  uint32_t exitst[EB_T];   // S1 -> S2: run[last[j]], the state with which the orbit of j leaves the chunk
+  uint16_t meta[EB_T];     // lo 8: nb (1..32), hi 8: last
+  uint32_t inst[EB_NCH];   // S2 -> S3: state of the segment covering the elements before the chunk's entry
+  uint32_t outst[EB_NCH];  // S2 -> S3: state of the segment that starts at the chunk's last start
+  uint8_t entry[EB_NCH];   // S2 -> S3: first start inside the chunk (0xff: none)
+  int red[2 * EB_WARPS];
+  int head, open_from, wb_head;
+  uint32_t carry, wb_state;
+};
+
+template <bool EXACT>
+__device__ __forceinline__ void eb_plane_tiles(EbTileSmem &sm, int16_t *__restrict__ d, int n, int C, double E,
+                                               int G1, int warp, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int tid = warp * 32 + lane;
+  if (tid == 0) {
+    sm.head = 0;
+    sm.carry = EBP_ID;
+  }
+  for (int tile = 0; tile < n; tile += EB_T) {
+    const int Tn = min(EB_T, n - tile);
+    const int nch = (Tn + 31) >> 5;
+    // ---------------------------------------------------------------- S1
+    {
+      const int16_t *dp = d + (long long)(tile + tid) * C;
+      for (int c = warp; c < nch; c += EB_WARPS, dp += (long long)EB_THREADS * C) {
+        const int i = 32 * c + lane;
+        const uint32_t v = (i < Tn) ? ebp_pack((int)*dp) : EBP_ID;
+        uint32_t pre = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t u = __shfl_up_sync(FULL, pre, off);
+          pre = ebp_join(pre, (lane >= off) ? u : EBP_ID);
+        }
+        uint32_t M[5];   // M[k][j] = join(v[j .. j + 2^k)), identity beyond the chunk
+        M[0] = v;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t u = __shfl_down_sync(FULL, M[k], 1 << k);
+          M[k + 1] = ebp_join(M[k], (lane + (1 << k) < 32) ? u : EBP_ID);
+        }
+        uint32_t run = v;
+        int pos = lane + 1;
+#pragma unroll
+        for (int k = 4; k >= 0; k--) {   // binary lifting: the longest unbroken [lane, pos)
+          const uint32_t nx = ebp_join(run, __shfl_sync(FULL, M[k], pos));
+          const bool ok = (pos + (1 << k) <= 32) & !ebp_broken(nx, G1);
+          run = ok ? nx : run;
+          pos = ok ? pos + (1 << k) : pos;
+        }
+        uint32_t pk = ((uint32_t)pos << 8) | (uint32_t)lane;   // (next start, last start visited)
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const uint32_t u = __shfl_sync(FULL, pk, pk >> 8);
+          pk = (pk < (32u << 8)) ? u : pk;
+        }
+        const uint32_t ex = __shfl_sync(FULL, run, pk);   // lane = pk & 31 = last
+        sm.pre[i] = pre;
+        sm.run[i] = run;
+        sm.exitst[i] = ex;
+        sm.meta[i] = (uint16_t)((uint32_t)pos | ((pk & 0xffu) << 8));
+        if (lane == 0) sm.entry[c] = 0xff;
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- S2
+    if (warp == 0) {
+      uint32_t X = sm.carry;
+      const int hd0 = sm.head;
+      int seg_chunk = -1;   // chunk of this tile in which the open segment starts (-1: before the tile)
+      int seg_b = 0;        // its entry lane
+      int wbh = -1;
+      uint32_t wbs = 0;
+      uint32_t pj = sm.pre[lane];
+      for (int c = 0; c < nch; c++) {
+        const uint32_t tj = ebp_join(X, pj);
+        if (c + 1 < nch) pj = sm.pre[32 * (c + 1) + lane];   // does not depend on the chain: overlaps the ballot
+        const unsigned m = __ballot_sync(FULL, ebp_broken(tj, G1));
+        if (m == 0) {   // the whole chunk joins the open segment
+          X = __shfl_sync(FULL, tj, 31);
+          continue;
+        }
+        const int b = __ffs(m) - 1;
+        const uint32_t nextX = sm.exitst[32 * c + b];
+        const uint32_t before = __shfl_sync(FULL, tj, b + 31);   // lane b-1
+        const uint32_t Xc = (b > 0) ? before : X;   // the open segment closes at tile + 32c + b with this state
+        int from = 0;
+        if (seg_chunk < 0) {
+          wbh = hd0;
+          wbs = Xc;
+        } else {
+          from = seg_chunk + 1;
+          if (lane == 0) sm.outst[seg_chunk] = Xc;
+        }
+        if (lane == 0) {
+          sm.inst[c] = Xc;
+          sm.entry[c] = (uint8_t)b;
+        }
+        if (from < c)
+          for (int cc = from + lane; cc < c; cc += 32) sm.inst[cc] = Xc;
+        X = nextX;
+        seg_chunk = c;
+        seg_b = b;
+      }
+      if (lane == 0) {
+        int hd = hd0;
+        if (seg_chunk >= 0) hd = tile + 32 * seg_chunk + (sm.meta[32 * seg_chunk + seg_b] >> 8);
+        sm.carry = X;
+        sm.head = hd;
+        sm.open_from = (hd >= tile) ? hd - tile : 0;
+        sm.wb_head = wbh;
+        sm.wb_state = wbs;
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- S3
+    const int open_from = sm.open_from;
+    {
+      const int wbh = sm.wb_head;
+      if (wbh >= 0 && wbh < tile) {   // the part of the first closed segment that lies in earlier tiles
+        const int16_t q = ebp_mid<EXACT>(sm.wb_state, E);
+        for (int j = wbh + tid; j < tile; j += EB_THREADS) d[(long long)j * C] = q;
+      }
+    }
+    {
+      int16_t *dp = d + (long long)(tile + tid) * C;
+      for (int c = warp; c < nch && 32 * c < open_from; c += EB_WARPS, dp += (long long)EB_THREADS * C) {
+        const int i = 32 * c + lane;
+        const int ent = sm.entry[c];
+        uint32_t st = sm.inst[c];
+        if (ent != 0xff) {
+          const int nb = sm.meta[i] & 0xff;
+          const uint32_t run = sm.run[i];
+          unsigned R = 1u << ent;   // starts reachable from the entry
+          int J = nb;
+#pragma unroll
+          for (int r = 0; r < 5; r++) {
+            const unsigned tgt = ((R >> lane) & 1u) << (J & 31);
+            R |= __reduce_or_sync(FULL, (J < 32) ? tgt : 0u);
+            const int u = __shfl_sync(FULL, J, J);
+            J = (J < 32) ? u : 32;
+          }
+          const int s = 31 - __clz((int)(R & (0xffffffffu >> (31 - lane))));   // -1 for lanes before the entry
+          const int nb_s = __shfl_sync(FULL, nb, s);
+          const uint32_t run_s = __shfl_sync(FULL, run, s);
+          const uint32_t own = (nb_s >= 32) ? sm.outst[c] : run_s;
+          st = (lane >= ent) ? own : st;
+        }
+        if (i < min(Tn, open_from)) *dp = ebp_mid<EXACT>(st, E);
+      }
+    }
+    __syncthreads();
+  }
+  {   // compress.py:67: the segment still open at the end of the plane
+    const int head = sm.head;
+    const int16_t q = ebp_mid<EXACT>(sm.carry, E);
+    for (int j = head + tid; j < n; j += EB_THREADS) d[(long long)j * C] = q;
+  }
+}
+
+__global__ void __launch_bounds__(EB_THREADS) error_bound_tiles_kernel(const uint8_t *__restrict__ frames,
+                                                                       int16_t *__restrict__ x,
+                                                                       const uint8_t *__restrict__ apply,
+                                                                       long long nt, Geo g, int mode, double b0,
+                                                                       double b1) {
+  __shared__ EbTileSmem sm;
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long t = blockIdx.x;        // one CTA per (frame, channel)
+  const long long f = t / g.C;
+  const int ch = (int)(t - f * g.C);
+  if (!apply[f]) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULL, tid >> 5, 0);   // warp-uniform for the compiler: no divergence guards on shuffles
+  const int n = g.H * g.W;
+  const int C = g.C;
+  const uint8_t *o = frames + f * g.frame_elems + ch;
+  int16_t *d = x + f * g.frame_elems + ch;
+  double E = fabs(b0);                                                   // :29
+  if (mode != TZ_MODE_ABS) {
+    int mx = 0, mn = 255;                                                // :31-32 / :36-37
+    for (int i = tid; i < n; i += EB_THREADS) {
+      int v = o[(long long)i * C];
+      mx = max(mx, v);
+      mn = min(mn, v);
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    mn = __reduce_min_sync(FULL, mn);
+    if (lane == 0) {
+      sm.red[2 * warp] = mx;
+      sm.red[2 * warp + 1] = mn;
+    }
+    __syncthreads();
+    for (int w = 0; w < EB_WARPS; w++) {
+      mx = max(mx, sm.red[2 * w]);
+      mn = min(mn, sm.red[2 * w + 1]);
+    }
+    if (mode == TZ_MODE_REL) {
+      E = __dmul_rn((double)(mx - mn), b0);                              // :33
+    } else {
+      double a = fabs(b0), r = __dmul_rn((double)(mx - mn), b1);         // :38-39
+      E = (a < r) ? a : r;                                               // :40-43
+    }
+  }
+  const double twoE = E + E;
+  const double sc = E * 68719476736.0;   // 2^36
+  const bool exact = (E < 4096.0) && (sc == floor(sc));
+  const bool clear = fabs(twoE - rint(twoE)) > 1e-6;
+  if (!(E >= 0.0 && (exact || clear))) {   // the integer shortcut does not apply: IEEE-double scan, one warp
+    if (warp == 0) eb_plane_warp<EbDbl>(o, d, n, C, false, b0, E, 0);
+    return;
+  }
+  const int G1 = (twoE >= 70000.0 ? 70000 : (int)floor(twoE)) + 1;
+  if (exact)
+    eb_plane_tiles<true>(sm, d, n, C, E, G1, warp, lane);
+  else
+    eb_plane_tiles<false>(sm, d, n, C, E, G1, warp, lane);
+}
+
 // ------------------------------------------------------------------------------------------------ delta + histogram
 // compress.py:73-77 + :348-355.  Shared-memory histogram (16 KB), run-length aggregated atomics, one
 // 64-bit global atomic per non-empty bin per block.  SRC 0: x is materialised (int16); SRC 1/2: the
@@ -737,9 +996,16 @@ int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long
   if (nt == 0) return TZ_OK;
   Geo g = make_geo(H, W, C, H, W);
   long long planes = nt * C;
-  const int threads = 128;   // 4 warps = 4 planes per block
-  long long blocks = (planes * 32 + threads - 1) / threads;
-  error_bound_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode, b0, b1);
+  TZ_REQUIRE(planes < 2147483647LL, "tz_error_bound: too many planes (%lld)", planes);
+  static const bool legacy = getenv("TZ_EB_LEGACY") != nullptr;   // A/B switch: the warp-serial kernel for every mode
+  if (mode != TZ_MODE_PWREL && !legacy) {
+    error_bound_tiles_kernel<<<(unsigned)planes, EB_THREADS, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode,
+                                                                                       b0, b1);
+  } else {
+    const int threads = 128;   // 4 warps = 4 planes per block
+    long long blocks = (planes * 32 + threads - 1) / threads;
+    error_bound_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode, b0, b1);
+  }
   TZ_CHECK_LAUNCH();
   return TZ_OK;
 }

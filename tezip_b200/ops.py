@@ -93,21 +93,63 @@ def build_table(hist_np):
     return ii[order].astype(np.int16)
 
 
+def _sequential_replace(pairs):
+    """lut after `for (src, dst) in pairs: lut[lut == src] = dst`, starting from the identity over the 4096-symbol
+    domain.  The reference runs one full-array where() per table entry (compress.py:84-90, decompress.py:31-36); a
+    later pass sees the values earlier passes wrote, so value/index collisions chain.  Here the positions that
+    currently hold a value are kept as a group and whole groups move, which is the same function in O(len(table))
+    instead of O(len(table) * 4096) -- the table is on the critical path between the two GPU passes."""
+    groups = {}
+
+    def group(v):
+        g = groups.get(v)
+        if g is None:
+            g = groups[v] = [v] if 0 <= v < TZ_HIST_BINS else []
+        return g
+
+    for src, dst in pairs:
+        if src == dst:
+            continue
+        g = group(src)
+        if g:
+            group(dst).extend(g)
+            groups[src] = []
+    pos, val = [], []
+    for v, g in groups.items():
+        pos.extend(g)
+        val.extend([v] * len(g))
+    lut = np.arange(TZ_HIST_BINS, dtype=np.int16)
+    if pos:
+        lut[pos] = np.array(val, dtype=np.int64).astype(np.int16)
+    return lut
+
+
+def _no_collisions(t):
+    """True when every symbol of the table lies outside the rank range [0, len(table)) (and inside the domain) and
+    no symbol repeats: then no where() pass can see a value written by another pass, and the sequential replace
+    is a plain scatter.  The usual case: symbols cluster around 1600, tables hold tens of entries."""
+    return len(t) > 0 and int(t.min()) >= len(t) and int(t.max()) < TZ_HIST_BINS and len(np.unique(t)) == len(t)
+
+
 def encode_lut(table):
-    """symbol -> rank over the whole 4096-symbol domain, with the reference's sequential where() passes
-    (compress.py:84-90) so that value/index collisions behave identically."""
-    result = np.arange(TZ_HIST_BINS, dtype=np.int16)
-    for idx, num in enumerate(table):
-        result = np.where(result == num, np.int16(idx), result)
-    return result.astype(np.int16)
+    """symbol -> rank over the whole 4096-symbol domain, equal to the reference's sequential where() passes
+    (compress.py:84-90: result[result == num] = idx for every table entry in order)."""
+    t = np.asarray(table).astype(np.int64)
+    if _no_collisions(t):
+        lut = np.arange(TZ_HIST_BINS, dtype=np.int16)
+        lut[t] = np.arange(len(t), dtype=np.int16)
+        return lut
+    return _sequential_replace((num, idx) for idx, num in enumerate(t.tolist()))
 
 
 def decode_lut(table):
-    """rank -> symbol (decompress.py:31-36), identity beyond the table."""
-    result = np.arange(TZ_HIST_BINS, dtype=np.int16)
-    for idx, num in enumerate(table):
-        result = np.where(result == idx, np.int16(num), result)
-    return result.astype(np.int16)
+    """rank -> symbol (decompress.py:31-36: result[result == idx] = num in table order), identity beyond the table."""
+    t = np.asarray(table).astype(np.int64)
+    if _no_collisions(t):
+        lut = np.arange(TZ_HIST_BINS, dtype=np.int16)
+        lut[:len(t)] = t.astype(np.int16)
+        return lut
+    return _sequential_replace((idx, num) for idx, num in enumerate(t.tolist()))
 
 
 def reconstruct(body, shape, Hp, Wp, table_len, rank_lut, pred_pool, pred_slot, key_plane, first_mode=0, first_x=0,
