@@ -167,6 +167,15 @@ int tz_key_plane(const uint8_t *frames, const uint8_t *is_key, uint8_t *out, lon
 int tz_frames_nonzero(const uint8_t *key_plane, uint8_t *nonzero, long long nt, long long frame_bytes,
                       void *stream);
 
+/* Strided frame copy between host (pinned) and device, either direction: `height` pieces of `width` bytes, piece k
+ * at dst + k*dpitch from src + k*spitch.  Lets a caller send the key frames of every window first (the prediction
+ * steps need nothing else -- compress.py:219-229 reads one frame per window) and the remaining frames behind the
+ * PredNet kernels, where the reference loads the whole array up front (compress.py:131-152).  One 2-D DMA
+ * (cudaMemcpy2DAsync, direction inferred from the pointers); asynchronous with respect to the host when the host
+ * side is pinned. */
+int tz_memcpy2d_async(void *dst, long long dpitch, const void *src, long long spitch, long long width,
+                      long long height, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

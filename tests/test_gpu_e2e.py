@@ -145,18 +145,22 @@ def test_host_buffer_api_matches_device_api(cuda_lib):
     net = gpu_net(stack, ws, 24, 40, max_batch=8)
     frames = synth.make_frames(nt, H, W, 3, seed=41)
     fh = torch.from_numpy(frames).pin_memory()
-    for mode, bound in (("abs", [0.0]), ("abs", [2.0])):
-        ref = codec.encode_frames(fh.cuda(), net, 1, 4, None, mode, bound, True)
-        key_host = torch.empty_like(fh).pin_memory()
-        body_host = torch.empty(frames.size, dtype=torch.int16).pin_memory()
-        enc = codec.encode_frames_host(fh, net, 1, 4, None, mode, bound, key_host, body_host, True, chunks=3)
+    # p = 0 takes the split upload (key frames first, the rest behind the predictions; 17 = 4 windows of 4 + one
+    # frame, 18 = ... + two frames: both shapes of the trailing window), p = 1 the plain one
+    for p, n_use, mode, bound in ((1, 17, "abs", [0.0]), (1, 17, "abs", [2.0]), (0, 17, "abs", [2.0]),
+                                  (0, 16, "abs", [0.0]), (0, 15, "abs", [2.0])):
+        fh_n = fh[:n_use].clone().pin_memory()
+        ref = codec.encode_frames(fh_n.cuda(), net, p, 4, None, mode, bound, True)
+        key_host = torch.empty_like(fh_n).pin_memory()
+        body_host = torch.empty(fh_n.numel(), dtype=torch.int16).pin_memory()
+        enc = codec.encode_frames_host(fh_n, net, p, 4, None, mode, bound, key_host, body_host, True, chunks=3)
         torch.cuda.synchronize()
-        assert np.array_equal(body_host.numpy(), ref.body.cpu().numpy())
+        assert np.array_equal(body_host.numpy(), ref.body.cpu().numpy()), (p, n_use)
         assert np.array_equal(key_host.numpy(), ref.key_plane.cpu().numpy())
         assert np.array_equal(enc.table, ref.table)
-        out_host = torch.empty_like(fh).pin_memory()
-        codec.decode_arrays_host(key_host, body_host, enc.table, enc.shape, 1, net, out_host)
+        out_host = torch.empty_like(fh_n).pin_memory()
+        codec.decode_arrays_host(key_host, body_host, enc.table, enc.shape, p, net, out_host)
         torch.cuda.synchronize()
-        err = np.abs(out_host.numpy().astype(int) - frames.astype(int)).max()
+        err = np.abs(out_host.numpy().astype(int) - frames[:n_use].astype(int)).max()
         assert err <= (0 if bound == [0.0] else 2)
     net.close()

@@ -9,13 +9,14 @@ k-1 (from the key frame for k = 1).  So all windows advance in lock step: step k
 `PredNet.next` over every window that is longer than k.  Windows are ordered by length (descending, stable) so
 that the live set is always a prefix and each step reads / writes one contiguous block of the prediction pool.
 """
+import ctypes
 from dataclasses import dataclass, field
 
 import numpy as np
 import torch
 
-from . import ops
-from ._lib import TezipError, TZ_HIST_BINS
+from . import _lib, ops
+from ._lib import TezipError, TZ_HIST_BINS, check
 
 
 # ------------------------------------------------------------------------------------------------ schedules
@@ -229,7 +230,7 @@ def pool_slots_upper_bound(nt):
 
 
 def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
-                  keep_x=False, comm=None, sink=None):
+                  keep_x=False, comm=None, sink=None, frames_ready=None):
     """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
 
     comm: optional shard communicator (tezip_b200/dist.py) when `frames` is one rank's window-aligned shard of a
@@ -255,7 +256,11 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         # nothing on the host waits behind the predictions and the key plane's D2H copy runs under them
         staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink)
         run_plan(net, frames, plan, pool)
+        if frames_ready is not None:   # the non-key frames were still in flight (upload_frames); the residual needs them
+            torch.cuda.current_stream(dev).wait_event(frames_ready)
     else:
+        if frames_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(frames_ready)
         pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
     return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
@@ -396,9 +401,38 @@ def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_
     (pinned).  The H2D copy, the kernels and the D2H copies are pipelined; returns the Encoded record (table, keys)
     after the copies have been ordered on the current stream (synchronise before reading the host buffers)."""
     dev = net.device
-    frames = frames_host.to(dev, non_blocking=True)
     sink = HostSink(key_host, body_host, dev, chunks)
-    return encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink)
+    frames, ready = upload_frames(frames_host, dev, p, window, threshold)
+    return encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
+                         frames_ready=ready)
+
+
+def upload_frames(frames_host, dev, p, window, threshold):
+    """Host (pinned) -> device copy of the frames.  With a static window (SWP, p = 0) the key frames go first, on
+    the current stream: the prediction steps read nothing else (compress.py:219-229).  The other frames follow on
+    the side stream, behind the PredNet kernels; the returned event marks their arrival (None: everything was
+    copied on the current stream)."""
+    nt = frames_host.shape[0]
+    if threshold is not None or p != 0 or window is None or window < 2 or nt <= window or not frames_host.is_pinned():
+        return frames_host.to(dev, non_blocking=True), None
+    lib = _lib.load()
+    fb = frames_host[0].numel() * frames_host.element_size()
+    n_full, rem = divmod(nt, window)
+    main = torch.cuda.current_stream(dev)
+    frames = torch.empty(frames_host.shape, dtype=frames_host.dtype, device=dev)
+    src, dst, pitch = frames_host.data_ptr(), frames.data_ptr(), window * fb
+
+    def copy2d(offset, width, height, stream):
+        check(lib.tz_memcpy2d_async(ctypes.c_void_p(dst + offset), pitch, ctypes.c_void_p(src + offset), pitch, width,
+                                    height, ctypes.c_void_p(stream.cuda_stream)), "tz_memcpy2d_async")
+
+    copy2d(0, fb, n_full + (1 if rem else 0), main)                 # first frame of every window
+    side = side_stream(dev)
+    side.wait_event(main.record_event())                            # `frames` may reuse memory the main stream still reads
+    copy2d(fb, (window - 1) * fb, n_full, side)                     # frames 1..window-1 of the full windows
+    if rem > 1:
+        copy2d(n_full * pitch + fb, (rem - 1) * fb, 1, side)        # and of the trailing short one
+    return frames, side.record_event()
 
 
 def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, first_mode=0, first_x=0):

@@ -1139,4 +1139,14 @@ int tz_frames_nonzero(const uint8_t *key_plane, uint8_t *nonzero, long long nt, 
   return TZ_OK;
 }
 
+int tz_memcpy2d_async(void *dst, long long dpitch, const void *src, long long spitch, long long width,
+                      long long height, void *stream) {
+  TZ_REQUIRE(dst && src && width >= 0 && height >= 0 && dpitch >= width && spitch >= width,
+             "tz_memcpy2d_async: bad arguments");
+  if (width == 0 || height == 0) return TZ_OK;
+  TZ_CHECK_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                                  cudaMemcpyDefault, (cudaStream_t)stream));
+  return TZ_OK;
+}
+
 }  // extern "C"

@@ -646,10 +646,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float *ah = P.ahat_next + ((long long)(h >> 1) * Wo + (w >> 1)) * P.S_next;
         __half *dst = P.xe_out + opix * P.xe_cstride;
         const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
-        // The error units need Ahat0 of the pooled pixel (one private 32-byte piece per writer lane and chunk).  All
-        // of this warp's chunks are requested up front, so their L2 latency is paid once per tile, not per chunk.
         constexpr int PF = 6;
         const bool vec_ok = ((P.S_next | P.xe_cstride) & 7) == 0;
+        if (vec_ok && ((P.H | P.W) & 1) == 0 && P.tw_log >= 1 && P.th_log >= 1) {
+          // Lane-balanced pooling.  The four lanes of a 2x2 window swap halves instead of all computing everything
+          // (transpose-reduce: xor 1 keeps 4 of the 8 channels, xor tile-width keeps 2), so each lane ends with the
+          // pooled maximum of TWO channels and does bias, relu, the error units and a 4-byte store for those: 6
+          // shuffles per chunk instead of 16, no idle lanes in the E math.  max and (+bias, relu) commute exactly
+          // (both monotone), so the result is bit-identical to pooling relu(conv + bias).
+          const int hm = 1 << P.tw_log;
+          const bool wbit = (lane & 1) != 0, hbit = (lane & hm) != 0;
+          const int co = (wbit ? 4 : 0) + (hbit ? 2 : 0);   // this lane's channel pair inside an 8-channel chunk
+          float2 ahq[PF];
+#pragma unroll
+          for (int c = 0; c < PF; c++) {   // Ahat0 of all chunks up front: the L2 latency is paid once per tile
+            const int j0 = 8 * (part + c * nparts);
+            if (valid && j0 < n_real) ahq[c] = __ldg(reinterpret_cast<const float2 *>(ah + nt * P.n_tile + j0 + co));
+          }
+          auto fchunk = [&](int j0, float2 a2) {
+            float v[8];
+            tc_ld8(trow + j0, v);
+            const int chl = nt * P.n_tile + j0 + co;
+            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(P.bias + chl));
+            tc_ld_wait();
+            float u[4], z[2];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float send = wbit ? v[k] : v[k + 4], keep = wbit ? v[k + 4] : v[k];
+              u[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const float send = hbit ? u[k] : u[k + 2], keep = hbit ? u[k + 2] : u[k];
+              z[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, hm));
+            }
+            if (valid) {
+              const float a0 = fmaxf(__fadd_rn(z[0], b2.x), 0.0f), a1 = fmaxf(__fadd_rn(z[1], b2.y), 0.0f);
+              const __half2 up = __floats2half2_rn(fmaxf(__fsub_rn(a2.x, a0), 0.0f), fmaxf(__fsub_rn(a2.y, a1), 0.0f));
+              const __half2 dn = __floats2half2_rn(fmaxf(__fsub_rn(a0, a2.x), 0.0f), fmaxf(__fsub_rn(a1, a2.y), 0.0f));
+              *reinterpret_cast<__half2 *>(dst + chl) = up;
+              *reinterpret_cast<__half2 *>(dst + P.S_next + chl) = dn;
+            }
+          };
+#pragma unroll
+          for (int c = 0; c < PF; c++) {
+            const int j0 = 8 * (part + c * nparts);
+            if (j0 < n_real) fchunk(j0, ahq[c]);
+          }
+          for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) {
+            float2 a2 = make_float2(0.0f, 0.0f);
+            if (valid) a2 = __ldg(reinterpret_cast<const float2 *>(ah + nt * P.n_tile + j0 + co));
+            fchunk(j0, a2);
+          }
+        } else {
+        // Generic path (odd sizes, unaligned channel counts): every lane pools all 8 channels, the lane of the
+        // window's top-left pixel writes.  Ahat0 of all of this warp's chunks is requested up front.
         float ahp[PF][8];
 #pragma unroll
         for (int c = 0; c < PF; c++) {
@@ -698,6 +749,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (j0 < n_real) chunk(j0, ahp[c]);
         }
         for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) chunk(j0, nullptr);
+        }
       } else {
         // LSTM cell: columns [g*NCp + j], g = i,f,c,o.  c = f*C0 + i*tanh(.), r = o*tanh(c)
         const long long pix = (long long)h * P.W + w;
@@ -1009,7 +1061,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     const char *env = getenv("TZ_HALO");
     const bool want = !(env && env[0] == '0');
     const int cin64 = A.cin_pad;            // channels read: cin rounded up to 16, walked in chunks of KC
-    const uint32_t budget = 112u * 1024u;
+    // Stationary weights may take what two halo stages leave free: one wide N tile halves the MMA count of a split
+    // one (measured, a1 of the (3,48,96,192) net: N = 96 in one tile 0.098 ms, two tiles of 48 0.129 ms).
+    const char *envb = getenv("TZ_WBUDGET_KB");   // experiment: cap of the stationary weights in KB
+    const uint32_t halo_stage = (16u * 18u * 2u * (uint32_t)A.KC + 1023u) & ~1023u;
+    const uint32_t budget = envb ? (uint32_t)atoi(envb) * 1024u : 224u * 1024u - 2u * halo_stage;
     if (want && cin64 <= cx && (A.W % 8) == 0) {
       for (int split = 1; split <= 2; split++) {
         if (n_real % split) continue;
@@ -1017,7 +1073,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         if (epi == 1 && unit > 64) continue;
         if (epi == 0 && split > 1 && (unit % 16) != 0) continue;
         const int ntile = (epi == 1) ? round_up(4 * round_up(unit, 8), 16) : round_up(unit, 16);
-        if ((uint32_t)ntile * 9u * (uint32_t)cin64 * 2u > budget || ntile > 256) continue;
+        const uint32_t wbytes = 9u * (uint32_t)(cin64 / A.KC) * (((uint32_t)ntile * 2u * (uint32_t)A.KC + 1023u) & ~1023u);
+        if (wbytes > (split == 1 ? budget : 112u * 1024u) || ntile > 256) continue;
         A.halo = 1;
         n_unit = unit;
         A.tw_log = 3;
@@ -1169,7 +1226,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.a_stride = 0;
     A.stage_stride = (16u * 18u * row_bytes + 1023u) & ~1023u;   // one halo tile: 18 image rows x 16 pixels x KC channels
     A.tx_bytes = 16u * 18u * row_bytes;
-    stages = (int)((204u * 1024u - A.b_region) / A.stage_stride);
+    stages = (int)((224u * 1024u - A.b_region) / A.stage_stride);
     if (stages > 4) stages = 4;
     if (stages < 2) {
       set_error("internal: halo mode does not fit (weights %u bytes)", A.b_region);
