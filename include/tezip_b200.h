@@ -87,6 +87,14 @@ int tz_prednet_p0(tz_prednet *h, float *out, void *stream);
  * frames share the batch. */
 int tz_prednet_next(tz_prednet *h, const float *in, float *out, int B, void *stream);
 
+/* The loop of compress.py:222-229 / decompress.py:161-179 feeds every prediction straight back as the next input
+ * (X_test_one = X_hat[0, 1] until the window closes).  tz_prednet_next_chained() is tz_prednet_next() whose input
+ * is the first B frames of the prediction written by the previous next / next_chained call on this handle (B may
+ * shrink as windows end, never grow); that buffer must still hold the prediction.  Same result bit for bit; the
+ * tensor-core path has already staged the layer-0 error units of that prediction and skips one kernel and one
+ * read of the frames.  Errors: no previous call, B larger than the previous B, out == the previous out. */
+int tz_prednet_next_chained(tz_prednet *h, float *out, int B, void *stream);
+
 /* Per-kernel view of one tz_prednet_next() for the roofline report: kernel i of tz_prednet_kernel_count()
  * has a name and an algorithmic FLOP count per frame; tz_prednet_next_timed() runs one next() with CUDA events
  * between the launches on `stream` and returns the device time of each kernel in ms (synchronous). */

@@ -85,3 +85,29 @@ def test_predict_protocol(cuda_lib):
     got1 = net.predict(x[:, :1], 10)
     assert np.abs(got1 - onet.predict(x[:, :1], 10)).max() <= TOL_DIRECT
     net.close()
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_chained_steps_bitwise(cuda_lib, direct):
+    """next_chained (input = the previous prediction, compress.py:222-229) equals next() on that tensor bit for
+    bit, with a shrinking batch (windows that end), and refuses what it cannot honour."""
+    import torch
+    from tezip_b200._lib import TezipError
+    stack, H, W = TINY, 24, 40
+    _onet, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, H, W, max_batch=6, fp32_direct=direct)
+    x = torch.from_numpy(_inputs(6, H, W, H, W, seed=13)).cuda()
+    with pytest.raises(TezipError):
+        net.next_chained(torch.empty_like(x))                   # nothing to chain from yet
+    ref1 = net.next(x)
+    ref2 = net.next(ref1)                                       # plain: 6 frames
+    ref3 = net.next(ref2[:4].contiguous())                      # plain: the first 4 only
+    a1 = net.next(x)
+    a2 = net.next_chained(torch.empty_like(x))
+    a3 = net.next_chained(torch.empty_like(x[:4]))
+    assert torch.equal(a1, ref1) and torch.equal(a2, ref2) and torch.equal(a3, ref3)
+    with pytest.raises(TezipError):
+        net.next_chained(torch.empty_like(x))                   # 6 > 4: the batch may not grow
+    with pytest.raises(TezipError):
+        net.next_chained(a3)                                    # out is the previous prediction
+    net.close()

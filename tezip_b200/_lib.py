@@ -36,6 +36,7 @@ SIGNATURES = {
     "tz_prednet_destroy": (c_int, [c_vp]),
     "tz_prednet_p0": (c_int, [c_vp, c_vp, c_vp]),
     "tz_prednet_next": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "tz_prednet_next_chained": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "tz_prednet_kernel_count": (c_int, [c_vp]),
     "tz_prednet_kernel_info": (c_int, [c_vp, c_int, ctypes.c_char_p, c_int, ctypes.POINTER(c_dbl)]),
     "tz_prednet_next_timed": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, ctypes.POINTER(c_flt), c_int]),

@@ -82,13 +82,19 @@ def run_plan(net, frames, plan, pool):
     net.p0(out=pool[0])
     mb = net.max_batch
     prev = None
+    chain = False   # the previous step was ONE next() call whose output is this step's input
     for key_idx, slot0, B in plan.steps:
         if key_idx is not None:
             idx = torch.from_numpy(key_idx).to(frames.device)
             prev = ops.pad_normalize(frames, idx, net.Hp, net.Wp)          # compress.py:219 / decompress.py:161
+            chain = False
         out = pool[slot0:slot0 + B]
-        for b0 in range(0, B, mb):
-            net.next(prev[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])  # compress.py:222-229
+        if chain and B <= mb:
+            net.next_chained(out)                                          # the live windows are a prefix of the last step's
+        else:
+            for b0 in range(0, B, mb):
+                net.next(prev[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])  # compress.py:222-229
+        chain = B <= mb
         prev = out
 
 

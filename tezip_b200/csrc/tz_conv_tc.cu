@@ -891,10 +891,13 @@ __global__ void pack_bm_kernel(const float *__restrict__ src, float *__restrict_
 
 // prednet.py:268-271 at layer 0: prediction = min(relu(conv3x3(r_0) + b), pixel_max), C -> C channels (C = 1 or 3).
 // 16x16 output pixels per block; the 18x18xC input patch and the 9*C*C weights sit in shared memory.
+// xe != nullptr: also stage the next step's layer-0 error units (what e0_tc_kernel would compute from `out`), so
+// that a chained step (the usual case: frame k+1 is predicted from the prediction of frame k) skips that kernel.
 template <int C>
 __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0, const float *__restrict__ wt,
                                                     const float *__restrict__ bias, float *__restrict__ out, int H,
-                                                    int W, float clip) {
+                                                    int W, float clip, const float *__restrict__ p0,
+                                                    __half *__restrict__ xe, int cstride) {
   __shared__ float tile[18][18 * C + 1];
   __shared__ float ws[9 * C * C];
   __shared__ float bs[C];
@@ -925,9 +928,23 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
 #pragma unroll
         for (int co = 0; co < C; co++) acc[co] = fmaf(v, ws[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
       }
-  float *dst = out + (((long long)b * H + y) * W + x) * C;
+  const long long pix = ((long long)b * H + y) * W + x;
+  float *dst = out + pix * C;
+  __align__(16) __half ev[8];   // [relu(ahat - a) x C | relu(a - ahat) x C | zeros]: 2C <= 6 of the 8 lanes
 #pragma unroll
-  for (int co = 0; co < C; co++) dst[co] = fminf(fmaxf(acc[co] + bs[co], 0.0f), clip);
+  for (int j = 0; j < 8; j++) ev[j] = __float2half_rn(0.0f);
+#pragma unroll
+  for (int co = 0; co < C; co++) {
+    const float a = fminf(fmaxf(acc[co] + bs[co], 0.0f), clip);
+    dst[co] = a;
+    if (xe) {   // prednet.py:274-277 of the NEXT step at layer 0, t = 0 (as e0_tc_kernel)
+      const float ah = p0[((long long)y * W + x) * C + co];
+      ev[co] = __float2half_rn(fmaxf(__fsub_rn(ah, a), 0.0f));
+      ev[C + co] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
+    }
+  }
+  // one 16-byte store per pixel (channels 2C..7 of X_0 are padding that multiplies zero weights; they stay zero)
+  if (xe) *reinterpret_cast<uint4 *>(xe + pix * cstride) = *reinterpret_cast<const uint4 *>(ev);
 }
 
 __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
@@ -1438,12 +1455,15 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   return TZ_OK;
 }
 
-int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev) {
+int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev, bool skip_e0) {
   TcState *T = h->tc;
   const int L = h->L;
   int ne = 0;
+  h->x0_staged = false;
   if (ev) cudaEventRecord(ev[ne++], st);
-  {
+  if (skip_e0) {
+    if (ev) cudaEventRecord(ev[ne++], st);
+  } else {
     const int C = h->S[0];
     long long total = (long long)B * h->H[0] * h->W[0] * C;
     e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], T->X[0], total,
@@ -1465,10 +1485,13 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
   if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
     dim3 grid((h->W[0] + 15) / 16, (h->H[0] + 15) / 16, B);
     if (h->S[0] == 3)
-      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max);
+      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max,
+                                            h->Ahat0[0], T->X[0], T->cx[0]);
     else
-      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max);
+      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max,
+                                            h->Ahat0[0], T->X[0], T->cx[0]);
     TZ_CHECK_LAUNCH();
+    h->x0_staged = true;
   } else {
     ConvSrc s = {T->r0, h->R[0], 0, 0, (long long)h->H[0] * h->W[0] * h->R[0]};
     rc = conv3x3_direct(&s, 1, h->w_ahat[0], h->R[0], h->S[0], h->b_ahat[0], nullptr, out, B, h->H[0], h->W[0], 2,

@@ -425,14 +425,39 @@ int tz_prednet_next(tz_prednet *h, const float *in, float *out, int B, void *str
   TZ_REQUIRE(B >= 0 && B <= h->cfg.max_batch, "tz_prednet_next: B=%d exceeds max_batch=%d", B, h->cfg.max_batch);
   if (B == 0) return TZ_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!h->direct) return tc_next(h, in, out, B, st);
+  h->last_out = nullptr;
+  if (!h->direct) {
+    int rc = tc_next(h, in, out, B, st);
+    if (rc == TZ_OK) {
+      h->last_out = out;
+      h->last_B = B;
+    }
+    return rc;
+  }
   const long long frame = (long long)h->H[0] * h->W[0] * h->S[0];
   for (int b0 = 0; b0 < B; b0 += h->direct_chunk) {
     int nb = B - b0 < h->direct_chunk ? B - b0 : h->direct_chunk;
     int rc = direct_next_chunk(h, in + b0 * frame, out + b0 * frame, nb, st);
     if (rc) return rc;
   }
+  h->last_out = out;
+  h->last_B = B;
   return TZ_OK;
+}
+
+int tz_prednet_next_chained(tz_prednet *h, float *out, int B, void *stream) {
+  TZ_REQUIRE(h && out, "tz_prednet_next_chained: null argument");
+  TZ_REQUIRE(h->last_out != nullptr, "tz_prednet_next_chained: no previous tz_prednet_next on this handle");
+  TZ_REQUIRE(B >= 0 && B <= h->last_B, "tz_prednet_next_chained: B=%d exceeds the previous step's %d frames", B,
+             h->last_B);
+  TZ_REQUIRE(out != h->last_out, "tz_prednet_next_chained: out must not be the previous prediction");
+  if (B == 0) return TZ_OK;
+  const float *in = h->last_out;
+  if (h->direct || !h->x0_staged) return tz_prednet_next(h, in, out, B, stream);
+  int rc = tc_next(h, in, out, B, (cudaStream_t)stream, nullptr, true);
+  h->last_out = rc == TZ_OK ? out : nullptr;
+  h->last_B = B;
+  return rc;
 }
 
 int tz_prednet_kernel_count(tz_prednet *h) {
@@ -471,6 +496,7 @@ int tz_prednet_next_timed(tz_prednet *h, const float *in, float *out, int B, voi
   TZ_REQUIRE(n_ms >= n, "tz_prednet_next_timed: need room for %d timings", n);
   cudaEvent_t ev[2 * TZ_MAX_LAYERS + 2];
   for (int i = 0; i <= n; i++) TZ_CHECK_CUDA(cudaEventCreate(&ev[i]));
+  h->last_out = nullptr;   // a timed step does not take part in chaining
   int rc = tc_next(h, in, out, B, (cudaStream_t)stream, ev);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (rc == TZ_OK && e == cudaSuccess)

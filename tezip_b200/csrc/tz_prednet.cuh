@@ -35,6 +35,11 @@ struct tz_prednet {
   float *pre;               // [chunk, max pre-activation plane]
 
   TcState *tc;
+
+  // chained stepping (tz_prednet_next_chained): the last prediction written and how many frames of it are staged
+  const float *last_out;
+  int last_B;
+  bool x0_staged;   // tensor-core path: X_0 already holds the error units of last_out (written by the ahat0 kernel)
 };
 
 namespace tz {
@@ -59,6 +64,8 @@ int lstm_direct(const float *pre, const float *c_prev, float *r_out, float *c_ou
 // tensor-core path (tz_conv_tc.cu)
 int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &w_host);
 void tc_destroy(tz_prednet *h);
-int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev = nullptr);
+// skip_e0: X_0 already holds the error units of `in` (staged by the previous step's ahat0 kernel)
+int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev = nullptr,
+            bool skip_e0 = false);
 
 }  // namespace tz

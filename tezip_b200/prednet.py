@@ -148,6 +148,17 @@ class PredNet:
                    "tz_prednet_next")
         return out
 
+    def next_chained(self, out):
+        """next() of the first out.shape[0] frames of the prediction the previous next()/next_chained() call on
+        this net wrote (compress.py:222-229 feeds X_hat[0, 1] straight back); the caller must not have modified
+        that tensor.  Bit-identical to next(previous_out[:B], out); saves one kernel per step."""
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        assert tuple(out.shape[1:]) == self.frame_shape()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.tz_prednet_next_chained(self._h, _lib.ptr(out), out.shape[0], ctypes.c_void_p(st)),
+                   "tz_prednet_next_chained")
+        return out
+
     def kernels(self):
         """[(name, algorithmic FLOPs per frame)] of the launches inside one next()."""
         out = []
