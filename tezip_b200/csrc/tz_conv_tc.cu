@@ -894,25 +894,31 @@ __global__ void pack_bm_kernel(const float *__restrict__ src, float *__restrict_
 // xe != nullptr: also stage the next step's layer-0 error units (what e0_tc_kernel would compute from `out`), so
 // that a chained step (the usual case: frame k+1 is predicted from the prediction of frame k) skips that kernel.
 template <int C>
-__global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0, const float *__restrict__ wt,
-                                                    const float *__restrict__ bias, float *__restrict__ out, int H,
-                                                    int W, float clip, const float *__restrict__ p0,
-                                                    __half *__restrict__ xe, int cstride) {
-  __shared__ float tile[18][18 * C + 1];
-  __shared__ float ws[9 * C * C];
-  __shared__ float bs[C];
-  const int b = blockIdx.z, x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+struct Ahat0W {   // kernel parameter: the FMAs read the 9*C*C weights straight from the constant bank
+  float w[9 * C * C];
+  float b[C];
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0, const __grid_constant__ Ahat0W<C> wb,
+                                                    float *__restrict__ out, int H, int W, float clip,
+                                                    const float *__restrict__ p0, __half *__restrict__ xe, int cstride) {
+  constexpr int TW = 32, TH = 8;                 // output pixels per block: a warp is one image row of the tile
+  __shared__ float tile[TH + 2][(TW + 2) * C];
+  const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const float *src = r0 + (long long)b * H * W * C;
-  for (int i = threadIdx.x; i < 18 * 18 * C; i += 256) {
-    const int yy = i / (18 * C), rem = i - yy * (18 * C);
-    const int xx = rem / C, c = rem - xx * C;
-    const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-    tile[yy][rem] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? src[((long long)gy * W + gx) * C + c] : 0.0f;
+  // rows of the patch are contiguous in memory ((TW+2)*C floats): consecutive threads read consecutive floats
+  for (int yy = threadIdx.x / 32; yy < TH + 2; yy += 8) {
+    const int gy = y0 + yy - 1;
+    const bool rowok = gy >= 0 && gy < H;
+    const float *row = src + ((long long)gy * W + (x0 - 1)) * C;
+    for (int i = threadIdx.x & 31; i < (TW + 2) * C; i += 32) {
+      const int gx = x0 - 1 + i / C;
+      tile[yy][i] = (rowok && gx >= 0 && gx < W) ? row[i] : 0.0f;
+    }
   }
-  for (int i = threadIdx.x; i < 9 * C * C; i += 256) ws[i] = wt[i];
-  if (threadIdx.x < C) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = x0 + tx, y = y0 + ty;
   if (x >= W || y >= H) return;
   float acc[C];
@@ -926,7 +932,7 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
       for (int ci = 0; ci < C; ci++) {
         const float v = tile[ty + ky][(tx + kx) * C + ci];
 #pragma unroll
-        for (int co = 0; co < C; co++) acc[co] = fmaf(v, ws[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
+        for (int co = 0; co < C; co++) acc[co] = fmaf(v, wb.w[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
       }
   const long long pix = ((long long)b * H + y) * W + x;
   float *dst = out + pix * C;
@@ -935,7 +941,7 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
   for (int j = 0; j < 8; j++) ev[j] = __float2half_rn(0.0f);
 #pragma unroll
   for (int co = 0; co < C; co++) {
-    const float a = fminf(fmaxf(acc[co] + bs[co], 0.0f), clip);
+    const float a = fminf(fmaxf(acc[co] + wb.b[co], 0.0f), clip);
     dst[co] = a;
     if (xe) {   // prednet.py:274-277 of the NEXT step at layer 0, t = 0 (as e0_tc_kernel)
       const float ah = p0[((long long)y * W + x) * C + co];
@@ -972,6 +978,7 @@ struct TcState {
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
   int sm_count;
+  float ahat0_w[9 * 3 * 3], ahat0_b[3];   // host copy of the layer-0 A-hat kernel (C = R_0 = S_0 <= 3), passed by value
 };
 
 namespace tz {
@@ -1341,6 +1348,11 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   }
   T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
   if (!T->r0) return TZ_ENOMEM;
+  if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1)) {
+    const int C = h->S[0];
+    TZ_CHECK_CUDA(cudaMemcpy(T->ahat0_w, h->w_ahat[0], sizeof(float) * 9 * C * C, cudaMemcpyDeviceToHost));
+    TZ_CHECK_CUDA(cudaMemcpy(T->ahat0_b, h->b_ahat[0], sizeof(float) * C, cudaMemcpyDeviceToHost));
+  }
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -1483,13 +1495,20 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
   }
   int rc = TZ_OK;
   if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
-    dim3 grid((h->W[0] + 15) / 16, (h->H[0] + 15) / 16, B);
-    if (h->S[0] == 3)
-      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max,
-                                            h->Ahat0[0], T->X[0], T->cx[0]);
-    else
-      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, h->w_ahat[0], h->b_ahat[0], out, h->H[0], h->W[0], h->cfg.pixel_max,
-                                            h->Ahat0[0], T->X[0], T->cx[0]);
+    dim3 grid((h->W[0] + 31) / 32, (h->H[0] + 7) / 8, B);
+    if (h->S[0] == 3) {
+      Ahat0W<3> wb;
+      memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
+      memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
+      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
+                                            T->cx[0]);
+    } else {
+      Ahat0W<1> wb;
+      memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
+      memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
+      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
+                                            T->cx[0]);
+    }
     TZ_CHECK_LAUNCH();
     h->x0_staged = true;
   } else {
