@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import codec_oracle as co
-from tezip_b200 import codec, container, ops, dist as tzdist
+from tezip_b200 import codec, container, ops, synth, dist as tzdist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -168,3 +168,34 @@ def test_cabi_exports_every_declared_symbol():
         h = ctypes.c_void_p()
         assert lib.tz_prednet_create(ctypes.byref(cfg), ptrs, sizes, n, ctypes.byref(h)) != 0
         assert lib.tz_last_error()
+
+
+def test_keras_weight_converter_orders_by_weight_names(tmp_path):
+    """scripts/convert_keras_weights.py reads the datasets in the `weight_names` order of the one layer that owns
+    weights (Keras' get_weights() order), from a weights-only file or the model_weights group of a full-model file;
+    h5py is not in this image, so the file is stood in for by objects with the same attrs / [] shape."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("convert_keras_weights",
+                                                  os.path.join(ROOT, "scripts", "convert_keras_weights.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+
+    class Node(dict):
+        def __init__(self, items=(), **attrs):
+            super().__init__(items)
+            self.attrs = attrs
+
+    ws = synth.make_weights((3, 8, 16), bias="uniform", seed=5)
+    names = ["pred_net_1/w%d:0" % i for i in range(len(ws))]
+    order = np.random.default_rng(0).permutation(len(ws))                 # storage order differs from weight_names
+    layer = Node({names[i]: ws[i] for i in order}, weight_names=[n.encode() for n in names])
+    root = Node({"input_1": Node(weight_names=[]), "pred_net_1": layer}, layer_names=[b"input_1", b"pred_net_1"])
+    got = conv.prednet_weights(root)
+    assert len(got) == len(ws) and all(np.array_equal(a, b) for a, b in zip(got, ws))
+    full = Node({"model_weights": root, "optimizer_weights": Node()})
+    got = conv.prednet_weights(full)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ws))
+    with pytest.raises(ValueError):
+        conv.prednet_weights(Node({"x": Node()}))
+    with pytest.raises(ValueError):                                       # two layers with weights: not this model
+        conv.prednet_weights(Node({"a": layer, "b": layer}, layer_names=[b"a", b"b"]))

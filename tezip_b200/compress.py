@@ -22,8 +22,17 @@ def _die(*msg):
     sys.exit(1)
 
 
-def load_images(DATA_DIR):
-    """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB."""
+def io_workers():
+    """Threads for image decode/encode (PIL releases the GIL inside its codecs); TEZIP_IO_WORKERS overrides."""
+    env = os.environ.get("TEZIP_IO_WORKERS")
+    return max(1, int(env)) if env else max(1, min(32, os.cpu_count() or 1))
+
+
+def load_images(DATA_DIR, workers=None):
+    """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB.
+    One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
+    pool, so the array goes to the GPU with one asynchronous copy."""
+    from concurrent.futures import ThreadPoolExecutor
     from PIL import Image, UnidentifiedImageError
     file_paths = sorted(glob.glob(os.path.join(DATA_DIR, '*')))
     if len(file_paths) == 0:
@@ -35,15 +44,37 @@ def load_images(DATA_DIR):
             _die("ERROR: input image is {0}. Only RGB and grayscale are supported.".format(image_mode))
         isRGB = image_mode == 'RGB'
         w, h = first.size
-        frames = np.empty((len(file_paths), h, w, 3), np.uint8)       # one allocation instead of nt hstacks
-        files = []
-        for i, path in enumerate(file_paths):
-            img = Image.open(path)
-            frames[i] = np.array(img if isRGB else img.convert('RGB'))
-            files.append(os.path.basename(path))
+        buf = torch.empty((len(file_paths), h, w, 3), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            buf = buf.pin_memory()
+        frames = buf.numpy()
+
+        def decode(i):
+            img = Image.open(file_paths[i])
+            frames[i] = np.asarray(img if isRGB else img.convert('RGB'))    # shape mismatch -> ValueError
+
+        with ThreadPoolExecutor(workers or io_workers()) as pool:
+            list(pool.map(decode, range(len(file_paths))))
+        files = [os.path.basename(path) for path in file_paths]
     except (PermissionError, IndexError, UnidentifiedImageError, IsADirectoryError, ValueError):
         _die(DATA_DIR, "contains files or folders that are not images.")
     return frames, files, isRGB
+
+
+def save_images(frames, file_names, isRGB, OUTPUT_DIR, workers=None):
+    """decompress.py:266-279 with a thread pool.  The reference re-saves every image as RGB (decompress.py:278),
+    overwriting its own 'L' conversion; the grayscale branch is honoured here (documented deviation, SURVEY.md
+    Appendix B)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+    print("save as RGB" if isRGB else "save as gray")
+
+    def encode(j):
+        img = Image.fromarray(frames[j])
+        (img if isRGB else img.convert("L")).save(os.path.join(OUTPUT_DIR, file_names[j]))
+
+    with ThreadPoolExecutor(workers or io_workers()) as pool:
+        list(pool.map(encode, range(len(file_names))))
 
 
 def load_predictor(WEIGHTS_DIR, max_batch, device=0):
@@ -71,8 +102,8 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, M
     try:
         t0 = time.time()
         dev = net.device
-        enc = codec.encode_frames(torch.from_numpy(frames).to(dev), net, PREPROCESS, WINDOW_SIZE, THRESHOLD, MODE,
-                                  list(BOUND_VALUE), ENTROPY_RUN, dwp_chains=dwp_chains)
+        enc = codec.encode_frames(torch.from_numpy(frames).to(dev, non_blocking=True), net, PREPROCESS, WINDOW_SIZE,
+                                  THRESHOLD, MODE, list(BOUND_VALUE), ENTROPY_RUN, dwp_chains=dwp_chains)
         payload = enc.payload()
         key_plane = enc.key_plane.cpu().numpy()
         torch.cuda.synchronize(dev)

@@ -8,7 +8,7 @@ import torch
 
 from . import codec, container
 from ._lib import TezipError
-from .compress import load_predictor
+from .compress import load_predictor, save_images
 
 
 def _die(*msg):
@@ -42,12 +42,5 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, GPU_FLAG, VERBOSE):
             print("gpu_decode:{0}".format(time.time() - t0) + "[sec]")
     except TezipError as e:
         _die(str(e))
-    from PIL import Image
-    for j in range(shape[1]):                                                          # decompress.py:266-279
-        img = Image.fromarray(frames[j])
-        if j == 0:
-            print("save as RGB" if isRGB else "save as gray")
-        # the reference re-saves every image as RGB (decompress.py:278), overwriting the 'L' conversion; the
-        # grayscale branch is honoured here (documented deviation)
-        (img if isRGB else img.convert("L")).save(os.path.join(OUTPUT_DIR, file_names[j]))
+    save_images(frames, file_names, isRGB, OUTPUT_DIR)
     net.close()
