@@ -194,6 +194,7 @@ struct ConvArgs {
                                  // G > 1: narrow tiles -- warp group g (4 warps) owns the tiles with index % G == g,
                                  // so G epilogues are in flight and their latency overlaps
   int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
+  int mma_issuers;               // halo + stationary weights: 2 warps issue the MMAs of alternate tiles, else 1
   int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
   int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
   int sub_stride;                // TMEM columns between the accumulators of the two M tiles of a pair
@@ -324,6 +325,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // thread issues every TMA and ONE thread every tcgen05.mma of the CTA, so the instruction count of these two
   // loops bounds the tensor pipe (a microbenchmark reaches N/2 cycles per M128 MMA only with straight-line issue;
   // runtime divisions and 64-bit descriptor arithmetic per MMA cost more than the MMA itself).
+  // Halo + stationary-weights mode: the MMA issue loop.  The tensor work of one tile is short here (9 * ksteps MMAs
+  // of <= 56 cycles per chunk), shorter than the ~1000 cycles one thread needs to walk the barriers and form the
+  // descriptors of a tile (measured: a0 issued at 119 cycles per MMA against a floor of 44), so TWO warps issue,
+  // each taking every other tile of this CTA (any thread may issue tcgen05.mma; a tcgen05.commit tracks the MMAs
+  // of the thread that executes it, which is exactly the per-tile granularity the barriers need).
+  auto halo1_issue = [&](uint32_t k0, uint32_t kstep, bool dbg) {
+    if ((int)blockIdx.x >= n_tiles) return;
+    const uint32_t hi = P.desc_hi, idesc = P.idesc;
+    const uint32_t rowb = 2u * (uint32_t)P.KC;
+    const uint32_t ahi_halo = (((16u * rowb) >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
+    const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;
+    const uint32_t nst = (uint32_t)P.stages, nacc = (uint32_t)P.acc_stages, kch = (uint32_t)P.kchunks;
+    auto advance = [](uint32_t &idx, uint32_t &phase, uint32_t by, uint32_t size) {
+      idx += by;
+      while (idx >= size) {
+        idx -= size;
+        phase ^= 1u;
+      }
+    };
+    uint32_t s = 0, ph = 0, a = 0, aph = 0;
+    advance(s, ph, k0 * kch, nst);
+    advance(a, aph, k0, nacc);
+    long long w_tempty = 0, w_full = 0, c0 = 0, t_start = 0;
+    if (dbg) t_start = clock64();
+    mbar_wait(bfull, 0);
+    tc_fence_after();
+    for (int t = t_first + (int)k0 * t_step; t < n_tiles; t += (int)kstep * t_step) {
+      if (dbg) c0 = clock64();
+      mbar_wait(tempty0 + 8 * a, aph ^ 1u);
+      if (dbg) w_tempty += clock64() - c0;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)P.acc_stride;
+      for (uint32_t ch = 0; ch < kch; ch++) {
+        if (dbg) c0 = clock64();
+        mbar_wait(full0 + 8 * s, ph);
+        if (dbg) w_full += clock64() - c0;
+        tc_fence_after();
+        const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
+        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo = (((smem0 + ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
+        if (elect_one()) {
+          if (P.ksteps == 4)
+            issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+          else if (P.ksteps == 2)
+            issue_halo_chunk<2>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+          else
+            issue_halo_chunk<1>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
+          tc_commit(empty0 + 8 * s);   // halo slot free once its MMAs retire
+          if (ch + 1 == kch) tc_commit(tfull0 + 8 * a);   // accumulator complete
+        }
+        __syncwarp();
+        advance(s, ph, 1, nst);
+      }
+      advance(s, ph, (kstep - 1) * kch, nst);   // the other issuer's chunks
+      advance(a, aph, kstep, nacc);
+    }
+    if (dbg) {
+      long long *o = P.dbg + 8 * blockIdx.x;
+      o[0] = clock64() - t_start;
+      o[1] = w_tempty;
+      o[2] = w_full;
+      o[3] = 0;
+    }
+  };
+
   if (warp == 0) {
     // ===================================================================== TMA producer
     // (whole warp walks the loop with warp-uniform state; one elected lane issues the TMA instructions)
@@ -444,23 +510,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     // The whole warp walks the loop (waits, ring state, descriptors are warp-uniform); one elected lane issues.
-    if (crank == 0) {
+    if (P.halo == 1) {
+      halo1_issue(0, (uint32_t)P.mma_issuers, P.dbg != nullptr && lane == 0);
+    } else if (crank == 0) {
       uint32_t s = 0, ph = 0, sl = 0, pha = 0;
       uint32_t a = 0, aph = 0;   // accumulator ring
       const uint32_t hi = P.desc_hi;
       const uint32_t idesc = P.idesc;
-      if (P.halo == 1 && (int)blockIdx.x < n_tiles) {
-        mbar_wait(bfull, 0);
-        tc_fence_after();
-      }
       const uint32_t rowb = 2u * (uint32_t)P.KC;   // bytes per pixel row of a chunk
       // halo tiles: 16 pixels per image row -> the 8-row groups (one image row of the 8-wide tile) are 16*rowb apart
       // (pair mode: 10 pixels of 128 B).  Neither needs to be a multiple of the swizzle period: the swizzle is a
       // function of the absolute shared-memory address bits (what TMA wrote), and the descriptor base_offset stays 0
       // -- measured on B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
-      const uint32_t ahi_halo = (((16u * rowb) >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
       const uint32_t ahi_pair = ((1280u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
-      const uint32_t btap16 = ((uint32_t)P.kchunks * P.b_block) >> 4;   // halo mode: block kb = tap * kchunks + chunk
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
       const bool dbg = P.dbg != nullptr && lane == 0;
@@ -540,27 +602,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc = 1;
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
           }
-        } else if (P.halo == 1) {
-          for (int ch = 0; ch < P.kchunks; ch++) {
-            if (dbg) c0 = clock64();
-            mbar_wait(full0 + 8 * s, ph);
-            if (dbg) w_full += clock64() - c0;
-            tc_fence_after();
-            const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
-            const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t b_lo = (((smem0 + (uint32_t)ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-            if (elect_one()) {
-              if (P.ksteps == 4)
-                issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-              else if (P.ksteps == 2)
-                issue_halo_chunk<2>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-              else
-                issue_halo_chunk<1>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
-              tc_commit(empty0 + 8 * s);   // halo slot free once its MMAs retire
-            }
-            __syncwarp();
-            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-          }
         } else {
           uint32_t acc = 0;
           for (int ch = 0; ch < P.kchunks; ch++) {
@@ -608,6 +649,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         o[3] = w_afull;
       }
     }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===================================================================== second MMA issuer (halo mode only)
+    if (P.halo == 1 && P.mma_issuers == 2) halo1_issue(1, 2, false);
     __syncwarp();
   } else if (warp >= 4) {
     // ===================================================================== epilogue (warps 4 .. 4+epi_warps-1)
@@ -1287,6 +1332,15 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       A.acc_stages = 6;
       A.acc_stride = 64;
     }
+  }
+  {
+    // Two issuers take alternate tiles.  mbarrier waits are by phase PARITY, so a thread may only wait on a barrier
+    // whose previous phase it has itself seen complete: every halo slot and every accumulator must always belong to
+    // the same issuer, i.e. one chunk per tile and even ring sizes (otherwise a wait one full phase ahead returns
+    // at once -- seen as a launch failure on a1, three chunks per tile, when this was unconditional).
+    const char *env = getenv("TZ_MMA_ISSUERS");   // A/B switch
+    A.mma_issuers = (A.halo == 1 && A.kchunks == 1 && (A.stages % 2) == 0 && (A.acc_stages % 2) == 0 &&
+                     !(env && env[0] == '1')) ? 2 : 1;
   }
   // ---- descriptors
   const CUtensorMapSwizzle swz = A.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
