@@ -11,6 +11,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]  # never fast-math: bit-exact codec arithmetic
+FLAGS += os.environ.get("TZ_NVCC_FLAGS", "").split()         # diagnostics builds, e.g. -DTZ_EPI_DEBUG=1
 
 
 def sources():

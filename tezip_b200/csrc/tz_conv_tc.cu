@@ -23,6 +23,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef TZ_EPI_DEBUG
+#define TZ_EPI_DEBUG 0
+#endif
+
 namespace tz {
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -665,6 +669,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
     const int tb = m >> (P.tw_log + P.th_log);
     uint32_t tc = 0;
+#if TZ_EPI_DEBUG   // compile-time: the LSTM epilogue has no registers to spare (nvcc -DTZ_EPI_DEBUG=1 via TZ_NVCC_FLAGS)
+    const bool edbg = P.dbg != nullptr && warp == 4 && lane == 0;
+#else
+    constexpr bool edbg = false;
+#endif
+    long long e_wait = 0, e_work = 0, e_tiles = 0, ec0 = 0, e_a = 0, e_b = 0, e_c = 0;
     for (int t = t_first; t < n_tiles; t += t_step, tc++) {
       if (P.epi_groups > 1 && (int)(tc % (uint32_t)P.epi_groups) != group) continue;   // another group's tile
       const int nt = t % P.n_tiles_n;
@@ -676,7 +686,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tbi = mt / P.tiles_h;
       const int w = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
       const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
+      if (edbg) ec0 = clock64();
       mbar_wait(tfull0 + 8 * a, aph);
+      if (edbg) {
+        const long long now = clock64();
+        e_wait += now - ec0;
+        ec0 = now;
+        e_tiles++;
+      }
       tc_fence_after();
       for (int sub = 0; sub < P.sub_tiles; sub++) {
       const int h = thi * P.tile_h + (sub << P.th_log) + th;
@@ -708,40 +725,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int j0 = 8 * (part + c * nparts);
             if (valid && j0 < n_real) ahq[c] = __ldg(reinterpret_cast<const float2 *>(ah + nt * P.n_tile + j0 + co));
           }
-          auto fchunk = [&](int j0, float2 a2) {
-            float v[8];
-            tc_ld8(trow + j0, v);
-            const int chl = nt * P.n_tile + j0 + co;
-            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(P.bias + chl));
-            tc_ld_wait();
-            float u[4], z[2];
+          // Two chunks at a time: their shuffle / max / store chains are independent, which gives the scheduler two
+          // instruction streams per warp (the epilogue runs 3 warps per scheduler; with one chain per warp it was
+          // bound by dependent-issue latency, ~700-1100 cycles per chunk).
+          auto finish2 = [&](int ja, int jb, bool has_b, const float *va, const float *vb, float2 aa, float2 ab) {
+            const int cha = nt * P.n_tile + ja + co, chb = nt * P.n_tile + jb + co;
+            const float2 ba = __ldg(reinterpret_cast<const float2 *>(P.bias + cha));
+            const float2 bb = has_b ? __ldg(reinterpret_cast<const float2 *>(P.bias + chb)) : make_float2(0.0f, 0.0f);
+            float ua[4], ub[4], za[2], zb[2];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              const float send = wbit ? v[k] : v[k + 4], keep = wbit ? v[k + 4] : v[k];
-              u[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+              const float sa = wbit ? va[k] : va[k + 4], ka = wbit ? va[k + 4] : va[k];
+              const float sb = wbit ? vb[k] : vb[k + 4], kb = wbit ? vb[k + 4] : vb[k];
+              ua[k] = fmaxf(ka, __shfl_xor_sync(0xffffffffu, sa, 1));
+              ub[k] = fmaxf(kb, __shfl_xor_sync(0xffffffffu, sb, 1));
             }
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-              const float send = hbit ? u[k] : u[k + 2], keep = hbit ? u[k + 2] : u[k];
-              z[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, hm));
+              const float sa = hbit ? ua[k] : ua[k + 2], ka = hbit ? ua[k + 2] : ua[k];
+              const float sb = hbit ? ub[k] : ub[k + 2], kb = hbit ? ub[k + 2] : ub[k];
+              za[k] = fmaxf(ka, __shfl_xor_sync(0xffffffffu, sa, hm));
+              zb[k] = fmaxf(kb, __shfl_xor_sync(0xffffffffu, sb, hm));
             }
             if (valid) {
-              const float a0 = fmaxf(__fadd_rn(z[0], b2.x), 0.0f), a1 = fmaxf(__fadd_rn(z[1], b2.y), 0.0f);
-              const __half2 up = __floats2half2_rn(fmaxf(__fsub_rn(a2.x, a0), 0.0f), fmaxf(__fsub_rn(a2.y, a1), 0.0f));
-              const __half2 dn = __floats2half2_rn(fmaxf(__fsub_rn(a0, a2.x), 0.0f), fmaxf(__fsub_rn(a1, a2.y), 0.0f));
-              *reinterpret_cast<__half2 *>(dst + chl) = up;
-              *reinterpret_cast<__half2 *>(dst + P.S_next + chl) = dn;
+              const float a0 = fmaxf(__fadd_rn(za[0], ba.x), 0.0f), a1 = fmaxf(__fadd_rn(za[1], ba.y), 0.0f);
+              const float b0 = fmaxf(__fadd_rn(zb[0], bb.x), 0.0f), b1 = fmaxf(__fadd_rn(zb[1], bb.y), 0.0f);
+              *reinterpret_cast<__half2 *>(dst + cha) =
+                  __floats2half2_rn(fmaxf(__fsub_rn(aa.x, a0), 0.0f), fmaxf(__fsub_rn(aa.y, a1), 0.0f));
+              *reinterpret_cast<__half2 *>(dst + P.S_next + cha) =
+                  __floats2half2_rn(fmaxf(__fsub_rn(a0, aa.x), 0.0f), fmaxf(__fsub_rn(a1, aa.y), 0.0f));
+              if (has_b) {
+                *reinterpret_cast<__half2 *>(dst + chb) =
+                    __floats2half2_rn(fmaxf(__fsub_rn(ab.x, b0), 0.0f), fmaxf(__fsub_rn(ab.y, b1), 0.0f));
+                *reinterpret_cast<__half2 *>(dst + P.S_next + chb) =
+                    __floats2half2_rn(fmaxf(__fsub_rn(b0, ab.x), 0.0f), fmaxf(__fsub_rn(b1, ab.y), 0.0f));
+              }
             }
           };
 #pragma unroll
-          for (int c = 0; c < PF; c++) {
-            const int j0 = 8 * (part + c * nparts);
-            if (j0 < n_real) fchunk(j0, ahq[c]);
+          for (int c = 0; c < PF; c += 2) {
+            const int ja = 8 * (part + c * nparts), jb = ja + 8 * nparts;
+            if (ja < n_real) {   // warp-uniform
+              const bool has_b = jb < n_real;
+              float va[8], vb[8];
+              tc_ld8(trow + ja, va);
+              tc_ld8(trow + (has_b ? jb : ja), vb);
+              tc_ld_wait();
+              finish2(ja, jb, has_b, va, vb, ahq[c], ahq[c + 1]);
+            }
           }
-          for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) {
+          for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) {   // more than PF chunks per warp
             float2 a2 = make_float2(0.0f, 0.0f);
             if (valid) a2 = __ldg(reinterpret_cast<const float2 *>(ah + nt * P.n_tile + j0 + co));
-            fchunk(j0, a2);
+            float va[8];
+            tc_ld8(trow + j0, va);
+            tc_ld_wait();
+            finish2(j0, j0, false, va, va, a2, a2);
           }
         } else {
         // Generic path (odd sizes, unaligned channel counts): every lane pools all 8 channels, the lane of the
@@ -803,11 +842,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // r for channels j0..j0+7 of this N tile -> fp16 into hv (or straight to the fp32 r_0 buffer at layer 0)
         auto lstm_chunk = [&](int j0, __half *hv) {
           float vi[8], vf[8], vc[8], vo[8];
+          long long q0 = 0;
+          if (edbg) q0 = clock64();
           tc_ld8(trow + 0 * P.NCp + j0, vi);
           tc_ld8(trow + 1 * P.NCp + j0, vf);
           tc_ld8(trow + 2 * P.NCp + j0, vc);
           tc_ld8(trow + 3 * P.NCp + j0, vo);
           tc_ld_wait();
+          if (edbg) {
+            const long long q1 = clock64();
+            e_a += q1 - q0;
+            q0 = q1;
+          }
           if (!valid) return;
           float r[8];
           if (P.bm_packed) {
@@ -842,6 +888,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (edbg) e_b += clock64() - q0;
           if (P.xr_out) {
 #pragma unroll
             for (int j = 0; j < 8; j++) hv[j] = __float2half_rn(r[j]);
@@ -891,6 +938,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (TWO) mbar_arrive_cluster(tempty0 + 8 * a, 0);   // the leader waits for both CTAs' epilogues
         else mbar_arrive(tempty0 + 8 * a);
       }
+      if (edbg) e_work += clock64() - ec0;
+    }
+    if (edbg) {   // TZ_CONV_DEBUG: epilogue warp 4 of this CTA: cycles waiting for accumulators / working, tiles done
+      long long *o = P.dbg + 8 * blockIdx.x;
+      o[4] = e_wait;
+      o[5] = e_work;
+      o[6] = e_tiles;
+      o[7] = e_a;
+      o[3] = e_b;
     }
   }
   tc_fence_before();
@@ -1517,6 +1573,12 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
     fprintf(stderr, "[tz conv] epi %d halo %d H %d N %d kchunks %d: mma-thread cycles total %lld, wait tempty %lld, "
             "wait full %lld, wait afull %lld (CTA 0; units per issuing CTA ~%lld)\n", c->epi, A.halo, A.H, A.n_tile,
             A.kchunks, hbuf[0], hbuf[1], hbuf[2], hbuf[3], (n_tiles + issuers - 1) / issuers);
+#if TZ_EPI_DEBUG
+    fprintf(stderr, "[tz conv]     epilogue warp 4: %lld tiles, cycles waiting for an accumulator %lld, working %lld "
+            "(%lld per tile; LSTM: TMEM loads %lld, bias-map loads + gate math %lld); %d epilogue warps in %d group(s), "
+            "%d accumulator stages, %d MMA issuer(s)\n", hbuf[6], hbuf[4], hbuf[5], hbuf[6] ? hbuf[5] / hbuf[6] : 0,
+            hbuf[7], c->epi == 1 ? hbuf[3] : 0, A.epi_warps, A.epi_groups, A.acc_stages, A.mma_issuers);
+#endif
   }
   return TZ_OK;
 }
