@@ -86,11 +86,13 @@ def eb_tiles(d, E, G, T=64):
                 l = np.where(go, tl, l)
             assert (e >= 32).all()
             spre[c], srun[c], snb[c], slast[c] = pre, run, pos, l
-        # ---- S2 (warp 0)
+        # ---- S2 (warp 0): the serial chain records (entry, X on entry, previous closing chunk) per closing chunk
         X = carry
         hd = head
         seg_chunk = -1
         wb = None
+        sinx = [None] * nchT
+        sprev = [None] * nchT
         for c in range(nch):
             p = spre[c]
             t = join((np.full(32, X[0]), np.full(32, X[1])), p)
@@ -99,20 +101,28 @@ def eb_tiles(d, E, G, T=64):
                 X = (t[0][31], t[1][31])
                 continue
             b = int(np.argmax(m))
-            Xc = (t[0][b - 1], t[1][b - 1]) if b > 0 else X
-            if seg_chunk < 0:
-                wb = (hd, Xc)
-                frm = 0
-            else:
-                soutst[seg_chunk] = Xc
-                frm = seg_chunk + 1
-            for cc in range(frm, c + 1):
-                sinst[cc] = Xc
-            l = int(slast[c][b])
             sentry[c] = b
+            sinx[c] = X
+            sprev[c] = seg_chunk
+            l = int(slast[c][b])
             X = (srun[c][0][l], srun[c][1][l])
             hd = tb + 32 * c + l
             seg_chunk = c
+        # ---- S2b (lane c owns chunk c): closing states and the chunks they cover
+        for c in range(nch):
+            b = int(sentry[c])
+            if b == 255:
+                continue
+            xin = sinx[c]
+            Xc = join(xin, (spre[c][0][b - 1], spre[c][1][b - 1])) if b > 0 else xin
+            pc = sprev[c]
+            sinst[c] = Xc
+            if pc >= 0:
+                soutst[pc] = Xc
+            else:
+                wb = (head, Xc)
+            for cc in range(pc + 1, c):
+                sinst[cc] = Xc
         carry, head = X, hd
         open_from = hd - tb if hd >= tb else 0
         # ---- write-back of the part of a closed segment that lies in earlier tiles
