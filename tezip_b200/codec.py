@@ -122,23 +122,31 @@ def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None):
     net.p0(out=pool[0])
     cursor = 1
     mb = net.max_batch
+    chain_base = None   # pool slot of the first output of the previous step when that step was one next() call
     while True:
         act = [c for c in chains if c["idx"] < c["end"]]
         if not act:
             break
         B = len(act)
-        X = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=dev)
+        out = pool[cursor:cursor + B]
         from_key = [i for i, c in enumerate(act) if c["idx"] == c["key"] + 1]
         from_pred = [i for i, c in enumerate(act) if c["idx"] != c["key"] + 1]
-        if from_key:
-            kidx = torch.tensor([act[i]["key"] for i in from_key], dtype=torch.int32, device=dev)
-            X[torch.tensor(from_key, device=dev)] = ops.pad_normalize(frames, kidx, Hp, Wp)   # compress.py:219
-        if from_pred:
-            src = torch.tensor([act[i]["last"] for i in from_pred], device=dev)
-            X[torch.tensor(from_pred, device=dev)] = pool[src]                               # compress.py:222
-        out = pool[cursor:cursor + B]
-        for b0 in range(0, B, mb):
-            net.next(X[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])
+        # The common step: no window closed last time, so the inputs are exactly the first B predictions of the
+        # previous (single) next() call, in order -> chained step, no gather (compress.py:222)
+        if chain_base is not None and not from_key and B <= mb and \
+                all(c["last"] == chain_base + i for i, c in enumerate(act)):
+            net.next_chained(out)
+        else:
+            X = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=dev)
+            if from_key:
+                kidx = torch.tensor([act[i]["key"] for i in from_key], dtype=torch.int32, device=dev)
+                X[torch.tensor(from_key, device=dev)] = ops.pad_normalize(frames, kidx, Hp, Wp)   # compress.py:219
+            if from_pred:
+                src = torch.tensor([act[i]["last"] for i in from_pred], device=dev)
+                X[torch.tensor(from_pred, device=dev)] = pool[src]                               # compress.py:222
+            for b0 in range(0, B, mb):
+                net.next(X[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])
+        chain_base = cursor if B <= mb else None
         fidx = torch.tensor([c["idx"] for c in act], dtype=torch.int32, device=dev)
         sse = ops.window_sse(frames, fidx, out).cpu().numpy()                               # compress.py:245-246
         for i, c in enumerate(act):
