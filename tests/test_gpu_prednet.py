@@ -16,9 +16,9 @@ TOL_DIRECT = 2e-5
 TOL_TC = 6e-3
 
 
-def _inputs(n, H, W, Hp, Wp, seed=4):
-    fr = synth.make_frames(n, H, W, 3, seed=seed).astype(np.float32) / 255
-    x = np.zeros((n, Hp, Wp, 3), np.float32)
+def _inputs(n, H, W, Hp, Wp, seed=4, C=3):
+    fr = synth.make_frames(n, H, W, C, seed=seed).astype(np.float32) / 255
+    x = np.zeros((n, Hp, Wp, C), np.float32)
     x[:, :H, :W] = fr
     return x
 
@@ -110,4 +110,27 @@ def test_chained_steps_bitwise(cuda_lib, direct):
         net.next_chained(torch.empty_like(x))                   # 6 > 4: the batch may not grow
     with pytest.raises(TezipError):
         net.next_chained(a3)                                    # out is the previous prediction
+    net.close()
+
+
+@pytest.mark.parametrize("stack,H,W,B", [(FULL, 256, 320, 2),            # many tiles per image in both directions
+                                         (FULL, 512, 512, 2),            # 16x the bench frame
+                                         ((1, 16, 32, 64), 64, 96, 5),   # one channel (SURVEY 8(d) config 4 family)
+                                         ((3, 24, 40), 48, 72, 7),       # three layers, widths not multiples of 16
+                                         ((3, 48, 96, 192), 128, 160, 37)])   # odd batch: ragged last CTA pair
+def test_tc_matches_oracle_more_shapes(cuda_lib, stack, H, W, B):
+    import torch
+    onet, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, H, W, max_batch=B)
+    x = _inputs(B, H, W, H, W, seed=21, C=stack[0])
+    pred1 = net.next(torch.from_numpy(x).cuda())            # kept alive: the chained step's input
+    got = pred1.cpu().numpy()
+    check = sorted(set([0, B // 2, B - 1]))                 # the oracle is slow: spot-check frames across the batch
+    ref = onet.next(x[check])
+    err = np.abs(got[check] - ref).max()
+    assert err <= TOL_TC, err
+    # chained second step through next_chained
+    got2 = net.next_chained(torch.empty_like(pred1)).cpu().numpy()
+    ref2 = onet.next(ref)
+    assert np.abs(got2[check] - ref2).max() <= TOL_TC
     net.close()
