@@ -230,6 +230,21 @@ def run_native(args):
         torch.cuda.synchronize(dev)
         return enc
 
+    # streaming variant of the host-buffer path: consecutive sequences alternate between two sets of pinned output
+    # buffers and the next sequence's kernels do not queue behind the previous one's device->host copies
+    host_sets = [(keyp_host, body_host),
+                 (torch.empty_like(keyp_host).pin_memory(), torch.empty_like(body_host).pin_memory())]
+    seq = [0]
+
+    def compress_e2e_pipelined():
+        kh, bh = host_sets[seq[0] & 1]
+        seq[0] += 1
+        enc = codec.encode_frames_host(frames_host, net, 0, win, thr, mode, bound, kh, bh, True, dwp_chains=chains,
+                                       comm=comm, wait_copies=False)
+        if comm is not None:
+            comm.stream_offsets(enc.body.numel())
+        return enc
+
     enc0 = compress_dev()
     first_mode, first_x = (0, 0) if rank == 0 else (1, 0)
 
@@ -271,6 +286,9 @@ def run_native(args):
     clocks = sampler.stop()
     _ms, wall_ce, _ = timed(compress_e2e, args.steps, max(1, args.warmup - 1))
     _ms, wall_de, _ = timed(decompress_e2e, args.steps, max(1, args.warmup - 1))
+    _ms, wall_cp, _ = timed(compress_e2e_pipelined, args.steps, max(1, args.warmup - 1))
+    torch.cuda.synchronize(dev)
+    pipelined_ok = bool(torch.equal(host_sets[0][1], host_sets[1][1]) and torch.equal(host_sets[0][0], host_sets[1][0]))
 
     # correctness inside the bench: the decoded frames respect the bound
     dec = decompress_dev()
@@ -446,6 +464,13 @@ def run_native(args):
             "decompress": {"value": total_mb / (ms_d * 1e-3), "unit": "MB/s", "ms_per_step": ms_d,
                            "e2e": {"value": total_mb / (wall_de * 1e-3), "unit": "MB/s",
                                    "h2d_bytes_per_step": int(N * 3), "d2h_bytes_per_step": int(N)}},
+            "e2e_pipelined": {"value": total_mb / (wall_cp * 1e-3), "unit": "MB/s",
+                              "note": "same host-buffer API with wait_copies=False and two alternating sets of pinned "
+                                      "output buffers, one synchronize after the K steps: the D2H copies of sequence i "
+                                      "run under the kernels of sequence i+1 (a streaming compressor); every step "
+                                      "still copies its inputs in and its results out. Not the headline: `e2e` "
+                                      "synchronises after every step.",
+                              "both_buffer_sets_identical": pipelined_ok},
             "e2e": {"value": total_mb / (wall_ce * 1e-3), "unit": "MB/s", "h2d_bytes_per_step": int(N),
                     "d2h_bytes_per_step": int(N * 3)},
             "gpu_launches": int(launches), "gpu_launches_decompress": int(launches_d),

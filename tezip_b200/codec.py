@@ -180,6 +180,7 @@ class Encoded:
     pred_slot: np.ndarray
     pool: torch.Tensor = None    # kept only when keep_pool=True
     x: torch.Tensor = None
+    copies_done: object = None   # encode_frames_host(wait_copies=False): CUDA event after the device->host copies
 
     def payload(self):
         """entropy.dat before zstd (compress.py:375-395), host int16."""
@@ -212,26 +213,35 @@ class HostSink:
     the schedule is known (before any PredNet step), the int16 stream in chunks as the rank-map kernel produces them.
     Copies run on a side stream; `finish()` makes the current stream wait for them."""
 
-    def __init__(self, key_host, body_host, device, chunks=4):
+    def __init__(self, key_host, body_host, device, chunks=4, wait_copies=True):
         self.key_host, self.body_host, self.chunks = key_host, body_host, max(1, int(chunks))
         self.device = device
         self.stream = side_stream(device)
+        self.wait_copies = wait_copies
+        self.done = None   # wait_copies=False: event after the last copy (finish())
 
     def _after_current(self):
         self.stream.wait_event(torch.cuda.current_stream(self.device).record_event())
 
     def key_plane(self, t):
         self._after_current()
+        if not self.wait_copies:
+            t.record_stream(self.stream)   # the copy may outlive the tensor: keep its memory out of reuse until then
         with torch.cuda.stream(self.stream):
             self.key_host.view(-1).copy_(t.view(-1), non_blocking=True)
 
     def body_chunk(self, t, a, b):
         self._after_current()
+        if not self.wait_copies:
+            t.record_stream(self.stream)
         with torch.cuda.stream(self.stream):
             self.body_host[a:b].copy_(t[a:b], non_blocking=True)
 
     def finish(self):
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        if self.wait_copies:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        else:
+            self.done = self.stream.record_event()
 
 
 def is_lossless(mode, bound):
@@ -410,15 +420,20 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
 
 
 def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_host, body_host, entropy=True,
-                       dwp_chains=1, comm=None, chunks=4):
+                       dwp_chains=1, comm=None, chunks=4, wait_copies=True):
     """Host-buffer API: frames_host u8 [nt,H,W,C] (pinned) -> key_host u8 (pinned, same shape), body_host int16 [N]
     (pinned).  The H2D copy, the kernels and the D2H copies are pipelined; returns the Encoded record (table, keys)
-    after the copies have been ordered on the current stream (synchronise before reading the host buffers)."""
+    after the copies have been ordered on the current stream (synchronise before reading the host buffers).
+    wait_copies=False (streaming use: the next sequence's kernels should not queue behind this one's device->host
+    copies): the copies are only ordered on the side stream and the record carries `copies_done`, the event to
+    synchronise before reading key_host / body_host; give consecutive calls different host buffers."""
     dev = net.device
-    sink = HostSink(key_host, body_host, dev, chunks)
+    sink = HostSink(key_host, body_host, dev, chunks, wait_copies)
     frames, ready = upload_frames(frames_host, dev, p, window, threshold)
-    return encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
-                         frames_ready=ready)
+    enc = encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
+                        frames_ready=ready)
+    enc.copies_done = sink.done
+    return enc
 
 
 def upload_frames(frames_host, dev, p, window, threshold):
