@@ -189,6 +189,7 @@ struct ConvArgs {
   int B, H, W;
   int tw_log, th_log, tb_log;    // tile = 2^tb x 2^th x 2^tw pixels = 128
   int tiles_w, tiles_h, n_tiles_n;
+  uint32_t m_tiles_w, m_tiles_h, m_tiles_n;   // fast_div magic numbers of the three
   int kchunks, ksteps;           // K blocks per tap, MMAs (K=16) per K block
   int KC, cin_pad;               // channels per K block, kchunks*KC
   int n_tile;                    // MMA N (multiple of 16)
@@ -242,6 +243,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+// n / d for small operands without the ~20-instruction runtime division: m = ceil(2^32 / d) (host), exact while
+// n * d < 2^32; d == 1 is encoded as m == 0.
+__device__ __forceinline__ int fast_div(int n, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n; }
+
 template <int KSTEPS>
 __device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                  uint32_t b_hi, uint32_t row16 /*row bytes >> 4*/,
@@ -412,13 +417,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       for (int t = t_first; t < n_tiles; t += t_step) {
-        const int nt = t % P.n_tiles_n;
-        int mt = t / P.n_tiles_n;
+        int mt = fast_div(t, P.m_tiles_n);
+        const int nt = t - mt * P.n_tiles_n;
         if (two) mt = 2 * mt + (int)crank;
-        const int twi = mt % P.tiles_w;
-        mt /= P.tiles_w;
-        const int thi = mt % P.tiles_h;
-        const int tbi = mt / P.tiles_h;
+        const int mq = fast_div(mt, P.m_tiles_w);
+        const int twi = mt - mq * P.tiles_w;
+        const int tbi = fast_div(mq, P.m_tiles_h);
+        const int thi = mq - tbi * P.tiles_h;
         const int w0 = twi << P.tw_log, h0 = thi * P.tile_h, b0 = tbi << P.tb_log;
         const int n0 = nt * P.n_tile;
         if constexpr (TWO) {
@@ -669,6 +674,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int th = (m >> P.tw_log) & ((1 << P.th_log) - 1);
     const int tb = m >> (P.tw_log + P.th_log);
     uint32_t tc = 0;
+    uint32_t ring_a = 0, ring_ph = 0, ring_g = 0;   // accumulator stage / phase / owning group of tile tc, kept incrementally
 #if TZ_EPI_DEBUG   // compile-time: the LSTM epilogue has no registers to spare (nvcc -DTZ_EPI_DEBUG=1 via TZ_NVCC_FLAGS)
     const bool edbg = P.dbg != nullptr && warp == 4 && lane == 0;
 #else
@@ -676,16 +682,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
     long long e_wait = 0, e_work = 0, e_tiles = 0, ec0 = 0, e_a = 0, e_b = 0, e_c = 0;
     for (int t = t_first; t < n_tiles; t += t_step, tc++) {
-      if (P.epi_groups > 1 && (int)(tc % (uint32_t)P.epi_groups) != group) continue;   // another group's tile
-      const int nt = t % P.n_tiles_n;
-      int mt = t / P.n_tiles_n;
+      const uint32_t a = ring_a, aph = ring_ph;
+      const bool mine = P.epi_groups <= 1 || (int)ring_g == group;
+      if (++ring_a == (uint32_t)P.acc_stages) {
+        ring_a = 0;
+        ring_ph ^= 1u;
+      }
+      if (++ring_g >= (uint32_t)P.epi_groups) ring_g = 0;
+      if (!mine) continue;   // another group's tile
+      int mt = fast_div(t, P.m_tiles_n);
+      const int nt = t - mt * P.n_tiles_n;
       if (two) mt = 2 * mt + (int)crank;
-      const int twi = mt % P.tiles_w;
-      mt /= P.tiles_w;
-      const int thi = mt % P.tiles_h;
-      const int tbi = mt / P.tiles_h;
+      const int mq = fast_div(mt, P.m_tiles_w);
+      const int twi = mt - mq * P.tiles_w;
+      const int tbi = fast_div(mq, P.m_tiles_h);
+      const int thi = mq - tbi * P.tiles_h;
       const int w = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
-      const uint32_t a = tc % (uint32_t)P.acc_stages, aph = (tc / (uint32_t)P.acc_stages) & 1u;
       if (edbg) ec0 = clock64();
       mbar_wait(tfull0 + 8 * a, aph);
       if (edbg) {
@@ -1388,6 +1400,12 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       A.acc_stages = 6;
       A.acc_stride = 64;
     }
+  }
+  {
+    auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
+    A.m_tiles_w = magic(A.tiles_w);
+    A.m_tiles_h = magic(A.tiles_h);
+    A.m_tiles_n = magic(A.n_tiles_n);
   }
   {
     // Two issuers take alternate tiles.  mbarrier waits are by phase PARITY, so a thread may only wait on a barrier
