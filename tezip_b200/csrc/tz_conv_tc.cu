@@ -38,8 +38,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The only arrive issued by a thread is "this accumulator has been read out of TMEM" (epilogue -> MMA issuer).  No
+// generic-proxy data travels with it -- tcgen05.wait::ld has completed the reads, tcgen05.fence::before_thread_sync
+// orders them -- so it is RELAXED: the default .release compiles to MEMBAR.ALL.CTA (.cluster: MEMBAR.ALL.GPU), which
+// made every epilogue warp wait, once per tile, until its up-sampled global stores were visible GPU-wide (16 % of
+// the LSTM epilogue's stall samples on gates1).
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
@@ -148,7 +153,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta_rank) {
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_bar), "r"(cta_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-parity bit: the address then names the leader's smem
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
