@@ -1020,7 +1020,8 @@ struct Ahat0W {   // kernel parameter: the FMAs read the 9*C*C weights straight 
 template <int C>
 __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0, const __grid_constant__ Ahat0W<C> wb,
                                                     float *__restrict__ out, int H, int W, float clip,
-                                                    const float *__restrict__ p0, __half *__restrict__ xe, int cstride) {
+                                                    const float *__restrict__ p0, __half *__restrict__ xe, int cstride,
+                                                    int epad) {
   constexpr int TW = 32, TH = 8;                 // output pixels per block: a warp is one image row of the tile
   __shared__ float tile[TH + 2][(TW + 2) * C];
   const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -1067,8 +1068,19 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
       ev[C + co] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
     }
   }
-  // one 16-byte store per pixel (channels 2C..7 of X_0 are padding that multiplies zero weights; they stay zero)
-  if (xe) *reinterpret_cast<uint4 *>(xe + pix * cstride) = *reinterpret_cast<const uint4 *>(ev);
+  // One store per pixel covering the whole e block (channels 2C.. of it are padding that multiplies zero weights and
+  // stays zero).  When the block is 16 channels = one 32-byte sector the store is 256 bits wide: a 16-byte store
+  // leaves half a sector untouched and makes L2 read it back from DRAM first (ncu: 86 MB read per launch, 61 MB of
+  // them for nothing).
+  if (xe) {
+    const uint4 lo = *reinterpret_cast<const uint4 *>(ev);
+    if (epad >= 16)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %5, %5, %5};" ::"l"(xe + pix * cstride), "r"(lo.x),
+                   "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(0u)
+                   : "memory");
+    else
+      *reinterpret_cast<uint4 *>(xe + pix * cstride) = lo;
+  }
 }
 
 __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
@@ -1645,13 +1657,13 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
       memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
       memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
       ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
-                                            T->cx[0]);
+                                            T->cx[0], T->epad[0]);
     } else {
       Ahat0W<1> wb;
       memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
       memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
       ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
-                                            T->cx[0]);
+                                            T->cx[0], T->epad[0]);
     }
     TZ_CHECK_LAUNCH();
     h->x0_staged = true;
