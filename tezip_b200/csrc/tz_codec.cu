@@ -373,44 +373,66 @@ __device__ __forceinline__ void eb_plane_tiles(EbTileSmem<EB_T> &sm, int16_t *__
     const int nch = (Tn + 31) >> 5;
     // ---------------------------------------------------------------- S1
     {
+      // two chunks per pass (c and c + EB_WARPS): their shuffle chains are independent, which doubles the
+      // instruction-level parallelism of a warp
+      constexpr int U = 2;
       const int16_t *dp = d + (long long)(tile + tid) * C;
-      for (int c = warp; c < nch; c += EB_WARPS, dp += (long long)EB_THREADS * C) {
-        const int i = 32 * c + lane;
-        const uint32_t v = (i < Tn) ? ebp_pack((int)*dp) : EBP_ID;
-        uint32_t pre = v;
+      for (int c = warp; c < nch; c += U * EB_WARPS, dp += (long long)U * EB_THREADS * C) {
+        int i[U];
+        uint32_t v[U], pre[U], M[5][U], run[U], pk[U];
+        int pos[U];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const uint32_t u = __shfl_up_sync(FULL, pre, off);
-          pre = ebp_join(pre, (lane >= off) ? u : EBP_ID);
+        for (int u = 0; u < U; u++) {
+          i[u] = 32 * (c + u * EB_WARPS) + lane;
+          v[u] = (i[u] < Tn) ? ebp_pack((int)dp[(long long)u * EB_THREADS * C]) : EBP_ID;
+          pre[u] = v[u];
+          M[0][u] = v[u];
+          run[u] = v[u];
+          pos[u] = lane + 1;
         }
-        uint32_t M[5];   // M[k][j] = join(v[j .. j + 2^k)), identity beyond the chunk
-        M[0] = v;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t u = __shfl_down_sync(FULL, M[k], 1 << k);
-          M[k + 1] = ebp_join(M[k], (lane + (1 << k) < 32) ? u : EBP_ID);
-        }
-        uint32_t run = v;
-        int pos = lane + 1;
+        for (int off = 1; off < 32; off <<= 1)
 #pragma unroll
-        for (int k = 4; k >= 0; k--) {   // binary lifting: the longest unbroken [lane, pos)
-          const uint32_t nx = ebp_join(run, __shfl_sync(FULL, M[k], pos));
-          const bool ok = (pos + (1 << k) <= 32) & !ebp_broken(nx, G1);
-          run = ok ? nx : run;
-          pos = ok ? pos + (1 << k) : pos;
-        }
-        uint32_t pk = ((uint32_t)pos << 8) | (uint32_t)lane;   // (next start, last start visited)
+          for (int u = 0; u < U; u++) {
+            const uint32_t t = __shfl_up_sync(FULL, pre[u], off);
+            pre[u] = ebp_join(pre[u], (lane >= off) ? t : EBP_ID);
+          }
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-          const uint32_t u = __shfl_sync(FULL, pk, pk >> 8);
-          pk = (pk < (32u << 8)) ? u : pk;
+        for (int k = 0; k < 4; k++)   // M[k][j] = join(v[j .. j + 2^k)), identity beyond the chunk
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t t = __shfl_down_sync(FULL, M[k][u], 1 << k);
+            M[k + 1][u] = ebp_join(M[k][u], (lane + (1 << k) < 32) ? t : EBP_ID);
+          }
+#pragma unroll
+        for (int k = 4; k >= 0; k--)   // binary lifting: the longest unbroken [lane, pos)
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t nx = ebp_join(run[u], __shfl_sync(FULL, M[k][u], pos[u]));
+            const bool ok = (pos[u] + (1 << k) <= 32) & !ebp_broken(nx, G1);
+            run[u] = ok ? nx : run[u];
+            pos[u] = ok ? pos[u] + (1 << k) : pos[u];
+          }
+#pragma unroll
+        for (int u = 0; u < U; u++) pk[u] = ((uint32_t)pos[u] << 8) | (uint32_t)lane;   // (next start, last start visited)
+#pragma unroll
+        for (int r = 0; r < 5; r++)
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t t = __shfl_sync(FULL, pk[u], pk[u] >> 8);
+            pk[u] = (pk[u] < (32u << 8)) ? t : pk[u];
+          }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t ex = __shfl_sync(FULL, run[u], pk[u]);   // lane = pk & 31 = last
+          if (c + u * EB_WARPS < nch) {   // warp-uniform
+            sm.pre[i[u]] = pre[u];
+            sm.run[i[u]] = run[u];
+            sm.exitst[i[u]] = ex;
+            sm.meta[i[u]] = (uint16_t)((uint32_t)pos[u] | ((pk[u] & 0xffu) << 8));
+            if (lane == 0) sm.entry[c + u * EB_WARPS] = 0xff;
+          }
         }
-        const uint32_t ex = __shfl_sync(FULL, run, pk);   // lane = pk & 31 = last
-        sm.pre[i] = pre;
-        sm.run[i] = run;
-        sm.exitst[i] = ex;
-        sm.meta[i] = (uint16_t)((uint32_t)pos | ((pk & 0xffu) << 8));
-        if (lane == 0) sm.entry[c] = 0xff;
       }
     }
     __syncthreads();
@@ -485,30 +507,45 @@ __device__ __forceinline__ void eb_plane_tiles(EbTileSmem<EB_T> &sm, int16_t *__
       }
     }
     {
+      constexpr int U = 2;   // two chunks per pass, as in S1
       int16_t *dp = d + (long long)(tile + tid) * C;
-      for (int c = warp; c < nch && 32 * c < open_from; c += EB_WARPS, dp += (long long)EB_THREADS * C) {
-        const int i = 32 * c + lane;
-        const int ent = sm.entry[c];
-        uint32_t st = sm.inst[c];
-        if (ent != 0xff) {
-          const int nb = sm.meta[i] & 0xff;
-          const uint32_t run = sm.run[i];
-          unsigned R = 1u << ent;   // starts reachable from the entry
-          int J = nb;
+      for (int c = warp; c < nch && 32 * c < open_from; c += U * EB_WARPS, dp += (long long)U * EB_THREADS * C) {
+        int i[U], ent[U], nb[U], J[U];
+        uint32_t st[U], run[U];
+        unsigned R[U];
+        bool live[U];
 #pragma unroll
-          for (int r = 0; r < 5; r++) {
-            const unsigned tgt = ((R >> lane) & 1u) << (J & 31);
-            R |= __reduce_or_sync(FULL, (J < 32) ? tgt : 0u);
-            const int u = __shfl_sync(FULL, J, J);
-            J = (J < 32) ? u : 32;
-          }
-          const int s = 31 - __clz((int)(R & (0xffffffffu >> (31 - lane))));   // -1 for lanes before the entry
-          const int nb_s = __shfl_sync(FULL, nb, s);
-          const uint32_t run_s = __shfl_sync(FULL, run, s);
-          const uint32_t own = (nb_s >= 32) ? sm.outst[c] : run_s;
-          st = (lane >= ent) ? own : st;
+        for (int u = 0; u < U; u++) {
+          const int cu = c + u * EB_WARPS;
+          live[u] = cu < nch && 32 * cu < open_from;   // warp-uniform
+          const int cc = live[u] ? cu : c;             // a dead second chunk replays the first (results unused)
+          i[u] = 32 * cc + lane;
+          ent[u] = sm.entry[cc];
+          st[u] = sm.inst[cc];
+          nb[u] = sm.meta[i[u]] & 0xff;
+          run[u] = sm.run[i[u]];
+          R[u] = (ent[u] != 0xff) ? 1u << ent[u] : 0u;   // starts reachable from the entry
+          J[u] = nb[u];
         }
-        if (i < min(Tn, open_from)) *dp = ebp_mid<EXACT>(st, E);
+#pragma unroll
+        for (int r = 0; r < 5; r++)
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned tgt = ((R[u] >> lane) & 1u) << (J[u] & 31);
+            R[u] |= __reduce_or_sync(FULL, (J[u] < 32) ? tgt : 0u);
+            const int t = __shfl_sync(FULL, J[u], J[u]);
+            J[u] = (J[u] < 32) ? t : 32;
+          }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int cu = live[u] ? c + u * EB_WARPS : c;
+          const int s = 31 - __clz((int)(R[u] & (0xffffffffu >> (31 - lane))));   // -1 for lanes before the entry
+          const int nb_s = __shfl_sync(FULL, nb[u], s);
+          const uint32_t run_s = __shfl_sync(FULL, run[u], s);
+          const uint32_t own = (nb_s >= 32) ? sm.outst[cu] : run_s;
+          if (ent[u] != 0xff && lane >= ent[u]) st[u] = own;
+          if (live[u] && i[u] < min(Tn, open_from)) dp[(long long)u * EB_THREADS * C] = ebp_mid<EXACT>(st[u], E);
+        }
       }
     }
     __syncthreads();
