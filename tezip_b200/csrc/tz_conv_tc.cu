@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
                                                     float *__restrict__ out, int H, int W, float clip,
                                                     const float *__restrict__ p0, __half *__restrict__ xe, int cstride,
                                                     int epad) {
-  constexpr int TW = 32, TH = 8;                 // output pixels per block: a warp is one image row of the tile
+  constexpr int TW = 32, TH = 16, PT = TH / 8;   // output pixels per block; a warp is one image row, PT rows per thread
   __shared__ float tile[TH + 2][(TW + 2) * C];
   const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const float *src = r0 + (long long)b * H * W * C;
@@ -1037,49 +1037,53 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
     }
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = x0 + tx, y = y0 + ty;
-  if (x >= W || y >= H) return;
-  float acc[C];
+  const int tx = threadIdx.x & 31;
+  const int x = x0 + tx;
 #pragma unroll
-  for (int co = 0; co < C; co++) acc[co] = 0.0f;
+  for (int pt = 0; pt < PT; pt++) {
+    const int ty = (threadIdx.x >> 5) + 8 * pt;
+    const int y = y0 + ty;
+    if (x >= W || y >= H) continue;
+    float acc[C];
 #pragma unroll
-  for (int ky = 0; ky < 3; ky++)
+    for (int co = 0; co < C; co++) acc[co] = 0.0f;
 #pragma unroll
-    for (int kx = 0; kx < 3; kx++)
+    for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-      for (int ci = 0; ci < C; ci++) {
-        const float v = tile[ty + ky][(tx + kx) * C + ci];
+      for (int kx = 0; kx < 3; kx++)
 #pragma unroll
-        for (int co = 0; co < C; co++) acc[co] = fmaf(v, wb.w[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
+        for (int ci = 0; ci < C; ci++) {
+          const float v = tile[ty + ky][(tx + kx) * C + ci];
+#pragma unroll
+          for (int co = 0; co < C; co++) acc[co] = fmaf(v, wb.w[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
+        }
+    const long long pix = ((long long)b * H + y) * W + x;
+    float *dst = out + pix * C;
+    __align__(16) __half ev[8];   // [relu(ahat - a) x C | relu(a - ahat) x C | zeros]: 2C <= 6 of the 8 lanes
+#pragma unroll
+    for (int j = 0; j < 8; j++) ev[j] = __float2half_rn(0.0f);
+#pragma unroll
+    for (int co = 0; co < C; co++) {
+      const float a = fminf(fmaxf(acc[co] + wb.b[co], 0.0f), clip);
+      dst[co] = a;
+      if (xe) {   // prednet.py:274-277 of the NEXT step at layer 0, t = 0 (as e0_tc_kernel)
+        const float ah = p0[((long long)y * W + x) * C + co];
+        ev[co] = __float2half_rn(fmaxf(__fsub_rn(ah, a), 0.0f));
+        ev[C + co] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
       }
-  const long long pix = ((long long)b * H + y) * W + x;
-  float *dst = out + pix * C;
-  __align__(16) __half ev[8];   // [relu(ahat - a) x C | relu(a - ahat) x C | zeros]: 2C <= 6 of the 8 lanes
-#pragma unroll
-  for (int j = 0; j < 8; j++) ev[j] = __float2half_rn(0.0f);
-#pragma unroll
-  for (int co = 0; co < C; co++) {
-    const float a = fminf(fmaxf(acc[co] + wb.b[co], 0.0f), clip);
-    dst[co] = a;
-    if (xe) {   // prednet.py:274-277 of the NEXT step at layer 0, t = 0 (as e0_tc_kernel)
-      const float ah = p0[((long long)y * W + x) * C + co];
-      ev[co] = __float2half_rn(fmaxf(__fsub_rn(ah, a), 0.0f));
-      ev[C + co] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
     }
-  }
-  // One store per pixel covering the whole e block (channels 2C.. of it are padding that multiplies zero weights and
-  // stays zero).  When the block is 16 channels = one 32-byte sector the store is 256 bits wide: a 16-byte store
-  // leaves half a sector untouched and makes L2 read it back from DRAM first (ncu: 86 MB read per launch, 61 MB of
-  // them for nothing).
-  if (xe) {
-    const uint4 lo = *reinterpret_cast<const uint4 *>(ev);
-    if (epad >= 16)
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %5, %5, %5};" ::"l"(xe + pix * cstride), "r"(lo.x),
-                   "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(0u)
-                   : "memory");
-    else
-      *reinterpret_cast<uint4 *>(xe + pix * cstride) = lo;
+    // One store per pixel covering the whole e block (channels 2C.. of it are padding that multiplies zero weights
+    // and stays zero).  When the block is 16 channels = one 32-byte sector the store is 256 bits wide: a 16-byte
+    // store leaves half a sector untouched and makes L2 read it back from DRAM first.
+    if (xe) {
+      const uint4 lo = *reinterpret_cast<const uint4 *>(ev);
+      if (epad >= 16)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %5, %5, %5};" ::"l"(xe + pix * cstride), "r"(lo.x),
+                     "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(0u)
+                     : "memory");
+      else
+        *reinterpret_cast<uint4 *>(xe + pix * cstride) = lo;
+    }
   }
 }
 
@@ -1651,7 +1655,7 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
   }
   int rc = TZ_OK;
   if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
-    dim3 grid((h->W[0] + 31) / 32, (h->H[0] + 7) / 8, B);
+    dim3 grid((h->W[0] + 31) / 32, (h->H[0] + 15) / 16, B);
     if (h->S[0] == 3) {
       Ahat0W<3> wb;
       memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
