@@ -205,6 +205,10 @@ struct ConvArgs {
                                  // so G epilogues are in flight and their latency overlaps
   int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
   int mma_issuers;               // halo + stationary weights: 2 warps issue the MMAs of alternate tiles, else 1
+  int pool_cols;                 // A path, halo + stationary weights: the four pixels of a 2x2 pooling window are
+                                 // four COLUMN groups of one accumulator row (tile = 8x16 POOLED pixels), see make_conv
+  uint32_t desc_hi_pc;           // pool_cols: high word of the A descriptors (groups one sub-box row of 9 pixels apart)
+  uint32_t pc_slot;              // pool_cols: bytes per parity sub-box slot inside a stage
   int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
   int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
   int sub_stride;                // TMEM columns between the accumulators of the two M tiles of a pair
@@ -270,7 +274,9 @@ __device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo,
 // ------------------------------------------------------------------------------------------------ the kernel
 // TWO = CTA-pair instantiation (launched as clusters of 2): kernels that contain cta_group::2 instructions can only
 // be launched with a matching cluster size, so the one-CTA modes use the TWO = false instantiation.
-template <int EPI, bool TWO>  // EPI 0: A path (pool + E), 1: R path (LSTM)
+// POOLC = the pooling-in-accumulator-columns variant of the one-CTA A path (its own instantiation: its epilogue
+// keeps prefetched Ahat0 values live across the accumulator wait, which the other variants have no registers for).
+template <int EPI, bool TWO, bool POOLC = false>  // EPI 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -379,7 +385,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t b_lo = (((smem0 + ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-        if (elect_one()) {
+        if (POOLC) {
+          if (elect_one()) {
+            // 4 window positions x 9 taps (x ksteps): A starts at box pixel (py+dy+1, px+dx+1) = (q, o)
+            const uint32_t pix16 = rowb >> 4, ks = (uint32_t)P.ksteps;
+            const uint32_t slot16 = P.pc_slot >> 4;
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {   // straight-line: 36 * ksteps MMAs, offsets are small multiples of two values
+              const uint32_t dcol = d_tmem + (uint32_t)pp * (uint32_t)P.n_tile;
+#pragma unroll
+              for (int tap = 0; tap < 9; tap++) {
+                // q = py + dy + 1, o = px + dx + 1 in 0..3: odd sub-box for q = 0, 2, shift one row for q >= 2
+                const uint32_t q = (uint32_t)((pp >> 1) + tap / 3), o = (uint32_t)((pp & 1) + tap % 3);
+                const uint32_t sb = (((q + 1u) & 1u) << 1) | ((o + 1u) & 1u);
+                const uint32_t al = a_lo + sb * slot16 + ((q >> 1) * 9u + (o >> 1)) * pix16;
+                const uint32_t bl = b_lo + (uint32_t)tap * btap16;
+                if (ks == 1) {
+                  tc_mma_f16(dcol, make_desc(al, P.desc_hi_pc), make_desc(bl, hi), idesc, tap != 0 || ch != 0);
+                } else {
+                  for (uint32_t k = 0; k < ks; k++)
+                    tc_mma_f16(dcol, make_desc(al + 2 * k, P.desc_hi_pc), make_desc(bl + 2 * k, hi), idesc,
+                               (tap | (int)k) != 0 || ch != 0);
+                }
+              }
+            }
+            tc_commit(empty0 + 8 * s);
+            if (ch + 1 == kch) tc_commit(tfull0 + 8 * a);
+          }
+        } else if (elect_one()) {
           if (P.ksteps == 4)
             issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
           else if (P.ksteps == 2)
@@ -486,7 +519,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (elect_one()) {
               const uint32_t full = full0 + 8 * s;
               mbar_expect_tx(full, P.tx_bytes);
-              tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
+              if (POOLC) {   // sub-box (by, bx): rows 2*h0 - by + 2j, pixels 2*w0 - bx + 2i
+                const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
+#pragma unroll
+                for (int sb = 0; sb < 4; sb++)
+                  tma_load_4d(sa + (uint32_t)sb * P.pc_slot, &tmA, full, c, 2 * w0 - (sb & 1), 2 * h0 - (sb >> 1), b0);
+              } else
+                tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
             }
             __syncwarp();
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
@@ -703,6 +742,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tbi = fast_div(mq, P.m_tiles_h);
       const int thi = mq - tbi * P.tiles_h;
       const int w = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
+      // pool_cols: Ahat0 of this lane's pooled pixel for the first two of this warp's chunks is requested BEFORE
+      // waiting for the accumulator: its L2 latency (~1000 cycles) then hides behind the MMAs of the tile
+      float alp[POOLC ? 2 : 1][8];
+      if (EPI == 0 && POOLC) {
+        const int hp = thi * P.tile_h + th;
+        if ((b < P.B) && (2 * hp < P.H) && (2 * w < P.W)) {
+          const float *ahp = P.ahat_next + ((long long)hp * (P.W >> 1) + w) * P.S_next + nt * P.n_tile;
+          const int nr = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            if (8 * (part + c * nparts) < nr) ldg256(ahp + 8 * (part + c * nparts), alp[c]);
+        }
+      }
       if (edbg) ec0 = clock64();
       mbar_wait(tfull0 + 8 * a, aph);
       if (edbg) {
@@ -714,10 +766,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       for (int sub = 0; sub < P.sub_tiles; sub++) {
       const int h = thi * P.tile_h + (sub << P.th_log) + th;
-      const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
+      const bool valid = POOLC ? (b < P.B) && (2 * h < P.H) && (2 * w < P.W) : (b < P.B) && (h < P.H) && (w < P.W);
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride +
                             sub * (uint32_t)P.sub_stride;
-      if (EPI == 0) {
+      if (EPI == 0 && POOLC) {
+        // (w, h) are POOLED coordinates here.  a = relu(max over the four column groups + bias); e = [relu(ahat - a),
+        // relu(a - ahat)]: 32 contiguous bytes per lane, no cross-lane traffic.
+        const int Ho = P.H >> 1, Wo = P.W >> 1;
+        const long long opix = ((long long)b * Ho + h) * Wo + w;
+        const float *ah = P.ahat_next + ((long long)h * Wo + w) * P.S_next;
+        __half *dst = P.xe_out + opix * P.xe_cstride;
+        const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
+        auto pchunk = [&](int j0, const float *al) {
+          const int ch0 = nt * P.n_tile + j0;
+          float mx[8], v1[8], v2[8], v3[8];
+          tc_ld8(trow + 0 * P.n_tile + j0, mx);
+          tc_ld8(trow + 1 * P.n_tile + j0, v1);
+          tc_ld8(trow + 2 * P.n_tile + j0, v2);
+          tc_ld8(trow + 3 * P.n_tile + j0, v3);
+          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.bias + ch0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4 *>(P.bias + ch0 + 4));
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          tc_ld_wait();
+          if (valid) {
+            __align__(16) __half up[8], dn[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float m4 = fmaxf(fmaxf(mx[j], v1[j]), fmaxf(v2[j], v3[j]));
+              const float a_ = fmaxf(__fadd_rn(m4, bb[j]), 0.0f);
+              up[j] = __float2half_rn(fmaxf(__fsub_rn(al[j], a_), 0.0f));
+              dn[j] = __float2half_rn(fmaxf(__fsub_rn(a_, al[j]), 0.0f));
+            }
+            *reinterpret_cast<uint4 *>(dst + ch0) = *reinterpret_cast<const uint4 *>(up);
+            *reinterpret_cast<uint4 *>(dst + P.S_next + ch0) = *reinterpret_cast<const uint4 *>(dn);
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int j0 = 8 * (part + c * nparts);
+          if (j0 < n_real) pchunk(j0, alp[c]);
+        }
+        for (int j0 = 8 * (part + 2 * nparts); j0 < n_real; j0 += 8 * nparts) {   // more than two chunks per warp
+          float al[8];
+          if (valid) ldg256(ah + nt * P.n_tile + j0, al);
+          pchunk(j0, al);
+        }
+      } else if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
         const bool writer = valid && ((tw & 1) == 0) && ((th & 1) == 0);
@@ -1313,6 +1407,24 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       return TZ_EINVAL;
     }
   }
+  // ---- pooling in accumulator columns (A path, halo + stationary weights, KC = 16 or 32).  TMA gathers the input
+  // tile by pixel parity: the tensor map has element strides {1, 2, 2, 1}, so one copy brings the even (or odd)
+  // columns of the even (or odd) rows of the 18 x 34-pixel halo region as a dense 9 x 17 sub-box -- space-to-depth
+  // on the fly, four copies per chunk.  For window position (py, px) and tap (dy, dx) the input pixel of pooled
+  // pixel (Y, X) is (2Y + py + dy, 2X + px + dx): a fixed sub-box (the parities of py+dy, px+dx) read at a fixed
+  // shift of 0 or 1 rows / pixels -- an ordinary shifted descriptor.  The MMA of that (position, tap) accumulates
+  // into column group 2*py+px, so one accumulator row holds all four candidates of a pooled pixel: the epilogue
+  // takes the maximum in registers (no shuffles, every lane a writer, 4x fewer tiles).
+  A.pool_cols = 0;
+  // Opt-in (TZ_POOLCOL=1): correct (the parity tests pass with it) but only ~10 % faster than the shuffle epilogue on
+  // a0 (0.093 vs 0.102 ms): in situ the 36 N=48 MMAs of a tile take ~2.7 k cycles and the epilogue ~2.8 k, and with
+  // room for only two accumulator stages (4 x 48 columns each) they overlap poorly.
+  if (epi == 0 && A.halo == 1 && getenv("TZ_POOLCOL") && (A.KC == 16 || A.KC == 32) && 4 * A.n_tile <= 256 &&
+      (A.H % 2) == 0 && (A.W % 2) == 0) {
+    A.pool_cols = 1;
+    A.tiles_w = (A.W / 2 + 7) >> 3;
+    A.tiles_h = (A.H / 2 + 15) >> 4;
+  }
   rows_total = A.n_tiles_n * A.n_tile;
   const int Ktot = 9 * A.cin_pad;
   // ---- pack weights: row n (tile-major; gates interleaved per tile), K-major, k = tap*cin_pad + c
@@ -1389,6 +1501,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.a_stride = 0;
     A.stage_stride = (16u * 18u * row_bytes + 1023u) & ~1023u;   // one halo tile: 18 image rows x 16 pixels x KC channels
     A.tx_bytes = 16u * 18u * row_bytes;
+    if (A.pool_cols) {   // four parity sub-boxes of 17 rows x 9 pixels: a 16 x 32 input tile + halo
+      A.pc_slot = (9u * 17u * row_bytes + 1023u) & ~1023u;
+      A.stage_stride = 4u * A.pc_slot;
+      A.tx_bytes = 4u * 9u * 17u * row_bytes;
+    }
     stages = (int)((224u * 1024u - A.b_region) / A.stage_stride);
     if (stages > 4) stages = 4;
     if (stages < 2) {
@@ -1420,6 +1537,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         A.acc_stride = 0;
         A.sub_stride = 256;
       }
+    } else if (A.pool_cols) {      // four column groups of n_tile per stage
+      A.epi_warps = 12;
+      A.epi_groups = 1;
+      A.acc_stages = 2;
+      A.acc_stride = 256;
     } else if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
       A.epi_warps = 12;
       A.epi_groups = 3;
@@ -1439,7 +1561,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     // the same issuer, i.e. one chunk per tile and even ring sizes (otherwise a wait one full phase ahead returns
     // at once -- seen as a launch failure on a1, three chunks per tile, when this was unconditional).
     const char *env = getenv("TZ_MMA_ISSUERS");   // A/B switch
-    A.mma_issuers = (A.halo == 1 && A.kchunks == 1 && (A.stages % 2) == 0 && (A.acc_stages % 2) == 0 &&
+    // (not in the pooled variant: its two accumulator stages pipeline better when one tile's MMAs finish first)
+    A.mma_issuers = (A.halo == 1 && !A.pool_cols && A.kchunks == 1 && (A.stages % 2) == 0 && (A.acc_stages % 2) == 0 &&
                      !(env && env[0] == '1')) ? 2 : 1;
   }
   // ---- descriptors
@@ -1448,6 +1571,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   const uint32_t layout_type = A.KC == 64 ? 2u : A.KC == 32 ? 4u : 6u;   // UMMA SWIZZLE_128B / 64B / 32B
   const uint32_t sbo = 8u * row_bytes;                                   // 8-row core-matrix group stride
   A.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+  if (A.pool_cols)   // 8-row groups (pooled rows) are one sub-box row of 9 pixels apart
+    A.desc_hi_pc = (((9u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
   A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | (((A.halo == 4 ? 256u : 128u) >> 4) << 24);   // f32 acc, f16 x f16, K-major
   {
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
@@ -1457,8 +1582,13 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       box[1] = (A.halo == 2 || A.halo == 4) ? 10 : 16;
       box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
+      if (A.pool_cols) {
+        box[1] = 18;
+        box[2] = 34;
+      }
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
+    if (A.pool_cols) es[1] = es[2] = 2;   // every other pixel of every other row: the box extent stays 18 x 34
     CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1508,6 +1638,7 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     TZ_CHECK_CUDA(cudaMemcpy(T->ahat0_b, h->b_ahat[0], sizeof(float) * C, cudaMemcpyDeviceToHost));
   }
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -1605,7 +1736,10 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
       return TZ_ECUDA;
     }
   } else if (c->epi == 0)
-    conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    if (A.pool_cols)
+      conv_tc_kernel<0, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    else
+      conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   else
     conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   TZ_CHECK_LAUNCH();
