@@ -18,6 +18,7 @@
 // Determinism: one kernel configuration per layer, no split-K, no atomics; each output element is a fixed-order
 // sum over K inside the tensor core, independent of batch size, tile position and grid size.
 #include "tz_prednet.cuh"
+#include <type_traits>
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -25,6 +26,9 @@
 
 #ifndef TZ_EPI_DEBUG
 #define TZ_EPI_DEBUG 0
+#endif
+#ifndef TZ_PHASE_PROTO
+#define TZ_PHASE_PROTO 0
 #endif
 
 namespace tz {
@@ -209,6 +213,14 @@ struct ConvArgs {
                                  // four COLUMN groups of one accumulator row (tile = 8x16 POOLED pixels), see make_conv
   uint32_t desc_hi_pc;           // pool_cols: high word of the A descriptors (groups one sub-box row of 9 pixels apart)
   uint32_t pc_slot;              // pool_cols: bytes per parity sub-box slot inside a stage
+  // phase_r (R path, layer with an up-sampled input): the accumulator holds four column groups, one per output-pixel
+  // parity; the e block is gathered by parity as in pool_cols, the up(r_{l+1}) block is read from the LOW-resolution
+  // r_{l+1} with 2x2 taps whose weights are the sums of the 3x3 taps that fall on the same low-resolution pixel
+  int phase_r, r_chunks;         // r_chunks = R_{l+1} / 16
+  int kblocks_total;             // stationary K16 weight blocks: 9 (e taps) + 4 phases * 4 taps * r_chunks
+  uint32_t pr_slot, desc_hi_pr;  // bytes per low-resolution chunk box (18 rows x 10 pixels x 16 ch) / its descriptor
+  __half *rl_out;                // if set: r is ALSO written at its own resolution, [B, H, W, rl_cstride] fp16
+  int rl_cstride;
   int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
   int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
   int sub_stride;                // TMEM columns between the accumulators of the two M tiles of a pair
@@ -276,9 +288,11 @@ __device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo,
 // be launched with a matching cluster size, so the one-CTA modes use the TWO = false instantiation.
 // POOLC = the pooling-in-accumulator-columns variant of the one-CTA A path (its own instantiation: its epilogue
 // keeps prefetched Ahat0 values live across the accumulator wait, which the other variants have no registers for).
-template <int EPI, bool TWO, bool POOLC = false>  // EPI 0: A path (pool + E), 1: R path (LSTM)
+// PHASE = the parity-phase variant of the one-CTA R path (see ConvArgs::phase_r); tmC is its low-resolution map.
+template <int EPI, bool TWO, bool POOLC = false, bool PHASE = false>  // EPI 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1 + 4];
   __shared__ uint32_t tmem_base_s;
@@ -304,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = two ? ((tiles_img * tiles_b + 1) >> 1) * P.n_tiles_n : tiles_img * tiles_b * P.n_tiles_n;
   const int t_first = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int kblocks = 9 * P.kchunks;
+  const int kblocks = PHASE ? P.kblocks_total : 9 * P.kchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; s++) {
@@ -385,7 +399,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t b_lo = (((smem0 + ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-        if (POOLC) {
+        if (PHASE) {
+          if (elect_one()) {
+            const uint32_t slot16 = P.pc_slot >> 4, rslot16 = P.pr_slot >> 4, bb16 = P.b_block >> 4;
+            const uint32_t r_lo = a_lo + 4u * slot16;
+            // straight-line issue (the issue loop's scalar work is what bounds narrow MMAs): everything below unrolls
+            // to MMAs whose descriptor offsets are sums of loop-invariant values; NRC is the usual R_{l+1} / 16
+            auto issue_all = [&](auto nrc_tag) {
+              constexpr uint32_t NRC = decltype(nrc_tag)::value;
+              const uint32_t nrc = NRC ? NRC : (uint32_t)P.r_chunks;
+#pragma unroll
+              for (uint32_t pp = 0; pp < 4; pp++) {   // output parity (qy, qx) -> column group pp
+                const uint32_t dcol = d_tmem + pp * (uint32_t)P.n_tile;
+                const uint32_t qy = pp >> 1, qx = pp & 1u;
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {   // e block: 3x3 taps on the parity sub-boxes
+                  const uint32_t q = qy + (uint32_t)(tap / 3), o = qx + (uint32_t)(tap % 3);
+                  const uint32_t sb = (((q + 1u) & 1u) << 1) | ((o + 1u) & 1u);
+                  const uint32_t al = a_lo + sb * slot16 + ((q >> 1) * 9u + (o >> 1)) * 2u;
+                  tc_mma_f16(dcol, make_desc(al, P.desc_hi_pc), make_desc(b_lo + (uint32_t)tap * bb16, hi), idesc, tap != 0);
+                }
+#pragma unroll
+                for (int t4 = 0; t4 < 4; t4++) {      // r block: 2x2 taps on the low-resolution boxes
+                  const uint32_t off = ((qy + (uint32_t)(t4 >> 1)) * 10u + qx + (uint32_t)(t4 & 1)) * 2u;
+#pragma unroll
+                  for (uint32_t c = 0; c < (NRC ? NRC : 1u); c++) {
+                    if (NRC) {
+                      tc_mma_f16(dcol, make_desc(r_lo + c * rslot16 + off, P.desc_hi_pr),
+                                 make_desc(b_lo + (9u + (pp * 4u + (uint32_t)t4) * NRC + c) * bb16, hi), idesc, 1);
+                    } else {
+                      for (uint32_t cc = 0; cc < nrc; cc++)
+                        tc_mma_f16(dcol, make_desc(r_lo + cc * rslot16 + off, P.desc_hi_pr),
+                                   make_desc(b_lo + (9u + (pp * 4u + (uint32_t)t4) * nrc + cc) * bb16, hi), idesc, 1);
+                    }
+                  }
+                }
+              }
+            };
+            if (P.r_chunks == 3) issue_all(std::integral_constant<uint32_t, 3>{});
+            else issue_all(std::integral_constant<uint32_t, 0>{});
+            tc_commit(empty0 + 8 * s);
+            tc_commit(tfull0 + 8 * a);
+          }
+        } else if (POOLC) {
           if (elect_one()) {
             // 4 window positions x 9 taps (x ksteps): A starts at box pixel (py+dy+1, px+dx+1) = (q, o)
             const uint32_t pix16 = rowb >> 4, ks = (uint32_t)P.ksteps;
@@ -514,6 +570,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
         } else if (P.halo == 1) {
           // halo mode: per chunk ONE box of (TH+2) x 16 pixels; the nine taps read it through shifted descriptors
+          if (PHASE) {   // one stage per region: 4 parity sub-boxes of e + r_chunks low-resolution boxes of r_{l+1}
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = full0 + 8 * s;
+              mbar_expect_tx(full, P.tx_bytes);
+              const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
+#pragma unroll
+              for (int sb = 0; sb < 4; sb++)
+                tma_load_4d(sa + (uint32_t)sb * P.pc_slot, &tmA, full, 0, 2 * w0 - (sb & 1), 2 * h0 - (sb >> 1), b0);
+              for (int c = 0; c < P.r_chunks; c++)
+                tma_load_4d(sa + 4u * P.pc_slot + (uint32_t)c * P.pr_slot, &tmC, full, 16 * c, w0 - 1, h0 - 1, b0);
+            }
+            __syncwarp();
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+          } else
           for (int c = 0; c < P.cin_pad; c += P.KC) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
             if (elect_one()) {
@@ -741,14 +812,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int twi = mt - mq * P.tiles_w;
       const int tbi = fast_div(mq, P.m_tiles_h);
       const int thi = mq - tbi * P.tiles_h;
-      const int w = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
+      const int w_tile = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
       // pool_cols: Ahat0 of this lane's pooled pixel for the first two of this warp's chunks is requested BEFORE
       // waiting for the accumulator: its L2 latency (~1000 cycles) then hides behind the MMAs of the tile
       float alp[POOLC ? 2 : 1][8];
       if (EPI == 0 && POOLC) {
         const int hp = thi * P.tile_h + th;
-        if ((b < P.B) && (2 * hp < P.H) && (2 * w < P.W)) {
-          const float *ahp = P.ahat_next + ((long long)hp * (P.W >> 1) + w) * P.S_next + nt * P.n_tile;
+        if ((b < P.B) && (2 * hp < P.H) && (2 * w_tile < P.W)) {
+          const float *ahp = P.ahat_next + ((long long)hp * (P.W >> 1) + w_tile) * P.S_next + nt * P.n_tile;
           const int nr = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
 #pragma unroll
           for (int c = 0; c < 2; c++)
@@ -765,7 +836,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_after();
       for (int sub = 0; sub < P.sub_tiles; sub++) {
-      const int h = thi * P.tile_h + (sub << P.th_log) + th;
+      // PHASE: column group `sub` holds the output pixels of parity (sub >> 1, sub & 1) of the region
+      const int h = PHASE ? 2 * (thi * P.tile_h + th) + (sub >> 1) : thi * P.tile_h + (sub << P.th_log) + th;
+      const int w = PHASE ? 2 * w_tile + (sub & 1) : w_tile;
       const bool valid = POOLC ? (b < P.B) && (2 * h < P.H) && (2 * w < P.W) : (b < P.B) && (h < P.H) && (w < P.W);
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride +
                             sub * (uint32_t)P.sub_stride;
@@ -1014,6 +1087,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool second = jp + 8 < P.NC;
           lstm_chunk(jp, hv);
           if (second) lstm_chunk(jp + 8, hv + 8);
+#if TZ_PHASE_PROTO   // prototype builds only (TZ_NVCC_FLAGS=-DTZ_PHASE_PROTO=1): the default LSTM epilogue has no registers to spare
+          if (valid && P.rl_out) {   // r at its own resolution, for a phase_r consumer
+            __half *dl = P.rl_out + (((long long)b * P.H + h) * P.W + w) * P.rl_cstride + nt * P.NC + jp;
+            if ((jp + 16 <= P.NC) && ((P.rl_cstride | (nt * P.NC + jp)) & 15) == 0) {
+              const uint4 lo = *reinterpret_cast<const uint4 *>(hv), hi4 = *reinterpret_cast<const uint4 *>(hv + 8);
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dl), "r"(lo.x), "r"(lo.y),
+                           "r"(lo.z), "r"(lo.w), "r"(hi4.x), "r"(hi4.y), "r"(hi4.z), "r"(hi4.w)
+                           : "memory");
+            } else {
+              for (int j = 0; j < 16 && jp + j < P.NC; j++) dl[j] = hv[j];
+            }
+          }
+#endif
           if (valid && P.xr_out) {
             // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
             const int H2 = P.H * 2, W2 = P.W * 2;
@@ -1188,7 +1274,7 @@ __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restr
 
 // ------------------------------------------------------------------------------------------------ host side
 struct ConvTc {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;   // tmC: low-resolution r map of the phase_r variant (a copy of tmA otherwise)
   ConvArgs args;
   int epi;
   uint32_t smem_bytes;
@@ -1206,6 +1292,7 @@ struct TcState {
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
   int sm_count;
+  __half *RL1;                // r_1 at its own resolution (phase_r prototype), else nullptr
   float ahat0_w[9 * 3 * 3], ahat0_b[3];   // host copy of the layer-0 A-hat kernel (C = R_0 = S_0 <= 3), passed by value
 };
 
@@ -1256,9 +1343,12 @@ static void pick_tile(int H, int W, bool pool, int *tw_log, int *th_log, int *tb
 
 // cmap[i] = input-channel row of the fp32 kernel that multiplies channel i of the activation buffer X (-1: none,
 // the packed weight is zero).  The conv reads channels [0, round_up(cmap.size(), 16)) of X.
+// rmap/RL: phase_r request -- rmap[i] = row of wsrc that multiplies channel i of up(r_{l+1}), RL = the tensor that
+// holds r_{l+1} at its own resolution ([maxB, H/2, W/2, rmap.size()] fp16); cmap then covers the e block only.
 static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx, const std::vector<int> &cmap,
                      const std::vector<float> &wsrc /*fp32 [3][3][cin_w][cout_w]*/, int cin_w, int cout_w,
-                     int n_real /*output channels or R*/) {
+                     int n_real /*output channels or R*/, const std::vector<int> *rmap = nullptr,
+                     __half *RL = nullptr) {
   const int cin_real = (int)cmap.size();
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -1425,8 +1515,21 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.tiles_w = (A.W / 2 + 7) >> 3;
     A.tiles_h = (A.H / 2 + 15) >> 4;
   }
+  A.phase_r = 0;
+  if (rmap) {
+    if (!(epi == 1 && A.halo == 1 && A.KC == 16 && A.kchunks == 1 && (rmap->size() % 16) == 0 && (A.H % 2) == 0 &&
+          (A.W % 2) == 0 && 4 * A.n_tile <= 128 && A.n_tiles_n == 1)) {
+      set_error("internal: phase_r requested for a conv it does not fit");
+      return TZ_EINVAL;
+    }
+    A.phase_r = 1;
+    A.r_chunks = (int)rmap->size() / 16;
+    A.kblocks_total = 9 + 16 * A.r_chunks;
+    A.tiles_w = (A.W / 2 + 7) >> 3;
+    A.tiles_h = (A.H / 2 + 15) >> 4;
+  }
   rows_total = A.n_tiles_n * A.n_tile;
-  const int Ktot = 9 * A.cin_pad;
+  const int Ktot = A.phase_r ? 16 * A.kblocks_total : 9 * A.cin_pad;
   // ---- pack weights: row n (tile-major; gates interleaved per tile), K-major, k = tap*cin_pad + c
   std::vector<float> wp((size_t)rows_total * Ktot, 0.0f);
   for (int nt = 0; nt < A.n_tiles_n; nt++)
@@ -1444,6 +1547,23 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       for (int tap = 0; tap < 9; tap++)
         for (int ci = 0; ci < cin_real; ci++)
           if (cmap[ci] >= 0) dst[tap * A.cin_pad + ci] = wsrc[((size_t)tap * cin_w + cmap[ci]) * cout_w + src_col];
+      if (A.phase_r) {
+        // block 9 + (phase*4 + t4)*r_chunks + chunk: output parity (qy, qx), low-resolution tap (a, b) = (t4>>1, t4&1).
+        // A 3x3 tap dy lands on low-resolution row offset a when: qy = 0: dy = -1 -> a = 0, dy = 0, +1 -> a = 1;
+        // qy = 1: dy = -1, 0 -> a = 0, dy = +1 -> a = 1 (rows 2Y+qy+dy of the up-sampled image are row (2Y+qy+dy)>>1).
+        auto lands = [](int q, int d /*-1..1*/, int a) { return ((q + d + 2) >> 1) - 1 == a - 1 + q; };
+        const int nrc = A.r_chunks;
+        for (int pp = 0; pp < 4; pp++)
+          for (int t4 = 0; t4 < 4; t4++)
+            for (int i = 0; i < (int)rmap->size(); i++) {
+              float acc = 0.0f;
+              for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++)
+                  if (lands(pp >> 1, dy, t4 >> 1) && lands(pp & 1, dx, t4 & 1))
+                    acc += wsrc[((size_t)((dy + 1) * 3 + dx + 1) * cin_w + (*rmap)[i]) * cout_w + src_col];
+              dst[16 * (9 + (pp * 4 + t4) * nrc + i / 16) + (i % 16)] = acc;
+            }
+      }
     }
   float *tmp = nullptr;
   TZ_CHECK_CUDA(cudaMalloc(&tmp, wp.size() * sizeof(float)));
@@ -1506,6 +1626,13 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       A.stage_stride = 4u * A.pc_slot;
       A.tx_bytes = 4u * 9u * 17u * row_bytes;
     }
+    if (A.phase_r) {     // the same four sub-boxes of e + r_chunks boxes of 18 rows x 10 low-resolution pixels x 16 ch
+      A.b_region = (uint32_t)A.kblocks_total * A.b_block;
+      A.pc_slot = (9u * 17u * 32u + 1023u) & ~1023u;
+      A.pr_slot = (10u * 18u * 32u + 1023u) & ~1023u;
+      A.stage_stride = 4u * A.pc_slot + (uint32_t)A.r_chunks * A.pr_slot;
+      A.tx_bytes = 4u * 9u * 17u * 32u + (uint32_t)A.r_chunks * 10u * 18u * 32u;
+    }
     stages = (int)((224u * 1024u - A.b_region) / A.stage_stride);
     if (stages > 4) stages = 4;
     if (stages < 2) {
@@ -1537,6 +1664,14 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         A.acc_stride = 0;
         A.sub_stride = 256;
       }
+    } else if (A.phase_r) {        // four column groups (output parities) of n_tile per stage, one region per warp group
+      A.epi_warps = 12;
+      A.epi_groups = 3;
+      A.acc_stages = 4;
+      A.acc_stride = 128;
+      A.sub_tiles = 4;
+      A.sub_stride = A.n_tile;
+      A.tile_h = 16;
     } else if (A.pool_cols) {      // four column groups of n_tile per stage
       A.epi_warps = 12;
       A.epi_groups = 1;
@@ -1571,8 +1706,10 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   const uint32_t layout_type = A.KC == 64 ? 2u : A.KC == 32 ? 4u : 6u;   // UMMA SWIZZLE_128B / 64B / 32B
   const uint32_t sbo = 8u * row_bytes;                                   // 8-row core-matrix group stride
   A.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
-  if (A.pool_cols)   // 8-row groups (pooled rows) are one sub-box row of 9 pixels apart
+  if (A.pool_cols || A.phase_r)   // 8-row groups (pooled rows) are one sub-box row of 9 pixels apart
     A.desc_hi_pc = (((9u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+  if (A.phase_r)                  // low-resolution boxes: rows of 10 pixels
+    A.desc_hi_pr = (((10u * 32u) >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
   A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | (((A.halo == 4 ? 256u : 128u) >> 4) << 24);   // f32 acc, f16 x f16, K-major
   {
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
@@ -1582,18 +1719,33 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       box[1] = (A.halo == 2 || A.halo == 4) ? 10 : 16;
       box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
-      if (A.pool_cols) {
+      if (A.pool_cols || A.phase_r) {
         box[1] = 18;
         box[2] = 34;
       }
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (A.pool_cols) es[1] = es[2] = 2;   // every other pixel of every other row: the box extent stays 18 x 34
+    if (A.pool_cols || A.phase_r) es[1] = es[2] = 2;   // every other pixel of every other row: the box extent stays 18 x 34
     CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(A, layer %d) failed: %d", l, (int)r);
+      return TZ_ECUDA;
+    }
+  }
+  c->tmC = c->tmA;
+  if (A.phase_r) {   // r_{l+1} at its own resolution: [maxB, H/2, W/2, R_up], one box = 18 rows x 10 pixels x 16 channels
+    const int Ru = (int)rmap->size();
+    cuuint64_t dims[4] = {(cuuint64_t)Ru, (cuuint64_t)(A.W / 2), (cuuint64_t)(A.H / 2), (cuuint64_t)h->cfg.max_batch};
+    cuuint64_t strides[3] = {(cuuint64_t)Ru * 2, (cuuint64_t)Ru * 2 * (A.W / 2), (cuuint64_t)Ru * 2 * (A.W / 2) * (A.H / 2)};
+    cuuint32_t box[4] = {16, 10, 18, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&c->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, RL, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(R, layer %d) failed: %d", l, (int)r);
       return TZ_ECUDA;
     }
   }
@@ -1640,6 +1792,7 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
@@ -1649,8 +1802,22 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     for (int i = 0; i < 2 * h->S[l]; i++) gmap[i] = h->R[l] + i;                                  // e_l
     if (l < L - 1)
       for (int i = 0; i < h->R[l + 1]; i++) gmap[T->epad[l] + i] = h->R[l] + 2 * h->S[l] + i;    // up(r_{l+1})
-    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l],
-                       h->R[l]);
+    // Opt-in prototype (TZ_PHASE0=1): layer 0 reads r_1 at its own resolution with parity-collapsed taps
+    const bool phase0 = TZ_PHASE_PROTO && l == 0 && L >= 2 && getenv("TZ_PHASE0") && (h->R[1] % 16) == 0 && T->epad[0] == 16 &&
+                        (h->H[0] % 2) == 0 && (h->W[0] % 8) == 0 && h->R[0] <= 8;
+    int rc;
+    if (phase0) {
+      T->RL1 = (__half *)dev_alloc(h, (size_t)mb * h->H[1] * h->W[1] * h->R[1] * sizeof(__half));
+      if (!T->RL1) return TZ_ENOMEM;
+      TZ_CHECK_CUDA(cudaMemset(T->RL1, 0, (size_t)mb * h->H[1] * h->W[1] * h->R[1] * sizeof(__half)));
+      std::vector<int> emap(T->epad[0], -1), rmap(h->R[1]);
+      for (int i = 0; i < 2 * h->S[0]; i++) emap[i] = h->R[0] + i;
+      for (int i = 0; i < h->R[1]; i++) rmap[i] = h->R[0] + 2 * h->S[0] + i;
+      rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], emap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l],
+                     &rmap, T->RL1);
+    } else {
+      rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
+    }
     if (rc) return rc;
     ConvArgs &G = T->gconv[l].args;
     G.bm = h->BM[l];
@@ -1665,6 +1832,10 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       TZ_CHECK_CUDA(cudaDeviceSynchronize());
       G.bm = bp;
       G.bm_packed = 1;
+    }
+    if (l == 1 && T->RL1) {   // the layer-0 phase_r consumer reads r_1 from here
+      G.rl_out = T->RL1;
+      G.rl_cstride = h->R[1];
     }
     if (l > 0) {
       G.xr_out = T->X[l - 1];
@@ -1729,19 +1900,22 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, A)
-                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, A);
+    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, c->tmC, A)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, c->tmC, A);
     if (e != cudaSuccess) {
       set_error("cluster launch failed: %s", cudaGetErrorString(e));
       return TZ_ECUDA;
     }
   } else if (c->epi == 0)
     if (A.pool_cols)
-      conv_tc_kernel<0, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+      conv_tc_kernel<0, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
     else
-      conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+      conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
   else
-    conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+    if (A.phase_r)
+      conv_tc_kernel<1, false, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
+    else
+      conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
   TZ_CHECK_LAUNCH();
   if (dbg_on) {   // diagnostics only: synchronous
     long long hbuf[256 * 8];
