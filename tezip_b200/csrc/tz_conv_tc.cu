@@ -641,7 +641,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t a = 0, aph = 0;   // accumulator ring
       const uint32_t hi = P.desc_hi;
       const uint32_t idesc = P.idesc;
-      const uint32_t rowb = 2u * (uint32_t)P.KC;   // bytes per pixel row of a chunk
       // halo tiles: 16 pixels per image row -> the 8-row groups (one image row of the 8-wide tile) are 16*rowb apart
       // (pair mode: 10 pixels of 128 B).  Neither needs to be a multiple of the swizzle period: the swizzle is a
       // function of the absolute shared-memory address bits (what TMA wrote), and the descriptor base_offset stays 0
@@ -795,7 +794,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #else
     constexpr bool edbg = false;
 #endif
-    long long e_wait = 0, e_work = 0, e_tiles = 0, ec0 = 0, e_a = 0, e_b = 0, e_c = 0;
+    long long e_wait = 0, e_work = 0, e_tiles = 0, ec0 = 0, e_a = 0, e_b = 0;
     for (int t = t_first; t < n_tiles; t += t_step, tc++) {
       const uint32_t a = ring_a, aph = ring_ph;
       const bool mine = P.epi_groups <= 1 || (int)ring_g == group;

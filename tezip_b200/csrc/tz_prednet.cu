@@ -229,14 +229,13 @@ static int widx(int L, int key /*0 a,1 ahat,2 c,3 f,4 i,5 o*/, int l) {
 static int init_constants(tz_prednet *h) {
   cudaStream_t st = 0;
   const int L = h->L;
-  float *pre = nullptr, *rtmp = nullptr;
+  float *pre = nullptr;
   size_t mx = 0;
   for (int l = 0; l < L; l++) {
     size_t v = (size_t)h->H[l] * h->W[l] * 4 * h->R[l];
     if (v > mx) mx = v;
   }
   TZ_CHECK_CUDA(cudaMalloc(&pre, mx * sizeof(float)));
-  (void)rtmp;
   int rc = TZ_OK;
   for (int l = L - 1; l >= 0 && rc == TZ_OK; l--) {  // prednet.py:249-264 at t=0: inputs [0 | 0 | up(R0_{l+1})]
     ConvSrc s = {nullptr, 0, 0, 0, 0};
