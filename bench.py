@@ -36,6 +36,16 @@ H, W, C = 128, 160, 3
 WORKLOAD = "lossy abs bound 2 levels (~1e-2), 1000x128x160x3 u8 synthetic frames, 4-layer PredNet (3,48,96,192), SWP window 10, p=0"
 
 
+def workload_text(args):
+    """The default is BASELINE.json's configs[1]; other --frames/--window/--mode/--bound are named as they are."""
+    if args.frames == 1000 and args.window == 10 and args.mode == "abs" and list(args.bound) == [2.0]:
+        return WORKLOAD
+    b = list(args.bound)
+    kind = "lossless" if (b and b[0] == 0) else "lossy %s bound %s" % (args.mode, "/".join("%g" % v for v in b))
+    return "%s, %dx128x160x3 u8 synthetic frames, 4-layer PredNet (3,48,96,192), SWP window %d, p=0" % (
+        kind, args.frames, args.window)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,7 +169,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "raw_MB_per_s_compress", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(tcs)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 + int64/int16 (CPU)",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "boundary": "packed int16 stream + key plane, before zstd",
+            "data": "synthetic", "config": {"workload": workload_text(args), "boundary": "packed int16 stream + key plane, before zstd",
                                             "sample_frames": n},
             "decompress": {"value": vd, "unit": "MB/s", "ms_per_step": 1e3 * float(np.mean(tds))},
             "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port", "sample": sample,
@@ -453,8 +463,8 @@ def run_native(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_c, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 x f16 -> f32 (PredNet, tcgen05); int16/f64 codec",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.dwp else WORKLOAD.replace(
-                           "SWP window 10", "DWP threshold %.6g (calibrated), %d chains per GPU, %d key frames" %
+            "config": {"workload": workload_text(args) if not args.dwp else workload_text(args).replace(
+                           "SWP window %d" % args.window, "DWP threshold %.6g (calibrated), %d chains per GPU, %d key frames" %
                            (thr, chains, len(enc0.keys))),
                        "frames_per_gpu": nt, "windows_in_flight": Bk,
                        "boundary": "packed int16 stream + key plane, before zstd",

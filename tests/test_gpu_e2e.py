@@ -164,3 +164,25 @@ def test_host_buffer_api_matches_device_api(cuda_lib):
         err = np.abs(out_host.numpy().astype(int) - frames[:n_use].astype(int)).max()
         assert err <= (0 if bound == [0.0] else 2)
     net.close()
+
+
+def test_more_windows_than_max_batch_is_bitwise_equal(cuda_lib):
+    """The window scheduler takes the windows in groups of net.max_batch and chains the steps inside a group: the
+    stream must not depend on the group size (windows of unequal length included: 43 frames, window 4)."""
+    import torch
+    from tezip_b200 import codec
+    stack, H, W, nt = TINY, 24, 40, 43
+    _o, ws = oracle_net(stack)
+    frames = torch.from_numpy(synth.make_frames(nt, H, W, 3, seed=77)).cuda()
+    ref = None
+    for mb in (16, 4, 3, 1):
+        net = gpu_net(stack, ws, 24, 40, max_batch=mb)
+        enc = codec.encode_frames(frames, net, 0, 4, None, "abs", [2.0], True)
+        out, _plan = codec.decode_arrays(enc.key_plane, enc.body, enc.table, enc.shape, 0, net)
+        cur = (enc.body.cpu().numpy(), enc.key_plane.cpu().numpy(), out.cpu().numpy())
+        if ref is None:
+            ref = cur
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(cur, ref)), mb
+        net.close()
+    assert np.abs(ref[2].astype(int) - frames.cpu().numpy().astype(int)).max() <= 2

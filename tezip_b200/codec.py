@@ -78,24 +78,29 @@ def plan_from_keys(nt, p, keys):
 
 
 def run_plan(net, frames, plan, pool):
-    """Fills pool[1:] with the predictions of every non-key frame; pool[0] = P0."""
+    """Fills pool[1:] with the predictions of every non-key frame; pool[0] = P0.
+
+    Windows are independent, so they are taken in groups of at most net.max_batch (in the plan's length-sorted
+    order): a group runs all of its lock-steps back to back, the first from the key frames, every later one as a
+    chained step on the previous prediction (its live windows are a prefix of the previous step's)."""
     net.p0(out=pool[0])
+    if not plan.steps:
+        return
     mb = net.max_batch
-    prev = None
-    chain = False   # the previous step was ONE next() call whose output is this step's input
-    for key_idx, slot0, B in plan.steps:
-        if key_idx is not None:
-            idx = torch.from_numpy(key_idx).to(frames.device)
-            prev = ops.pad_normalize(frames, idx, net.Hp, net.Wp)          # compress.py:219 / decompress.py:161
-            chain = False
-        out = pool[slot0:slot0 + B]
-        if chain and B <= mb:
-            net.next_chained(out)                                          # the live windows are a prefix of the last step's
-        else:
-            for b0 in range(0, B, mb):
-                net.next(prev[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])  # compress.py:222-229
-        chain = B <= mb
-        prev = out
+    key_idx_all, _slot0, B1 = plan.steps[0]
+    for g0 in range(0, B1, mb):
+        g1 = min(g0 + mb, B1)
+        idx = torch.from_numpy(np.ascontiguousarray(key_idx_all[g0:g1])).to(frames.device)
+        x = ops.pad_normalize(frames, idx, net.Hp, net.Wp)                  # compress.py:219 / decompress.py:161
+        for k, (_kidx, slot0, B) in enumerate(plan.steps):
+            nb = min(B, g1) - g0                                            # windows of this group longer than k + 1
+            if nb <= 0:
+                break
+            out = pool[slot0 + g0:slot0 + g0 + nb]
+            if k == 0:
+                net.next(x[:nb], out=out)                                   # compress.py:222-229
+            else:
+                net.next_chained(out)
 
 
 def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None):
