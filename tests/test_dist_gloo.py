@@ -61,3 +61,46 @@ def test_sharded_stream_equals_single_process(tmp_path):
     assert all(np.array_equal(p["table"], table) for p in parts)
     assert [int(p["off"]) for p in parts] == [0, 2400]
     assert np.array_equal(np.concatenate([p["body"] for p in parts]), ref)
+
+
+def _worker_gather(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tezip_b200.dist import gather_varlen, scatter_varlen
+    sizes = [5, 9]
+    # int16 goes through the byte view (NCCL has no int16), uint8 directly
+    mine16 = torch.arange(sizes[rank], dtype=torch.int16) + 100 * (rank + 1) - 300
+    mine8 = (torch.arange(sizes[rank]) + 10 * rank).to(torch.uint8)
+    g16, g8 = gather_varlen(mine16, sizes), gather_varlen(mine8, sizes)
+    if rank == 0:
+        assert g16.dtype == torch.int16 and g16.tolist() == [-200 + i for i in range(5)] + [-100 + i for i in range(9)]
+        assert g8.tolist() == list(range(5)) + [10 + i for i in range(9)]
+    else:
+        assert g16 is None and g8 is None
+    back16 = scatter_varlen(g16, sizes, torch.int16, "cpu")
+    back8 = scatter_varlen(g8, sizes, torch.uint8, "cpu")
+    assert torch.equal(back16, mine16) and torch.equal(back8, mine8)
+    open(os.path.join(out_dir, "ok%d" % rank), "w").close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_scatter_varlen_world2(tmp_path):
+    """The collectives of the multi-GPU file drivers (compress.run_sharded / decompress.run_sharded)."""
+    world = 2
+    mp.spawn(_worker_gather, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(str(tmp_path / ("ok%d" % r))) for r in range(world))
+
+
+def test_key_aligned_ranges():
+    from tezip_b200.dist import key_aligned_ranges
+    keys = [0, 1, 2, 7, 12, 17, 22]          # p = 2: warm-up frames 0, 1; real windows start at 2, 7, 12, 17, 22
+    for world in (1, 2, 3, 5, 8):
+        rs = key_aligned_ranges(keys, 25, 2, world)
+        assert rs[0][0] == 0 and rs[-1][1] == 25 and len(rs) == world
+        for (a, b), (c, d) in zip(rs, rs[1:]):
+            assert b == c and a <= b
+        for r, (a, b) in enumerate(rs):
+            if r > 0 and b > a:
+                assert a in keys and a >= 2

@@ -28,13 +28,13 @@ def io_workers():
     return max(1, int(env)) if env else max(1, min(32, os.cpu_count() or 1))
 
 
-def load_images(DATA_DIR, workers=None):
+def load_images(DATA_DIR, workers=None, paths=None):
     """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB.
     One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
     pool, so the array goes to the GPU with one asynchronous copy."""
     from concurrent.futures import ThreadPoolExecutor
     from PIL import Image, UnidentifiedImageError
-    file_paths = sorted(glob.glob(os.path.join(DATA_DIR, '*')))
+    file_paths = list(paths) if paths is not None else sorted(glob.glob(os.path.join(DATA_DIR, '*')))
     if len(file_paths) == 0:
         _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
     try:
@@ -88,10 +88,63 @@ def load_predictor(WEIGHTS_DIR, max_batch, device=0):
         _die("ERROR: No such file or directory:", os.path.join(WEIGHTS_DIR, 'prednet_weights.hdf5'))
 
 
+def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE, BOUND_VALUE, VERBOSE, ENTROPY_RUN,
+                zstd_workers=0):
+    """compress.run under torchrun (one process per GPU, static windows): every rank decodes and encodes the images
+    of its own window-aligned shard (dist.shard_ranges), the ranks exchange the 1-element delta halo and sum the
+    symbol histogram (dist.ShardComm), rank 0 gathers the streams and writes the single container
+    (SURVEY.md 8(e)).  The container is byte-identical before zstd to the one a single process writes."""
+    import torch.distributed as tdist
+    from . import dist as tzdist
+    rank, world, local = tzdist.init_from_env()
+    file_paths = sorted(glob.glob(os.path.join(DATA_DIR, '*')))
+    nt = len(file_paths)
+    if nt == 0:
+        _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
+    ranges = tzdist.shard_ranges(nt, PREPROCESS, WINDOW_SIZE, world)
+    a, b = ranges[rank]
+    if b <= a:
+        _die("ERROR: fewer windows than GPUs; use fewer processes")
+    frames, files, isRGB = load_images(DATA_DIR, paths=file_paths[a:b])
+    n_win = max(1, (b - a + WINDOW_SIZE - 1) // WINDOW_SIZE)
+    net = load_predictor(WEIGHTS_DIR, max_batch=min(n_win, 256), device=local)
+    dev = net.device
+    comm = tzdist.ShardComm(device=dev)
+    try:
+        enc = codec.encode_frames(torch.from_numpy(frames).to(dev, non_blocking=True), net,
+                                  PREPROCESS if rank == 0 else 0, WINDOW_SIZE, None, MODE, list(BOUND_VALUE),
+                                  ENTROPY_RUN, comm=comm)
+    except TezipError as e:
+        _die(str(e))
+    fe = frames[0].size
+    sizes = [(rb - ra) * fe for ra, rb in ranges]
+    body = tzdist.gather_varlen(enc.body, sizes)
+    keyp = tzdist.gather_varlen(enc.key_plane.reshape(-1), sizes)
+    names = [None] * world
+    tdist.all_gather_object(names, files)
+    if rank == 0:
+        H, W, C = frames.shape[1:]
+        payload = codec.pack_payload(body.cpu().numpy(), enc.table, (1, nt, H, W, C), PREPROCESS)
+        kb, eb = container.write_container(OUTPUT_DIR, [f for part in names for f in part], isRGB,
+                                           keyp.cpu().numpy(), payload, workers=zstd_workers)
+        if VERBOSE:
+            print("ranks:", world, "ratio:", nt * fe / float(kb + eb))
+    tdist.barrier()
+    net.close()
+
+
 def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, MODE, BOUND_VALUE, GPU_FLAG, VERBOSE,
         ENTROPY_RUN, dwp_chains=1, zstd_workers=0):
     if not GPU_FLAG:
         _die("ERROR: tezip_b200 has no CPU path; a B200 (sm_100) GPU is required.")
+    from . import dist as tzdist
+    if tzdist.launched_by_torchrun():
+        if THRESHOLD is not None:
+            _die("ERROR: multi-GPU compression shards static windows; use -w (or one process for -t).")
+        if not os.path.exists(OUTPUT_DIR):
+            os.makedirs(OUTPUT_DIR, exist_ok=True)
+        return run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE, BOUND_VALUE, VERBOSE,
+                           ENTROPY_RUN, zstd_workers)
     if not os.path.exists(OUTPUT_DIR):
         os.mkdir(OUTPUT_DIR)
     frames, files, isRGB = load_images(DATA_DIR)

@@ -16,9 +16,60 @@ def _die(*msg):
     sys.exit(1)
 
 
+def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, VERBOSE):
+    """decompress.run under torchrun: rank 0 reads the container and finds the key frames, the windows are dealt out
+    as contiguous key-aligned frame ranges, every rank decodes its range (x restarts at 0 at its first key frame,
+    SURVEY.md A18) and writes its own images."""
+    import torch.distributed as tdist
+    from . import dist as tzdist, ops
+    rank, world, local = tzdist.init_from_env()
+    dev = torch.device("cuda", local)
+    meta = [None]
+    key_full = body_full = None
+    if rank == 0:
+        file_names, isRGB, key_plane, payload = container.read_container(DATA_DIR)
+        body, table, shape, p = codec.parse_payload(payload)
+        if len(file_names) != shape[1]:
+            print("ERROR：The lengths of filename.txt and images do not match.")
+            _die("number of images", shape[1])
+        _one, nt, H, W, C = shape
+        key_full = torch.from_numpy(np.ascontiguousarray(key_plane)).to(dev)
+        body_full = torch.from_numpy(np.ascontiguousarray(body)).to(dev)
+        nz = ops.frames_nonzero(key_full.view(nt, H, W, C)).cpu().numpy()
+        keys = [int(i) for i in np.nonzero(nz)[0]]
+        ranges = tzdist.key_aligned_ranges(keys, nt, p, world)
+        meta = [(file_names, isRGB, None if table is None else np.asarray(table), shape, p, ranges)]
+    tdist.broadcast_object_list(meta, src=0)
+    file_names, isRGB, table, shape, p, ranges = meta[0]
+    _one, nt, H, W, C = shape
+    fe = H * W * C
+    sizes = [(b - a) * fe for a, b in ranges]
+    a, b = ranges[rank]
+    key_part = tzdist.scatter_varlen(key_full, sizes, torch.uint8, dev)
+    body_part = tzdist.scatter_varlen(body_full, sizes, torch.int16, dev)
+    if b > a:
+        n_keys_guess = max(1, (b - a) // 4)
+        net = load_predictor(WEIGHTS_DIR, max_batch=min(n_keys_guess, 256), device=local)
+        try:
+            out, _plan = codec.decode_arrays(key_part.contiguous(), body_part.contiguous(), table, (1, b - a, H, W, C),
+                                             p if rank == 0 else 0, net, first_mode=0 if rank == 0 else 1, first_x=0)
+        except TezipError as e:
+            _die(str(e))
+        save_images(out.cpu().numpy(), file_names[a:b], isRGB, OUTPUT_DIR)
+        net.close()
+    tdist.barrier()
+
+
 def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, GPU_FLAG, VERBOSE):
     if not GPU_FLAG:
         _die("ERROR: tezip_b200 has no CPU path; a B200 (sm_100) GPU is required.")
+    from . import dist as tzdist
+    if tzdist.launched_by_torchrun():
+        os.makedirs(OUTPUT_DIR, exist_ok=True)
+        for fn in (container.NAMES_FILE, container.KEY_FILE, container.ENTROPY_FILE):
+            if not os.path.exists(os.path.join(DATA_DIR, fn)):
+                _die("ERROR: No such file or directory:", os.path.join(DATA_DIR, fn))
+        return run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, VERBOSE)
     if not os.path.exists(OUTPUT_DIR):
         os.mkdir(OUTPUT_DIR)
     for fn in (container.NAMES_FILE, container.KEY_FILE, container.ENTROPY_FILE):

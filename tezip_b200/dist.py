@@ -59,3 +59,75 @@ class ShardComm:
         dist.all_gather(alln, mine, group=self.group)
         sizes = np.array([int(t.item()) for t in alln], np.int64)
         return np.concatenate([[0], np.cumsum(sizes)[:-1]]), sizes
+
+
+# ------------------------------------------------------------------------------------------------ file drivers
+def launched_by_torchrun():
+    """True under `torchrun` / `python -m torch.distributed.run` with more than one rank."""
+    import os
+    return int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+def init_from_env():
+    """One process per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the launcher).  -> (rank, world, device)."""
+    import os
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return rank, world, local
+
+
+def gather_varlen(t, sizes, dst=0, group=None):
+    """Concatenation, on rank `dst`, of every rank's 1-D tensor `t` (rank r holds sizes[r] elements); None elsewhere.
+    Shards are padded to the largest size so that one gather moves them."""
+    if t.dtype not in (torch.uint8, torch.int32, torch.int64, torch.float32, torch.float16):   # e.g. int16: not an NCCL type
+        k = t.element_size()
+        out = gather_varlen(t.reshape(-1).view(torch.uint8), [int(v) * k for v in sizes], dst, group)
+        return None if out is None else out.view(t.dtype)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = int(max(sizes))
+    pad = torch.zeros(n, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t.reshape(-1)
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:int(sizes[r])] for r, b in enumerate(bufs)])
+
+
+def scatter_varlen(full, sizes, dtype, device, src=0, group=None):
+    """Inverse of gather_varlen: rank r receives elements [sum(sizes[:r]), sum(sizes[:r+1])) of `full` (given on src)."""
+    if dtype not in (torch.uint8, torch.int32, torch.int64, torch.float32, torch.float16):
+        k = torch.empty(0, dtype=dtype).element_size()
+        full8 = None if full is None else full.reshape(-1).view(torch.uint8)
+        return scatter_varlen(full8, [int(v) * k for v in sizes], torch.uint8, device, src, group).view(dtype)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = int(max(sizes))
+    out = torch.empty(n, dtype=dtype, device=device)
+    parts = None
+    if rank == src:
+        offs = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64))])
+        parts = []
+        for r in range(world):
+            buf = torch.zeros(n, dtype=dtype, device=device)
+            buf[:int(sizes[r])] = full[int(offs[r]):int(offs[r + 1])]
+            parts.append(buf)
+    dist.scatter(out, parts, src=src, group=group)
+    return out[:int(sizes[rank])]
+
+
+def key_aligned_ranges(keys, nt, p, world):
+    """Contiguous frame ranges [a, b) per rank for DECODING: every range but the first starts at a key frame >= p
+    (x restarts at 0 there), windows are dealt out evenly.  keys: sorted key-frame indices."""
+    starts = [k for k in keys if k >= p]
+    n_win = len(starts)
+    out = []
+    for r in range(world):
+        w0, w1 = n_win * r // world, n_win * (r + 1) // world
+        a = 0 if r == 0 else (starts[w0] if w0 < n_win else nt)
+        b = nt if r == world - 1 else (starts[w1] if w1 < n_win else nt)
+        out.append((min(a, nt), min(b, nt)))
+    return out
