@@ -525,7 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // transaction bytes of the pair are counted on the leader's barriers (the leader alone waits on them).
           int kc = 0;
           const int nb0 = n0 + (int)crank * (P.n_tile >> 1);
-          for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
+          for (int c = 0; c < P.cin_pad; c += P.KC, kc += P.KC) {
             mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
             if (elect_one()) {
               if (crank == 0) mbar_expect_tx(afull0 + 8 * sl, 2 * P.a_tx);
@@ -646,6 +646,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // function of the absolute shared-memory address bits (what TMA wrote), and the descriptor base_offset stays 0
       // -- measured on B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
       const uint32_t ahi_pair = ((1280u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
+      const uint32_t ahi_pair32 = ((640u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);   // 10 pixels of 64 B
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
       const bool dbg = P.dbg != nullptr && lane == 0;
@@ -674,14 +675,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_fence_after();
               const uint32_t b_base = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
               if (elect_one()) {
+                if (P.ksteps == 4) {   // 64-channel chunks: 128-byte pixels
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                  const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
-                  const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+                  for (int j = 0; j < 3; j++) {
+                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
 #pragma unroll
-                  for (int k = 0; k < 4; k++)
-                    tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
-                                acc | (uint32_t)(tg | j | k));
+                    for (int k = 0; k < 4; k++)
+                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                                  acc | (uint32_t)(tg | j | k));
+                  }
+                } else {               // 32-channel chunks (channel counts that are multiples of 32 only): 64-byte pixels
+#pragma unroll
+                  for (int j = 0; j < 3; j++) {
+                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 4u;
+                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair32), make_desc(b_lo + 2 * k, hi), idesc,
+                                  acc | (uint32_t)(tg | j | k));
+                  }
                 }
                 tc2_commit(empty0 + 8 * s);
               }
@@ -1390,10 +1403,20 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     if (((env && env[0] == '5') || big_a) && c64 <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
         (ntile_c % 16) == 0) {
       A.halo = 4;
+      if ((cin_real % 32) == 0 && (cin_real % 64) != 0 && getenv("TZ_PAIR_KC32")) {
+        // Experiment: 32-channel chunks instead of rounding the channels up to 64.  a1 (96 channels) then issues 54
+        // instead of 72 M256 MMAs per tile, but runs SLOWER (0.101 vs 0.082 ms): three chunks mean twelve barrier
+        // round trips per tile instead of eight, each weight stage carrying only ~300 cycles of MMAs.
+        A.cin_pad = cin_real;
+        A.KC = 32;
+        A.kchunks = cin_real / 32;
+        A.ksteps = 2;
+      } else {
       A.cin_pad = c64;
       A.KC = 64;
       A.kchunks = c64 / 64;
       A.ksteps = 4;
+      }
       A.tw_log = 3;
       A.th_log = 4;
       A.tb_log = 0;
@@ -1594,11 +1617,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   A.stages = stages;
   c->smem_bytes = (uint32_t)stages * A.stage_stride + 1024u;
   if (A.halo == 4) {
-    A.a_tx = 10u * 18u * 128u;     // 18 image rows x 10 pixels x 64 channels fp16 (this CTA's M tile + halo)
+    A.a_tx = 10u * 18u * row_bytes;     // 18 image rows x 10 pixels x KC channels fp16 (this CTA's M tile + halo)
     A.a_slot = (A.a_tx + 1023u) & ~1023u;
     A.a_stride = 0;
-    A.b_block = (((uint32_t)(A.n_tile / 2) * 128u) + 1023u) & ~1023u;   // this CTA's half of one tap's weight block
-    A.tx_bytes = 3u * (uint32_t)(A.n_tile / 2) * 128u;                  // a stage holds one filter row (3 taps)
+    A.b_block = (((uint32_t)(A.n_tile / 2) * row_bytes) + 1023u) & ~1023u;   // this CTA's half of one tap's weight block
+    A.tx_bytes = 3u * (uint32_t)(A.n_tile / 2) * row_bytes;                  // a stage holds one filter row (3 taps)
     A.stage_stride = 3u * A.b_block;
     stages = (int)((226u * 1024u - 1024u - 2u * A.a_slot) / A.stage_stride);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
