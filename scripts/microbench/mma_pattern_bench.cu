@@ -13,9 +13,9 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 }
 template <int G>
 __global__ void __launch_bounds__(512, 1) bench(int N, int nacc, int acc_stride, int commits, int ldwarps, int groups,
-                                                long long *out) {
+                                                long long *out, const uint8_t *gsrc, int bulk_kb) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar, bar2;
+  __shared__ __align__(8) uint64_t bar, bar2, bar3;
   __shared__ uint32_t tmem_s;
   __shared__ volatile int stop;
   const uint32_t s0 = (smem_u32(smem) + 1023u) & ~1023u;
@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(512, 1) bench(int N, int nacc, int acc_stride,
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(&bar2)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar3)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stop = 0;
   }
@@ -64,6 +65,21 @@ __global__ void __launch_bounds__(512, 1) bench(int N, int nacc, int acc_stride,
     long long t1 = clock64();
     out[blockIdx.x] = t1 - t0;
     stop = 1;
+  } else if (warp == 1 && bulk_kb > 0 && (threadIdx.x & 31) == 0) {
+    // TMA-like fill traffic: bulk_kb KB per round into the upper part of shared memory, back to back until stopped
+    const uint32_t b3 = smem_u32(&bar3);
+    uint32_t phase = 0;
+    const uint8_t *src = gsrc + (size_t)blockIdx.x * 64 * 1024;
+    while (!stop) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b3), "r"((uint32_t)bulk_kb * 1024u) : "memory");
+      for (int k = 0; k < bulk_kb; k += 4)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(s0 + 96u * 1024u + (uint32_t)k * 1024u), "l"(src + (size_t)k * 1024), "r"(4096u), "r"(b3) : "memory");
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b3), "r"(phase) : "memory");
+      phase ^= 1u;
+    }
   } else if (warp >= 4 && warp < 4 + ldwarps) {
     // epilogue-like TMEM readers: 8 columns at a time over the accumulator ring, lanes of this warp's quadrant
     const uint32_t row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -86,24 +102,27 @@ __global__ void __launch_bounds__(512, 1) bench(int N, int nacc, int acc_stride,
 
 int main() {
   long long *d;
+  uint8_t *g;
   cudaMalloc(&d, 148 * sizeof(long long));
+  cudaMalloc(&g, (size_t)148 * 64 * 1024);
+  cudaMemset(g, 0, (size_t)148 * 64 * 1024);
   cudaFuncSetAttribute(bench<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
   cudaFuncSetAttribute(bench<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
   const int groups = 200;
   for (int N : {32, 48})
-    for (int nacc : {1, 6})
-      for (int commits : {0, 1, 2})
-        for (int ldwarps : {0, 4, 12})
+    for (int commits : {0, 2})
+      for (int ldwarps : {0, 12})
+        for (int bulk_kb : {0, 8, 32})
           for (int G : {9, 36}) {
-            if (G == 9) bench<9><<<148, 512, 136 * 1024>>>(N, nacc, 64, commits, ldwarps, groups, d);
-            else bench<36><<<148, 512, 136 * 1024>>>(N, nacc, 64, commits, ldwarps, groups, d);
+            if (G == 9) bench<9><<<148, 512, 136 * 1024>>>(N, 6, 64, commits, ldwarps, groups, d, g, bulk_kb);
+            else bench<36><<<148, 512, 136 * 1024>>>(N, 6, 64, commits, ldwarps, groups, d, g, bulk_kb);
             cudaError_t e = cudaDeviceSynchronize();
             long long h[148];
             cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
             long long mx = 0;
             for (int i = 0; i < 146; i++) mx = h[i] > mx ? h[i] : mx;
-            printf("N %2d G %2d nacc %d commits %d ldwarps %2d : %6.1f cycles/MMA  %s\n", N, G, nacc, commits, ldwarps,
-                   (double)mx / (groups * G), e == cudaSuccess ? "" : cudaGetErrorString(e));
+            printf("N %2d G %2d commits %d ldwarps %2d bulk %2d KB/round : %6.1f cycles/MMA  %s\n", N, G, commits, ldwarps,
+                   bulk_kb, (double)mx / (groups * G), e == cudaSuccess ? "" : cudaGetErrorString(e));
           }
   return 0;
 }
