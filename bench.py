@@ -253,8 +253,10 @@ def run_native(args):
                                        comm=comm, wait_copies=False)
         if comm is not None:
             comm.stream_offsets(enc.body.numel())
+        in_flight[seq[0] & 1] = enc   # the record owns the device tensors its copies read: keep it until the next but one
         return enc
 
+    in_flight = [None, None]
     enc0 = compress_dev()
     first_mode, first_x = (0, 0) if rank == 0 else (1, 0)
 

@@ -137,6 +137,14 @@ int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsig
 /* finding_difference + replacing_based_on_frequency (compress.py:84-90,339-340,348,369):
  * out[i] = lut[1600 - y[i]] (lut: device int16[TZ_HIST_BINS], symbol -> rank), or y[i] when lut == NULL
  * (the -n / ENTROPY_RUN False stream). */
+/* compress.py:352-361 on the device: table[0..n) = symbols with count > 0 sorted by count descending, ties by
+ * ascending symbol; lut = symbol -> rank over the 4096-symbol domain (compress.py:84-90); meta[0] = n, meta[1] = 1 if
+ * some symbol lies inside [0, n) -- the reference's sequential replacement then chains and the caller must build the
+ * LUT on the host (never the case for real residual streams: symbols cluster around 1600).  hist: the u64[4096]
+ * histogram of tz_delta_hist / tz_encode_lossless pass 0; table, lut: int16[4096]; meta: int32[2].  Lets the rank-map
+ * pass follow the histogram pass without a host round trip. */
+int tz_build_table(const unsigned long long *hist, int16_t *table, int16_t *lut, int32_t *meta, void *stream);
+
 int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const int16_t *lut, int16_t *out,
                   void *stream);
 

@@ -160,3 +160,34 @@ def test_window_sse_matches_numpy(cuda_lib):
     pad[:, :H, :W] = (frames[idx].astype(np.float32) / 255)
     ref = ((pad - pred.astype(np.float64)) ** 2).reshape(3, -1).sum(axis=1)
     assert np.allclose(sse, ref, rtol=1e-12, atol=0)
+
+
+def test_device_table_matches_host(cuda_lib):
+    """tz_build_table (table + symbol->rank LUT on the device) vs the host construction that mirrors
+    compress.py:352-361 / :84-90: equal counts (tie -> ascending symbol), a single bin, every bin, and tables with a
+    symbol inside the rank range (flagged, LUT then comes from the host)."""
+    import torch
+    from tezip_b200 import ops
+    rng = np.random.default_rng(21)
+    dev = torch.device("cuda", 0)
+    cases = []
+    for n, lo, hi in ((60, 1500, 1700), (1, 1600, 1601), (300, 1000, 2200), (4096, 0, 4096), (40, 100, 4000)):
+        h = np.zeros(4096, np.int64)
+        sy = rng.choice(np.arange(lo, hi), size=min(n, hi - lo), replace=False)
+        h[sy] = rng.integers(1, 50, size=len(sy))            # many ties
+        cases.append(h)
+    h = np.zeros(4096, np.int64)
+    h[[3, 1600, 1601, 1599]] = [5, 10 ** 12, 7, 7]           # symbol 3 lies inside the rank range [0, 4): collision
+    cases.append(h)
+    for h in cases:
+        want_table = ops.build_table(h)
+        table = torch.empty(4096, dtype=torch.int16, device=dev)
+        lut = torch.empty(4096, dtype=torch.int16, device=dev)
+        meta = torch.empty(2, dtype=torch.int32, device=dev)
+        ops.build_table_device(torch.from_numpy(h).to(dev), table, lut, meta)
+        n, bad = (int(v) for v in meta.cpu().numpy())
+        assert n == len(want_table) and np.array_equal(table[:n].cpu().numpy(), want_table)
+        collides = len(want_table) > 0 and int(want_table.min()) < len(want_table)
+        assert bool(bad) == collides
+        if not bad:
+            assert np.array_equal(lut.cpu().numpy(), ops.encode_lut(want_table))

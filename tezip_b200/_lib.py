@@ -46,6 +46,7 @@ SIGNATURES = {
     "tz_residual": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_error_bound": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_vp]),
     "tz_delta_hist": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
+    "tz_build_table": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tz_delta_rank": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
     "tz_encode_lossless": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_vp, c_vp, c_vp, c_vp, c_vp]),

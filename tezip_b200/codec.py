@@ -230,15 +230,11 @@ class HostSink:
 
     def key_plane(self, t):
         self._after_current()
-        if not self.wait_copies:
-            t.record_stream(self.stream)   # the copy may outlive the tensor: keep its memory out of reuse until then
         with torch.cuda.stream(self.stream):
             self.key_host.view(-1).copy_(t.view(-1), non_blocking=True)
 
     def body_chunk(self, t, a, b):
         self._after_current()
-        if not self.wait_copies:
-            t.record_stream(self.stream)
         with torch.cuda.stream(self.stream):
             self.body_host[a:b].copy_(t[a:b], non_blocking=True)
 
@@ -247,6 +243,18 @@ class HostSink:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         else:
             self.done = self.stream.record_event()
+
+
+_HOST_SCRATCH = {}
+
+
+def _host_scratch(device):
+    """Pinned landing buffers for the table / flags of one encode (cached: pinning memory per call is slow)."""
+    key = str(device)
+    if key not in _HOST_SCRATCH:
+        _HOST_SCRATCH[key] = (torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16).pin_memory(),
+                              torch.empty(1, dtype=torch.int64).pin_memory())
+    return _HOST_SCRATCH[key]
 
 
 def is_lossless(mode, bound):
@@ -344,33 +352,51 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
                                 prev_x=prev_x)
         if comm is not None:
             comm.reduce_hist(hist_ovf)
-        hist_ovf_np = hist_ovf.cpu().numpy()
-        hist_np = hist_ovf_np[:TZ_HIST_BINS]
-        if int(hist_ovf_np[TZ_HIST_BINS]) != 0:
-            raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
-                             "cannot represent this bound" % TZ_HIST_BINS)
-        table = ops.build_table(hist_np)                                                 # :352-361
-        lut = torch.from_numpy(ops.encode_lut(table)).to(dev)
+        # table and symbol -> rank LUT on the device: the rank-map pass is queued right behind the histogram pass,
+        # the host reads the table (and the overflow / collision flags) only after everything has been launched
+        tm = torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16, device=dev)   # table | meta (2 x int32)
+        table_dev, meta = tm[:TZ_HIST_BINS], tm[TZ_HIST_BINS:].view(torch.int32)
+        lut = torch.empty(TZ_HIST_BINS, dtype=torch.int16, device=dev)
+        ops.build_table_device(hist, table_dev, lut, meta)                                # :352-361, :84-90
+        # their (small) copies to the host are queued NOW, ahead of the stream's large device->host copies in the
+        # copy engine's queue; they are waited for at the end
+        tm_host, ovf_host = _host_scratch(dev)
+        tm_host.copy_(tm, non_blocking=True)
+        ovf_host.copy_(ovf, non_blocking=True)
+        small_ready = torch.cuda.current_stream(dev).record_event()
     else:
         lut = None
-    if x is not None and sink is not None and sink.chunks > 1:
-        # rank map in chunks so that the device->host copy of chunk i overlaps the kernel of chunk i+1
-        xf = x.view(-1)
-        step = -(-N // sink.chunks) // 8 * 8 + 8
-        for a in range(0, N, step):
-            b = min(N, a + step)
-            if a == 0:
-                ops.finding_difference_rank(xf[a:b], lut, out=body[a:b], has_prev=has_prev, prev_x=prev_x)
-            else:
-                ops.finding_difference_rank(xf[a:b], lut, out=body[a:b], has_prev=2)      # y[a] = x[a-1] - x[a]
-            sink.body_chunk(body, a, b)
-    else:
-        if x is not None:
-            ops.finding_difference_rank(x, lut, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
+
+    def rank_pass(lut_):
+        if x is not None and sink is not None and sink.chunks > 1:
+            # rank map in chunks so that the device->host copy of chunk i overlaps the kernel of chunk i+1
+            xf = x.view(-1)
+            step = -(-N // sink.chunks) // 8 * 8 + 8
+            for a in range(0, N, step):
+                b = min(N, a + step)
+                if a == 0:
+                    ops.finding_difference_rank(xf[a:b], lut_, out=body[a:b], has_prev=has_prev, prev_x=prev_x)
+                else:
+                    ops.finding_difference_rank(xf[a:b], lut_, out=body[a:b], has_prev=2)  # y[a] = x[a-1] - x[a]
+                sink.body_chunk(body, a, b)
         else:
-            ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut, out=body, has_prev=has_prev, prev_x=prev_x)
-        if sink is not None:
-            sink.body_chunk(body, 0, N)
+            if x is not None:
+                ops.finding_difference_rank(x, lut_, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
+            else:
+                ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut_, out=body, has_prev=has_prev, prev_x=prev_x)
+            if sink is not None:
+                sink.body_chunk(body, 0, N)
+
+    rank_pass(lut)
+    if entropy:
+        small_ready.synchronize()
+        if int(ovf_host[0]) != 0:
+            raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
+                             "cannot represent this bound" % TZ_HIST_BINS)
+        meta_np = tm_host[TZ_HIST_BINS:].view(torch.int32).numpy()
+        table = tm_host[:int(meta_np[0])].numpy().copy()
+        if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
+            rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
     if sink is not None:
         sink.finish()
     return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),
@@ -431,7 +457,8 @@ def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_
     after the copies have been ordered on the current stream (synchronise before reading the host buffers).
     wait_copies=False (streaming use: the next sequence's kernels should not queue behind this one's device->host
     copies): the copies are only ordered on the side stream and the record carries `copies_done`, the event to
-    synchronise before reading key_host / body_host; give consecutive calls different host buffers."""
+    synchronise before reading key_host / body_host.  Keep the returned record alive until then (it owns the device
+    tensors the copies read) and give consecutive calls different host buffers."""
     dev = net.device
     sink = HostSink(key_host, body_host, dev, chunks, wait_copies)
     frames, ready = upload_frames(frames_host, dev, p, window, threshold)

@@ -617,6 +617,46 @@ __global__ void __launch_bounds__(EB_THREADS) error_bound_tiles_kernel(const uin
     eb_plane_tiles<false, EB_T, EB_THREADS>(sm, d, n, C, E, G1, warp, lane);
 }
 
+// ------------------------------------------------------------------------------------------------ table on the device
+// compress.py:352-361 + :84-90 without the host round trip between the histogram and the rank-map pass: one CTA
+// compacts the non-empty bins, ranks every one of them by counting the bins that sort before it (count descending,
+// ties by ascending symbol -- keys are distinct, so the rank is the table position), and writes the symbol -> rank
+// LUT.  The LUT is the plain scatter only when no symbol lies inside the rank range [0, n) (the reference's
+// sequential where() passes chain otherwise, ops._sequential_replace): meta[1] reports that case and the host redoes
+// the LUT.  meta[0] = table length.
+__global__ void __launch_bounds__(1024) build_table_kernel(const unsigned long long *__restrict__ hist,
+                                                           int16_t *__restrict__ table, int16_t *__restrict__ lut,
+                                                           int32_t *__restrict__ meta) {
+  __shared__ unsigned long long keys[TZ_HIST_BINS];   // count * 4096 + (4095 - symbol): larger sorts first
+  __shared__ int n_s, bad_s;
+  if (threadIdx.x == 0) {
+    n_s = 0;
+    bad_s = 0;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < TZ_HIST_BINS; s += blockDim.x) {
+    lut[s] = (int16_t)s;
+    const unsigned long long c = hist[s];
+    if (c) keys[atomicAdd(&n_s, 1)] = c * TZ_HIST_BINS + (unsigned long long)(TZ_HIST_BINS - 1 - s);
+  }
+  __syncthreads();
+  const int n = n_s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long k = keys[i];
+    int r = 0;
+    for (int j = 0; j < n; j++) r += keys[j] > k;
+    const int sym = TZ_HIST_BINS - 1 - (int)(k % TZ_HIST_BINS);
+    table[r] = (int16_t)sym;
+    if (sym < n) bad_s = 1;   // a symbol inside the rank range: the scatter is not the reference's LUT
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) lut[table[i]] = (int16_t)i;   // after the identity fill above
+  if (threadIdx.x == 0) {
+    meta[0] = n;
+    meta[1] = bad_s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ delta + histogram
 // compress.py:73-77 + :348-355.  Shared-memory histogram (16 KB), run-length aggregated atomics, one
 // 64-bit global atomic per non-empty bin per block.  SRC 0: x is materialised (int16); SRC 1/2: the
@@ -1073,6 +1113,13 @@ int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsig
   int grid = stream_grid((n + 7) / 8, 256, 4);
   delta_hist_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x,
                                                               hist, overflow);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_build_table(const unsigned long long *hist, int16_t *table, int16_t *lut, int32_t *meta, void *stream) {
+  TZ_REQUIRE(hist && table && lut && meta, "tz_build_table: null argument");
+  build_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, table, lut, meta);
   TZ_CHECK_LAUNCH();
   return TZ_OK;
 }

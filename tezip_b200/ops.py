@@ -86,6 +86,12 @@ def encode_lossless(frames, pred_pool, pred_slot, pass_, hist=None, overflow=Non
     return out
 
 
+def build_table_device(hist, table, lut, meta):
+    """compress.py:352-361 + :84-90 on the device (tz_build_table): hist int64[4096] -> table int16[4096],
+    lut int16[4096], meta int32[2] = (table length, 1 if the LUT must be rebuilt on the host)."""
+    check(_lib.load().tz_build_table(ptr(hist), ptr(table), ptr(lut), ptr(meta), _st(hist.device)), "tz_build_table")
+
+
 def build_table(hist_np):
     """compress.py:352-361: symbols with count > 0 sorted by count descending, ties by ascending symbol."""
     ii = np.nonzero(hist_np)[0]
