@@ -60,6 +60,15 @@ def test_payload_pack_parse_matches_oracle():
         assert np.array_equal(codec.pack_payload(body, table, shape, p), r["payload"])
 
 
+def test_payload_trailer_limits():
+    """The trailer stores nt, H, W and p as int16 (compress.py:390-394): larger values are refused, not wrapped."""
+    body = np.zeros(4, np.int16)
+    codec.pack_payload(body, None, (1, 32767, 1, 1, 3), 0)
+    for shape, p in (((1, 32768, 8, 8, 3), 0), ((1, 10, 40000, 8, 3), 0), ((1, 10, 8, 8, 3), 40000)):
+        with pytest.raises(Exception):
+            codec.pack_payload(body, None, shape, p)
+
+
 def test_luts_match_reference_replacing():
     rng = np.random.default_rng(2)
     y = rng.integers(-40, 41, 5000).astype(np.int16)

@@ -193,6 +193,10 @@ class Encoded:
 
 
 def pack_payload(body, table, shape, p):
+    # the trailer is int16 like the stream (compress.py:390-394): shapes beyond 32767 cannot be represented and the
+    # reference would silently wrap them (decompress.py:111-113 reads them back as int16)
+    if max(int(v) for v in shape) > 32767 or int(p) > 32767:
+        raise TezipError("sequence shape %r (p=%d) does not fit the container's int16 trailer" % (tuple(shape), int(p)))
     tail = []
     if table is not None:
         tail += [int(v) for v in table] + [len(table)]        # compress.py:383-385
