@@ -8,7 +8,10 @@ Recipe: fake modules keras{,.backend,.models,.layers,.preproces
 hickle, numba and zstd (libzstd.so.1 through ctypes) are injected into sys.modules, then
 /root/reference/src/{data_utils,compress,decompress}.py are exec'd with ONE text patch,
 `.tostring()` -> `.tobytes()` (NumPy >= 2.3 removed ndarray.tostring; used at compress.py:273,395).
-Model.predict is backed by oracle/prednet_oracle.py.  GPU_FLAG is always False.
+Model.predict is backed by oracle/prednet_oracle.py -- or, with real_prednet=True, by the reference's OWN
+/root/reference/src/prednet.py executed unmodified over the numpy Keras stand-in of oracle/keras_shim.py (then
+`from prednet import PredNet`, `Model`, `Input` inside compress.py / decompress.py are the real class and the
+stand-in's eager Model).  GPU_FLAG is always False.
 """
 import ctypes
 import io
@@ -144,7 +147,7 @@ class _FakeTestModel:
         return out
 
 
-def _install_stubs():
+def _install_stubs(real_prednet=False):
     def mod(name, **attrs):
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
@@ -162,6 +165,22 @@ def _install_stubs():
     kp = mod("keras.preprocessing", image=kpi)
     mod("keras", backend=kb, models=km, layers=kl, preprocessing=kp)
     mod("prednet", PredNet=_FakePredNet)
+    if real_prednet:
+        # the reference's own prednet.py over the numpy Keras stand-in; model_from_json stays the JSON/npz reader
+        from oracle import keras_shim
+        saved.update({k: v for k, v in keras_shim.install().items() if k not in saved})
+        sys.modules["keras.models"].model_from_json = lambda js, custom_objects=None: _FakeTrainModel(js)
+
+        class _CountingModel(keras_shim.Model):
+            def predict(self, x, batch_size=None, verbose=0):
+                _State.n_predict_calls += 1
+                out = super().predict(x, batch_size)
+                if _State.predict_log is not None:
+                    _State.predict_log.append((np.array(x, copy=True), np.array(out, copy=True)))
+                return out
+
+        sys.modules["keras.models"].Model = _CountingModel
+        sys.modules["prednet"] = keras_shim.load_reference_prednet()
     mod("hickle", load=lambda *a, **k: None)
     mod("numba", cuda=types.SimpleNamespace(select_device=lambda i: None, close=lambda: None))
     mod("zstd", compress=zstd_compress, decompress=zstd_decompress)
@@ -188,10 +207,13 @@ def _load_ref(name):
 class RefModules:
     """Context manager giving the reference's own compress / decompress / data_utils modules."""
 
+    def __init__(self, real_prednet=False):
+        self.real_prednet = real_prednet
+
     def __enter__(self):
         if not available():
             raise RuntimeError("/root/reference is not mounted here")
-        self._saved = _install_stubs()
+        self._saved = _install_stubs(self.real_prednet)
         self.data_utils = _load_ref("data_utils")
         sys.modules["data_utils"] = self.data_utils
         self.compress = _load_ref("compress")
@@ -204,18 +226,18 @@ class RefModules:
 
 
 def run_compress(model_dir, img_dir, out_dir, p, window, threshold, mode, bound, entropy=True, verbose=False,
-                 predictor=None):
+                 predictor=None, real_prednet=False):
     """compress.run exactly as tezip.py:54/56 calls it (GPU_FLAG False). Returns number of predict calls."""
     _State.predictor, _State.n_predict_calls = predictor, 0
-    with RefModules() as ref, contextlib.redirect_stdout(io.StringIO() if not verbose else sys.stdout):
+    with RefModules(real_prednet) as ref, contextlib.redirect_stdout(io.StringIO() if not verbose else sys.stdout):
         ref.compress.run(model_dir, img_dir, out_dir, p, window, threshold, mode, list(bound), False, verbose,
                          entropy)
     return _State.n_predict_calls
 
 
-def run_decompress(model_dir, comp_dir, out_dir, verbose=False, predictor=None):
+def run_decompress(model_dir, comp_dir, out_dir, verbose=False, predictor=None, real_prednet=False):
     _State.predictor, _State.n_predict_calls = predictor, 0
-    with RefModules() as ref, contextlib.redirect_stdout(io.StringIO() if not verbose else sys.stdout):
+    with RefModules(real_prednet) as ref, contextlib.redirect_stdout(io.StringIO() if not verbose else sys.stdout):
         ref.decompress.run(model_dir, comp_dir, out_dir, False, verbose)
     return _State.n_predict_calls
 

@@ -19,6 +19,9 @@ CASES = [
     (11, 16, 24, 0, 5, None, "abs", [0.0], False),     # rowlen % 8 == 0: vector paths
     (11, 16, 24, 3, 3, None, "abs", [1.0], True),
     (9, 16, 24, 0, None, 0.12, "abs", [0.0], True),    # DWP
+    (12, 128, 160, 0, 5, None, "abs", [2.0], True),    # the BASELINE frame shape: 20480-sample planes, 20 tiles each
+    (12, 128, 160, 1, 5, None, "abs", [0.0], True),
+    (7, 128, 160, 0, 3, None, "rel", [0.02], True),
 ]
 
 
