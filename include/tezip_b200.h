@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 1
+#define TZ_ABI_VERSION 2   /* 2: prev_x travels as a device pointer; 16-bit (container v2) entry points */
 
 #define TZ_OK 0
 #define TZ_EINVAL (-1)  /* bad argument */
@@ -128,11 +128,18 @@ int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long
                    int C, int mode, double b0, double b1, void *stream);
 
 /* finding_difference (compress.py:73-77) fused with the symbol histogram (compress.py:348-355):
- * y[i] = x[i-1] - x[i]; y[0] = x[0] if has_prev == 0; prev_x - x[0] if has_prev == 1 (prev_x = last x of the
- * previous shard); x[-1] - x[0] if has_prev == 2 (x points into a longer device stream: chunked calls).  hist[s] += 1 for s = 1600 - y.  hist: device u64[TZ_HIST_BINS], caller-zeroed.
- * overflow: device u64[1], caller-zeroed, counts symbols outside [0, TZ_HIST_BINS). */
-int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsigned long long *hist,
+ * y[i] = x[i-1] - x[i]; y[0] = x[0] if has_prev == 0; *prev_x - x[0] if has_prev == 1 (prev_x: DEVICE pointer to the
+ * last x of the previous shard -- it stays on the device, e.g. element rank-1 of an all-gathered int32 array, so that
+ * no host synchronisation sits between the shards' collectives and this kernel); x[-1] - x[0] if has_prev == 2 (x
+ * points into a longer device stream: chunked calls).  hist[s] += 1 for s = 1600 - y.  hist: device
+ * u64[TZ_HIST_BINS], caller-zeroed.  overflow: device u64[1], caller-zeroed, counts symbols outside [0, TZ_HIST_BINS). */
+int tz_delta_hist(const int16_t *x, long long n, int has_prev, const int32_t *prev_x, unsigned long long *hist,
                   unsigned long long *overflow, void *stream);
+
+/* The last residual of a shard, x[nt*H*W*C - 1] of tz_residual() BEFORE any error bound (what a lossless shard hands
+ * to its successor, compress.py:75), written to device int32 out[0]. */
+int tz_last_residual(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt, int H,
+                     int W, int C, int Hp, int Wp, int32_t *out, void *stream);
 
 /* finding_difference + replacing_based_on_frequency (compress.py:84-90,339-340,348,369):
  * out[i] = lut[1600 - y[i]] (lut: device int16[TZ_HIST_BINS], symbol -> rank), or y[i] when lut == NULL
@@ -145,13 +152,13 @@ int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsig
  * pass follow the histogram pass without a host round trip. */
 int tz_build_table(const unsigned long long *hist, int16_t *table, int16_t *lut, int32_t *meta, void *stream);
 
-int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const int16_t *lut, int16_t *out,
-                  void *stream);
+int tz_delta_rank(const int16_t *x, long long n, int has_prev, const int32_t *prev_x, const int16_t *lut,
+                  int16_t *out, void *stream);
 
 /* Fused lossless encode (compress.py:293-314,339-369 with b0 == 0): the same results as
  * tz_residual + tz_delta_hist (pass 0) or tz_residual + tz_delta_rank (pass 1) without materialising x. */
 int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt,
-                       int H, int W, int C, int Hp, int Wp, int has_prev, int prev_x, int pass,
+                       int H, int W, int C, int Hp, int Wp, int has_prev, const int32_t *prev_x, int pass,
                        unsigned long long *hist, unsigned long long *overflow, const int16_t *lut,
                        int16_t *out, void *stream);
 
@@ -168,6 +175,55 @@ int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int H
                    const int16_t *rank_lut, int first_mode, int first_x, const float *pred_pool,
                    const int32_t *pred_slot, const uint8_t *key_plane, uint8_t *out, int16_t *x_out,
                    void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ 16-bit samples
+ * Container v2 (BASELINE config 4: 1024x1024x1 u16 frames).  The reference cannot hold
+ * such data: compress.py:106-110 turns every input into 8-bit RGB, :183 keeps a u8 key plane, :333 int16 residuals,
+ * :348 the symbol offset 1600, :394 int16 shape fields.  These entry points restate the same pipeline at the widths
+ * 16-bit samples need -- the 8-bit container and its entry points above are untouched:
+ *   x = trunc_f32(pred * 65535) - sample (int32)      y = delta as compress.py:73-77 (int32)
+ *   s = TZ_WIDE_OFFSET - y, histogram bin = s - TZ_WIDE_SYM_MIN in [0, TZ_WIDE_BINS)
+ *   table / ranks as compress.py:352-369, int32.  TZ_WIDE_OFFSET follows the reference's rule for 1600: every
+ *   symbol (>= 268930) lies above every possible rank (<= 262140), so the replacement is a pure look-up.
+ * frames / key plane: u16 [n,H,W,C]; predictions as above.  prev_x / has_prev as in tz_delta_hist. */
+#define TZ_WIDE_OFFSET 400000
+#define TZ_WIDE_SYM_MIN (TZ_WIDE_OFFSET - 131071)
+#define TZ_WIDE_BINS 262144
+
+/* out[b] = pad8(f32(frames[frame_idx[b]]) / 65535) (compress.py:138,176 with the 16-bit maximum; IEEE division) */
+int tz_pad_normalize16(const uint16_t *frames, const int32_t *frame_idx, float *out, int B, int H, int W, int C,
+                       int Hp, int Wp, void *stream);
+/* compress.py:293-314 -> x int32 [nt,H,W,C] (needed only for the lossy modes; lossless encodes fused) */
+int tz_residual16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, int32_t *x, long long nt,
+                  int H, int W, int C, int Hp, int Wp, void *stream);
+int tz_last_residual16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt, int H,
+                       int W, int C, int Hp, int Wp, int32_t *out, void *stream);
+/* compress.py:23-70 in place on int32 residual planes, bounds in 0..65535 level units */
+int tz_error_bound16(const uint16_t *frames, int32_t *x, const uint8_t *apply, long long nt, int H, int W, int C,
+                     int mode, double b0, double b1, void *stream);
+/* compress.py:339-369.  pass 0: histogram of the delta symbols into hist (device u64[TZ_WIDE_BINS], caller-zeroed;
+ * overflow u64[1]); pass 1: out[i] = lut[bin(y[i])] (lut: device int32[TZ_WIDE_BINS] from tz_build_table16), or y[i]
+ * when lut == NULL (-n streams).  x != NULL: the materialised (error-bounded) residual is the source; x == NULL: the
+ * residual is recomputed from frames + pred_pool + pred_slot (lossless: nothing but the codes is ever written). */
+int tz_encode16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, const int32_t *x,
+                long long nt, int H, int W, int C, int Hp, int Wp, int has_prev, const int32_t *prev_x, int pass,
+                unsigned long long *hist, unsigned long long *overflow, const int32_t *lut, int32_t *out,
+                void *stream);
+/* compress.py:352-361 on the device: table[0..n) = symbols by count descending, ties ascending; lut = bin -> rank
+ * (identity symbol elsewhere); meta[0] = n (meta: device int32[2]).  workspace: tz_build_table16_workspace_bytes(). */
+long long tz_build_table16_workspace_bytes(void);
+int tz_build_table16(const unsigned long long *hist, int32_t *table, int32_t *lut, int32_t *meta, void *workspace,
+                     void *stream);
+/* decoder, as tz_reconstruct: rank_lut device int32[TZ_WIDE_BINS] (rank -> symbol, identity beyond the table),
+ * y = TZ_WIDE_OFFSET - s, out = clamp(P - x, 0, 65535) with P = trunc_f32(pred * 65535) or the key sample */
+long long tz_reconstruct16_workspace_bytes(long long n);
+int tz_reconstruct16(const int32_t *body, long long nt, int H, int W, int C, int Hp, int Wp, int table_len,
+                     const int32_t *rank_lut, int first_mode, int first_x, const float *pred_pool,
+                     const int32_t *pred_slot, const uint16_t *key_plane, uint16_t *out, int32_t *x_out,
+                     void *workspace, void *stream);
+/* compress.py:245-246 on 16-bit samples (f32(sample) / 65535 against the prediction, float64 sums) */
+int tz_window_sse16(const uint16_t *frames, const int32_t *frame_idx, const float *pred, double *sse, int B, int H,
+                    int W, int C, int Hp, int Wp, void *stream);
 
 /* DWP metric (compress.py:245-246): sse[b] = sum over the padded Hp x Wp x C area of
  * (f64(lut[frame]) - f64(pred))^2 with zeros in the padding, fixed reduction order (deterministic).

@@ -18,7 +18,7 @@ def gpu_net(stack, ws, Hp, Wp, max_batch=16, fp32_direct=False):
     return PredNet(stack, stack, weights=ws, input_hw=(Hp, Wp), max_batch=max_batch, fp32_direct=fp32_direct)
 
 
-def pool_from_oracle(r, device):
+def pool_from_oracle(r, device, p=None):
     """Oracle per-frame predictions -> (pool tensor, pred_slot, apply_eb) for the GPU codec kernels:
     slot f+1 holds the oracle's prediction for frame f; window starts use -1."""
     import torch
@@ -26,7 +26,8 @@ def pool_from_oracle(r, device):
     pool = torch.from_numpy(np.concatenate([r["preds"][:1], r["preds"]], axis=0)).to(device)
     pred_slot = np.arange(1, nt + 1, dtype=np.int32)
     apply_eb = np.ones(nt, np.uint8)
-    p = int(r["payload"][-1])
+    if p is None:
+        p = int(r["payload"][-1])          # the int16 trailer ends with p (compress.py:392); v2 callers pass p
     for wi, (first, n) in enumerate(r["windows"]):
         pred_slot[first] = -1
         apply_eb[first] = 0

@@ -35,7 +35,7 @@ def _worker(rank, world, port, x_all, ranges, out_dir):
     assert has_prev == (rank > 0)
     y = np.empty_like(x)
     y[1:] = x[:-1] - x[1:]
-    y[0] = (np.int16(prev_x) - x[0]) if has_prev else x[0]
+    y[0] = (np.int16(int(prev_x)) - x[0]) if has_prev else x[0]   # prev_x: a one-element int32 tensor
     hist = torch.from_numpy(np.bincount((1600 - y).astype(np.int64), minlength=4096).astype(np.int64))
     comm.reduce_hist(hist)
     table = ops.build_table(hist.numpy())

@@ -20,8 +20,8 @@ class _FakeComm:
 
     def exchange_last_x(self, x_last):
         if self.phase == 0:
-            self.last_x[self.rank] = int(x_last)
-        return (self.rank > 0), (self.last_x[self.rank - 1] if self.rank > 0 else 0)
+            self.last_x[self.rank] = x_last.clone()          # device int32[1], as ShardComm keeps it
+        return (self.rank > 0), (self.last_x[self.rank - 1] if self.rank > 0 else None)
 
     def reduce_hist(self, t):
         key = self.calls

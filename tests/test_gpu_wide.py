@@ -1,0 +1,179 @@
+"""16-bit samples (container v2, BASELINE config 4) on the GPU against oracle/wide_oracle.py: GIVEN IDENTICAL
+PREDICTIONS the key plane, the quantised residuals, the table, the int32 stream and the decoded frames are bit-exact;
+through the tcgen05 predictor the lossless round trip is exact (also at 1024x1024x1) and the lossy one bounded."""
+import numpy as np
+import pytest
+
+from helpers import oracle_net, gpu_net, pool_from_oracle
+from tezip_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MONO = (1, 16, 32, 64)
+
+CASES = [
+    # nt, H, W, C, p, window, threshold, mode, bound, entropy
+    (10, 20, 28, 1, 0, 4, None, "abs", [0.0], True),
+    (10, 20, 28, 1, 2, 4, None, "abs", [0.0], False),
+    (10, 16, 24, 1, 0, 4, None, "abs", [300.0], True),       # rowlen % 8 == 0: vector paths
+    (10, 16, 24, 1, 1, 3, None, "abs", [77.5], True),
+    (9, 20, 28, 1, 0, 4, None, "rel", [0.01], True),
+    (9, 16, 24, 1, 0, 4, None, "absrel", [500.0, 0.02], True),
+    (9, 16, 24, 1, 0, 3, None, "pwrel", [0.01], True),
+    (9, 16, 24, 1, 0, None, 0.2, "abs", [0.0], True),        # DWP
+    (6, 64, 96, 1, 0, 3, None, "abs", [0.0], True),
+    (7, 12, 20, 3, 0, 3, None, "abs", [0.0], True),          # three 16-bit channels
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(v) for v in c))
+def test_wide_codec_bit_exact_given_oracle_predictions(cuda_lib, case):
+    import torch
+    from oracle import wide_oracle as wo
+    from tezip_b200 import codec, ops
+    nt, H, W, C, p, window, thr, mode, bound, entropy = case
+    stack = (C, 16, 32, 64)
+    net, _ws = oracle_net(stack)
+    frames = synth.make_frames(nt, H, W, C, seed=3, dtype=np.uint16)
+    r = wo.compress_arrays(frames, net, p, window, thr, mode, bound, entropy)
+    dev = torch.device("cuda", 0)
+    pool, pred_slot, apply_eb = pool_from_oracle(r, dev, p)
+    fr = torch.from_numpy(frames).to(dev)
+    enc = codec.encode_with_pool(fr, pool, pred_slot, apply_eb, r["keys"], p, mode, bound, entropy, keep_x=True)
+    assert enc.key_plane.dtype == torch.uint16 and enc.body.dtype == torch.int32
+    assert np.array_equal(enc.key_plane.cpu().numpy().ravel(), r["key_plane"])
+    assert np.array_equal(enc.x.cpu().numpy().ravel(), r["x"])
+    if entropy:
+        assert np.array_equal(enc.table, r["table"])
+    assert np.array_equal(enc.payload(), r["payload"])
+    # fused (no materialised residual) == unfused for the lossless stream
+    if codec.is_lossless(mode, bound):
+        enc2 = codec.encode_with_pool(fr, pool, pred_slot, apply_eb, r["keys"], p, mode, bound, entropy, keep_x=False)
+        assert np.array_equal(enc2.payload(), r["payload"])
+    # decoder kernels on the oracle's stream with the oracle's predictions
+    body, table, shape, pp = codec.parse_payload(r["payload"])
+    ref_out, info = wo.decompress_arrays(r["key_plane"], r["payload"], net)
+    lut = torch.from_numpy(ops.decode_lut16(table)).to(dev) if table is not None else None
+    out, x = ops.reconstruct(torch.from_numpy(np.ascontiguousarray(body)).to(dev), (nt, H, W, C), pool.shape[1],
+                             pool.shape[2], len(table) if table is not None else -1, lut, pool,
+                             torch.from_numpy(pred_slot).to(dev), enc.key_plane, want_x=True)
+    assert np.array_equal(x.cpu().numpy(), r["x"])
+    assert np.array_equal(out.cpu().numpy(), ref_out)
+
+
+def test_wide_table_kernel_matches_host(cuda_lib):
+    import torch
+    from tezip_b200 import ops
+    from tezip_b200._lib import TZ_WIDE_BINS, TZ_WIDE_SYM_MIN
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda", 0)
+    for n, lo, hi in ((1, 131071, 131072), (300, 130000, 132000), (9000, 120000, 142000), (262144, 0, 262144)):
+        h = np.zeros(TZ_WIDE_BINS, np.int64)
+        bins = rng.choice(np.arange(lo, hi), size=min(n, hi - lo), replace=False)
+        h[bins] = rng.integers(1, 40, size=len(bins))            # many ties
+        if n > 1:
+            h[bins[0]] = 5 * 10 ** 9                             # a count beyond 32 bits
+        want = ops.build_table16(h)
+        table = torch.empty(TZ_WIDE_BINS, dtype=torch.int32, device=dev)
+        lut = torch.empty(TZ_WIDE_BINS, dtype=torch.int32, device=dev)
+        meta = torch.empty(2, dtype=torch.int32, device=dev)
+        ops.build_table16_device(torch.from_numpy(h).to(dev), table, lut, meta)
+        assert int(meta[0]) == len(want)
+        assert np.array_equal(table[:len(want)].cpu().numpy(), want)
+        lut_np = lut.cpu().numpy()
+        assert np.array_equal(lut_np[want - TZ_WIDE_SYM_MIN], np.arange(len(want)))
+        rest = np.setdiff1d(np.arange(TZ_WIDE_BINS), want - TZ_WIDE_SYM_MIN)
+        assert np.array_equal(lut_np[rest], rest + TZ_WIDE_SYM_MIN)
+
+
+@pytest.mark.parametrize("mode,bound,lim", [("abs", [0.0], 0), ("abs", [200.0], 200)])
+def test_wide_roundtrip_through_the_predictor(cuda_lib, mode, bound, lim):
+    import torch
+    from tezip_b200 import codec
+    _o, ws = oracle_net(MONO)
+    net = gpu_net(MONO, ws, 64, 96, max_batch=3)
+    frames = synth.make_frames(17, 60, 90, 1, seed=8, dtype=np.uint16)
+    fr = torch.from_numpy(frames).cuda()
+    for p, window, thr in ((0, 4, None), (2, 5, None), (0, None, 0.2)):
+        enc = codec.encode_frames(fr, net, p, window, thr, mode, bound, True)
+        payload = enc.payload()
+        body, table, shape, pp = codec.parse_payload(payload)
+        out, plan = codec.decode_arrays(enc.key_plane.clone(), torch.from_numpy(np.ascontiguousarray(body)).cuda(),
+                                        table, shape, pp, net)
+        assert plan.keys == enc.keys
+        err = np.abs(out.cpu().numpy().astype(np.int64) - frames.astype(np.int64)).max()
+        assert err <= lim, (p, window, thr, err)
+    net.close()
+
+
+def test_wide_matches_oracle_with_direct_path(cuda_lib):
+    """fp32 direct predictor (<= 2e-5 from the oracle): same key placement; at 65535 levels a 2e-5 difference moves
+    trunc(pred * 65535) by up to 2 levels, so the residuals agree within 2 and the stream sizes within 2 %."""
+    import torch
+    from oracle import wide_oracle as wo
+    from tezip_b200 import codec, container
+    onet, ws = oracle_net(MONO)
+    net = gpu_net(MONO, ws, 24, 40, max_batch=4, fp32_direct=True)
+    frames = synth.make_frames(13, 24, 40, 1, seed=12, dtype=np.uint16)
+    r = wo.compress_arrays(frames, onet, 1, 4, None, "abs", [0.0], True)
+    enc = codec.encode_frames(torch.from_numpy(frames).cuda(), net, 1, 4, None, "abs", [0.0], True, keep_x=True)
+    assert enc.keys == r["keys"]
+    assert np.abs(enc.x.cpu().numpy().ravel().astype(np.int64) - r["x"]).max() <= 2
+    a = len(container.zstd_compress(enc.payload())); b = len(container.zstd_compress(r["payload"]))
+    assert abs(a - b) <= 0.02 * b + 16
+    net.close()
+
+
+def test_wide_sharded_equals_unsharded_and_host_api(cuda_lib):
+    import torch
+    from tezip_b200 import codec
+    from tezip_b200.dist import shard_ranges
+    from test_gpu_dist import _FakeComm
+    _o, ws = oracle_net(MONO)
+    net = gpu_net(MONO, ws, 24, 40, max_batch=8)
+    frames = synth.make_frames(23, 24, 40, 1, seed=31, dtype=np.uint16)
+    fr = torch.from_numpy(frames).cuda()
+    for mode, bound in (("abs", [0.0]), ("abs", [150.0])):
+        whole = codec.encode_frames(fr, net, 0, 4, None, mode, bound, True)
+        ranges = shard_ranges(23, 0, 4, 3)
+        comm = _FakeComm(3)
+        for phase in (0, 1):
+            comm.phase = phase
+            encs = []
+            for r, (a, b) in enumerate(ranges):
+                comm.rank, comm.calls = r, 0
+                encs.append(codec.encode_frames(fr[a:b].contiguous(), net, 0, 4, None, mode, bound, True, comm=comm))
+        assert np.array_equal(torch.cat([e.body for e in encs]).cpu().numpy(), whole.body.cpu().numpy())
+        assert all(np.array_equal(e.table, whole.table) for e in encs)
+        # host-buffer API (pinned buffers, chunked rank map)
+        fh = torch.from_numpy(frames).pin_memory()
+        key_host = torch.empty_like(fh).pin_memory()
+        body_host = torch.empty(fh.numel(), dtype=torch.int32).pin_memory()
+        enc = codec.encode_frames_host(fh, net, 0, 4, None, mode, bound, key_host, body_host, True, chunks=3)
+        torch.cuda.synchronize()
+        assert np.array_equal(body_host.numpy(), whole.body.cpu().numpy())
+        assert np.array_equal(key_host.numpy(), whole.key_plane.cpu().numpy())
+        out_host = torch.empty_like(fh).pin_memory()
+        codec.decode_arrays_host(key_host, body_host, enc.table, enc.shape, 0, net, out_host)
+        torch.cuda.synchronize()
+        err = np.abs(out_host.numpy().astype(np.int64) - frames.astype(np.int64)).max()
+        assert err <= (0 if bound == [0.0] else 150)
+    net.close()
+
+
+def test_config4_frame_shape_roundtrip(cuda_lib):
+    """BASELINE config 4's frame: 1024x1024x1 u16, (1,48,96,192) PredNet, W = 10 (a 23-frame prefix): exact lossless
+    round trip, decode batched differently from encode."""
+    import torch
+    from tezip_b200 import codec
+    stack = (1, 48, 96, 192)
+    _o, ws = oracle_net(stack)
+    frames = synth.make_frames(23, 1024, 1024, 1, seed=4, dtype=np.uint16)
+    fr = torch.from_numpy(frames).cuda()
+    net = gpu_net(stack, ws, 1024, 1024, max_batch=3)
+    enc = codec.encode_frames(fr, net, 0, 10, None, "abs", [0.0], True)
+    net.close()
+    net = gpu_net(stack, ws, 1024, 1024, max_batch=2)
+    out, _ = codec.decode_arrays(enc.key_plane, enc.body, enc.table, enc.shape, 0, net)
+    assert torch.equal(out.view(torch.int16), fr.view(torch.int16))
+    net.close()

@@ -164,7 +164,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, "python binding lacks %s" % name
     assert set(_lib.SIGNATURES) == declared
-    assert lib.tz_abi_version() == 1
+    assert lib.tz_abi_version() == _lib.TZ_ABI_VERSION == 2
     import torch
     if not torch.cuda.is_available():
         assert lib.tz_device_count() < 0 and b"cuda" in lib.tz_last_error().lower()

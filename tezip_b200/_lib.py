@@ -10,6 +10,10 @@ TZ_MAX_LAYERS = 8
 TZ_HIST_BINS = 4096
 TZ_SYMBOL_OFFSET = 1600
 TZ_PREDNET_FP32_DIRECT = 1
+TZ_ABI_VERSION = 2
+TZ_WIDE_OFFSET = 400000
+TZ_WIDE_SYM_MIN = TZ_WIDE_OFFSET - 131071
+TZ_WIDE_BINS = 262144
 MODES = {"abs": 0, "rel": 1, "absrel": 2, "pwrel": 3}
 
 c_vp, c_int, c_ll, c_dbl, c_flt = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_float
@@ -45,11 +49,24 @@ SIGNATURES = {
     "tz_pad_normalize": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_residual": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_error_bound": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_vp]),
-    "tz_delta_hist": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
+    "tz_delta_hist": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "tz_last_residual": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "tz_build_table": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "tz_delta_rank": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
-    "tz_encode_lossless": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "tz_delta_rank": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "tz_encode_lossless": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int,
                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_pad_normalize16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "tz_residual16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "tz_last_residual16": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "tz_error_bound16": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_vp]),
+    "tz_encode16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int,
+                            c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_build_table16_workspace_bytes": (c_ll, []),
+    "tz_build_table16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_reconstruct16_workspace_bytes": (c_ll, [c_ll]),
+    "tz_reconstruct16": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_window_sse16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_reconstruct_workspace_bytes": (c_ll, [c_ll]),
     "tz_reconstruct": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -77,7 +94,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.tz_abi_version() != 1:
+    if lib.tz_abi_version() != TZ_ABI_VERSION:
         raise TezipError("ABI version mismatch")
     _lib = lib
     return lib

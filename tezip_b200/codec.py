@@ -16,7 +16,13 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import TezipError, TZ_HIST_BINS, check
+from ._lib import TezipError, TZ_HIST_BINS, TZ_WIDE_BINS, check
+
+# Container v2 (16-bit samples): the int32 trailer ends with bits, version and this magic.  Read as the
+# reference's int16 trailer the last two fields would be C = 0x3230 and p = 0x5A54 -- impossible values (the
+# reference always writes C = 3, compress.py:116-121), so no 8-bit container can be mistaken for a v2 one.
+V2_MAGIC = 0x5A543230
+V2_VERSION = 2
 
 
 # ------------------------------------------------------------------------------------------------ schedules
@@ -188,11 +194,32 @@ class Encoded:
     copies_done: object = None   # encode_frames_host(wait_copies=False): CUDA event after the device->host copies
 
     def payload(self):
-        """entropy.dat before zstd (compress.py:375-395), host int16."""
+        """entropy.dat before zstd (compress.py:375-395), host int16 (int32 for 16-bit samples: container v2)."""
         return pack_payload(self.body.cpu().numpy(), self.table, self.shape, self.p)
 
 
+def pack_payload_v2(body, table, shape, p, bits=16):
+    """Container v2 stream (16-bit samples), int32 little-endian, the layout of compress.py:375-394 with wider fields:
+    [codes N] [table T] [T | -1] [1, nt, H, W, C] [p] [bits] [version] [magic]."""
+    tail = ([int(v) for v in table] + [len(table)]) if table is not None else [-1]
+    tail += [int(v) for v in shape] + [int(p), int(bits), V2_VERSION, V2_MAGIC]
+    if max(int(v) for v in shape) >= 2 ** 31 or int(p) >= 2 ** 31:
+        raise TezipError("sequence shape %r does not fit the v2 trailer" % (tuple(shape),))
+    return np.concatenate([np.asarray(body, np.int32), np.array(tail, np.int64).astype(np.int32)])
+
+
+def is_v2_payload(data):
+    """True if the raw bytes / array of an entropy.dat stream end with the v2 magic."""
+    a = np.asarray(data)
+    if a.dtype not in (np.uint8, np.int16, np.int32):
+        return False
+    raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return raw.size >= 44 and raw.size % 4 == 0 and int(raw[-4:].view("<u4")[0]) == V2_MAGIC
+
+
 def pack_payload(body, table, shape, p):
+    if np.asarray(body).dtype == np.int32:
+        return pack_payload_v2(body, table, shape, p)
     # the trailer is int16 like the stream (compress.py:390-394): shapes beyond 32767 cannot be represented and the
     # reference would silently wrap them (decompress.py:111-113 reads them back as int16)
     if max(int(v) for v in shape) > 32767 or int(p) > 32767:
@@ -252,12 +279,12 @@ class HostSink:
 _HOST_SCRATCH = {}
 
 
-def _host_scratch(device):
+def _host_scratch(device, wide=False):
     """Pinned landing buffers for the table / flags of one encode (cached: pinning memory per call is slow)."""
-    key = str(device)
+    key = (str(device), wide)
     if key not in _HOST_SCRATCH:
-        _HOST_SCRATCH[key] = (torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16).pin_memory(),
-                              torch.empty(1, dtype=torch.int64).pin_memory())
+        tm = torch.empty(TZ_WIDE_BINS + 2, dtype=torch.int32) if wide else torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16)
+        _HOST_SCRATCH[key] = (tm.pin_memory(), torch.empty(1, dtype=torch.int64).pin_memory())
     return _HOST_SCRATCH[key]
 
 
@@ -278,7 +305,8 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
     longer sequence: comm.exchange_last_x(x_last) -> (has_prev, prev_x) supplies the one-element halo of the 1-D
     delta (compress.py:75 crosses shard boundaries) and comm.reduce_hist(t) sums the symbol histogram across
     ranks so that every rank derives the same table."""
-    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4
+    assert frames.is_cuda and frames.dtype in (torch.uint8, torch.uint16) and frames.is_contiguous() and \
+        frames.dim() == 4
     nt, H, W, C = frames.shape
     dev = frames.device
     Hp, Wp = padding_size(H), padding_size(W)
@@ -325,13 +353,17 @@ def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
                      keep_x=False, comm=None, sink=None, staged=None):
     """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map.
-    staged: the result of stage_plan() when the caller already ran it (before the predictions)."""
+    staged: the result of stage_plan() when the caller already ran it (before the predictions).
+    frames u8 -> the reference's int16 stream; frames u16 -> the container-v2 int32 stream (same steps, wider codes)."""
     nt, H, W, C = frames.shape
     dev = frames.device
+    wide = ops.is_wide(frames)
+    nbins = TZ_WIDE_BINS if wide else TZ_HIST_BINS
+    code_dtype = torch.int32 if wide else torch.int16
     pred_slot, apply_dev, key_plane = staged if staged is not None else stage_plan(frames, keys, pred_slot_np,
                                                                                    apply_np, sink)
     N = nt * H * W * C
-    body = torch.empty(N, dtype=torch.int16, device=dev)
+    body = torch.empty(N, dtype=code_dtype, device=dev)
     table = None
     x = None
     lossless = is_lossless(mode, bound)
@@ -339,55 +371,79 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         x = ops.residual(frames, pool, pred_slot)                                        # compress.py:293-314
         if not lossless:
             ops.error_bound(frames, x, apply_dev, mode, list(bound))                    # compress.py:315-319
-    has_prev, prev_x = False, 0
+    has_prev, prev_x = False, None
     if comm is not None:
+        # the one-element halo of the 1-D delta (compress.py:75 crosses shard boundaries) never visits the host: this
+        # shard's last residual is left in a device int32, all-gathered, and the kernels read element rank-1
         if x is not None:
-            x_last = int(x.view(-1)[-1].item())
+            x_last = x.view(-1)[-1:].to(torch.int32)
         else:   # lossless: the last residual straight from the last frame
-            x_last = int(ops.residual(frames[-1:], pool, pred_slot[-1:]).view(-1)[-1].item())
+            x_last = ops.last_residual(frames, pool, pred_slot)
         has_prev, prev_x = comm.exchange_last_x(x_last)
-    if entropy:
-        hist_ovf = torch.zeros(TZ_HIST_BINS + 1, dtype=torch.int64, device=dev)   # one buffer: one D2H, one reduce
-        hist, ovf = hist_ovf[:TZ_HIST_BINS], hist_ovf[TZ_HIST_BINS:]
-        if x is not None:
+
+    def hist_pass(hist, ovf):
+        if wide:
+            ops.encode16(frames, pool, pred_slot, x, 0, hist=hist, overflow=ovf, has_prev=has_prev, prev_x=prev_x)
+        elif x is not None:
             ops.finding_difference_hist(x, hist, ovf, has_prev, prev_x)                  # :339-340,348-355
         else:
             ops.encode_lossless(frames, pool, pred_slot, 0, hist=hist, overflow=ovf, has_prev=has_prev,
                                 prev_x=prev_x)
+
+    if entropy:
+        hist_ovf = torch.zeros(nbins + 1, dtype=torch.int64, device=dev)   # one buffer: one D2H, one reduce
+        hist, ovf = hist_ovf[:nbins], hist_ovf[nbins:]
+        hist_pass(hist, ovf)
         if comm is not None:
             comm.reduce_hist(hist_ovf)
         # table and symbol -> rank LUT on the device: the rank-map pass is queued right behind the histogram pass,
         # the host reads the table (and the overflow / collision flags) only after everything has been launched
-        tm = torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16, device=dev)   # table | meta (2 x int32)
-        table_dev, meta = tm[:TZ_HIST_BINS], tm[TZ_HIST_BINS:].view(torch.int32)
-        lut = torch.empty(TZ_HIST_BINS, dtype=torch.int16, device=dev)
-        ops.build_table_device(hist, table_dev, lut, meta)                                # :352-361, :84-90
+        if wide:
+            tm = torch.empty(nbins + 2, dtype=torch.int32, device=dev)      # table | meta (2 x int32)
+            table_dev, meta = tm[:nbins], tm[nbins:]
+            lut = torch.empty(nbins, dtype=torch.int32, device=dev)
+            ops.build_table16_device(hist, table_dev, lut, meta)
+        else:
+            tm = torch.empty(nbins + 4, dtype=torch.int16, device=dev)      # table | meta (2 x int32)
+            table_dev, meta = tm[:nbins], tm[nbins:].view(torch.int32)
+            lut = torch.empty(nbins, dtype=torch.int16, device=dev)
+            ops.build_table_device(hist, table_dev, lut, meta)                            # :352-361, :84-90
         # their (small) copies to the host are queued NOW, ahead of the stream's large device->host copies in the
         # copy engine's queue; they are waited for at the end
-        tm_host, ovf_host = _host_scratch(dev)
+        tm_host, ovf_host = _host_scratch(dev, wide)
         tm_host.copy_(tm, non_blocking=True)
         ovf_host.copy_(ovf, non_blocking=True)
         small_ready = torch.cuda.current_stream(dev).record_event()
     else:
         lut = None
 
+    def rank_call(a, b, lut_, hp, px):
+        """codes of stream elements [a, b) (a, b multiples of 8 or the ends)."""
+        if wide:
+            if x is not None:
+                ops.finding_difference_rank16(x.view(-1)[a:b], lut_, body[a:b], has_prev=hp, prev_x=px)
+            else:
+                assert a == 0 and b == N
+                ops.encode16(frames, pool, pred_slot, None, 1, lut=lut_, out=body, has_prev=hp, prev_x=px)
+        elif x is not None:
+            ops.finding_difference_rank(x.view(-1)[a:b], lut_, out=body[a:b], has_prev=hp, prev_x=px)  # :339-340,369
+        else:
+            assert a == 0 and b == N
+            ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut_, out=body, has_prev=hp, prev_x=px)
+
     def rank_pass(lut_):
         if x is not None and sink is not None and sink.chunks > 1:
             # rank map in chunks so that the device->host copy of chunk i overlaps the kernel of chunk i+1
-            xf = x.view(-1)
             step = -(-N // sink.chunks) // 8 * 8 + 8
             for a in range(0, N, step):
                 b = min(N, a + step)
                 if a == 0:
-                    ops.finding_difference_rank(xf[a:b], lut_, out=body[a:b], has_prev=has_prev, prev_x=prev_x)
+                    rank_call(a, b, lut_, has_prev, prev_x)
                 else:
-                    ops.finding_difference_rank(xf[a:b], lut_, out=body[a:b], has_prev=2)  # y[a] = x[a-1] - x[a]
+                    rank_call(a, b, lut_, 2, None)                 # y[a] = x[a-1] - x[a]
                 sink.body_chunk(body, a, b)
         else:
-            if x is not None:
-                ops.finding_difference_rank(x, lut_, out=body, has_prev=has_prev, prev_x=prev_x)  # :339-340,369
-            else:
-                ops.encode_lossless(frames, pool, pred_slot, 1, lut=lut_, out=body, has_prev=has_prev, prev_x=prev_x)
+            rank_call(0, N, lut_, has_prev, prev_x)
             if sink is not None:
                 sink.body_chunk(body, 0, N)
 
@@ -396,11 +452,14 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         small_ready.synchronize()
         if int(ovf_host[0]) != 0:
             raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
-                             "cannot represent this bound" % TZ_HIST_BINS)
-        meta_np = tm_host[TZ_HIST_BINS:].view(torch.int32).numpy()
-        table = tm_host[:int(meta_np[0])].numpy().copy()
-        if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
-            rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
+                             "cannot represent this bound" % nbins)
+        if wide:
+            table = tm_host[:int(tm_host[nbins])].numpy().copy()
+        else:
+            meta_np = tm_host[TZ_HIST_BINS:].view(torch.int32).numpy()
+            table = tm_host[:int(meta_np[0])].numpy().copy()
+            if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
+                rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
     if sink is not None:
         sink.finish()
     return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),
@@ -408,8 +467,29 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
 
 
 # ------------------------------------------------------------------------------------------------ decompress
+def parse_payload_v2(data):
+    data = np.asarray(data).view(np.uint8).reshape(-1).view("<i4")
+    if data.size < 11 or (int(data[-1]) & 0xffffffff) != V2_MAGIC or int(data[-2]) != V2_VERSION:
+        raise TezipError("not a container-v2 stream")
+    bits, p = int(data[-3]), int(data[-4])
+    if bits != 16:
+        raise TezipError("container v2 with %d-bit samples is not supported" % bits)
+    shape = tuple(int(v) for v in data[-9:-4])
+    data = data[:-9]
+    table_len = int(data[-1])
+    if table_len == -1:
+        return data[:-1], None, shape, p
+    if table_len < 0 or table_len + 1 > data.size:
+        raise TezipError("corrupt entropy.dat trailer (table length %d)" % table_len)
+    table_start = data.size - table_len - 1
+    return data[:table_start], data[table_start:-1].copy(), shape, p
+
+
 def parse_payload(data):
-    """decompress.py:103-113,203-221 -> (body view int16, table or None, shape(5), p)."""
+    """decompress.py:103-113,203-221 -> (body view int16, table or None, shape(5), p); container-v2 streams
+    (recognised by their magic) -> the same with int32 body / table."""
+    if is_v2_payload(data):
+        return parse_payload_v2(data)
     data = np.asarray(data, dtype=np.int16)
     if data.size < 8:
         raise TezipError("entropy.dat payload is too short")
@@ -442,8 +522,10 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
     plan = plan_from_keys(nt, p, keys)
     pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
     pred_slot = torch.from_numpy(plan.pred_slot).to(dev)
+    if ops.is_wide(body) != ops.is_wide(key_plane):
+        raise TezipError("key plane and stream disagree about the sample width")
     if table is not None:
-        lut = torch.from_numpy(ops.decode_lut(table)).to(dev)
+        lut = torch.from_numpy(ops.decode_lut16(table) if ops.is_wide(body) else ops.decode_lut(table)).to(dev)
         tl = len(table)
     else:
         lut, tl = None, -1
@@ -506,7 +588,7 @@ def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, firs
     dev = net.device
     main = torch.cuda.current_stream(dev)
     key_plane = key_host.to(dev, non_blocking=True)
-    body = torch.empty(body_host.numel(), dtype=torch.int16, device=dev)   # allocated on the main stream's pool
+    body = torch.empty(body_host.numel(), dtype=body_host.dtype, device=dev)   # allocated on the main stream's pool
     side = side_stream(dev)
     side.wait_event(main.record_event())      # after the key plane copy (same copy engine) and any earlier use of `body`
     with torch.cuda.stream(side):

@@ -2,30 +2,9 @@
 // decoder (rank -> symbol -> prefix scan -> reconstruct), DWP metric, key plane.
 // HBM-bound integer/byte work: coalesced 16-byte accesses, shared-memory histograms/LUTs, grids sized in
 // multiples of the SM count.  Reference lines cited per kernel (paths under /root/reference/src).
-#include "tz_common.cuh"
+#include "tz_codec.cuh"
 
 namespace {
-
-struct Geo {
-  int H, W, C, Hp, Wp;
-  int rowlen;              // W*C   samples per cropped row
-  int prow;                // Wp*C  floats per padded row
-  long long frame_elems;   // H*W*C
-  long long pframe_elems;  // Hp*Wp*C
-};
-
-static Geo make_geo(int H, int W, int C, int Hp, int Wp) {
-  Geo g;
-  g.H = H; g.W = W; g.C = C; g.Hp = Hp; g.Wp = Wp;
-  g.rowlen = W * C;
-  g.prow = Wp * C;
-  g.frame_elems = (long long)H * W * C;
-  g.pframe_elems = (long long)Hp * Wp * C;
-  return g;
-}
-
-// compress.py:307,310-311: float32 product, then truncation toward zero.
-__device__ __forceinline__ int q255(float p) { return __float2int_rz(__fmul_rn(p, 255.0f)); }
 
 // compress.py:293-314 for one sample (generic addressing).
 __device__ __forceinline__ int resid_at(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
@@ -141,120 +120,6 @@ __global__ void __launch_bounds__(256) residual_kernel(const uint8_t *__restrict
 // (abs / rel / absrel): with d integer, min_i fl(d_i+E) = fl(dmin+E) and max_i fl(d_i-E) = fl(dmax-E), so the
 // emptiness test depends only on the integer gap dmax - dmin; it equals gap > floor(2E) whenever the additions
 // are exact (E a multiple of 2^-36 below 4096) or 2E is at least 1e-6 from an integer (rounding is ~1e-13).
-struct EbInt {   // running (min d, max d)
-  int a, b;
-  __device__ static EbInt empty() { return {2147483647, -2147483647 - 1}; }
-  __device__ static EbInt of(int d, double, bool in) { return in ? EbInt{d, d} : empty(); }
-  __device__ EbInt join(const EbInt &o) const { return {min(a, o.a), max(b, o.b)}; }
-  __device__ bool broken(int G) const { return (long long)b - (long long)a > (long long)G; }
-  __device__ double mid(double E) const {   // (fl(dmin+E) + fl(dmax-E)) / 2, compress.py:61
-    return __dmul_rn(__dadd_rn(__dadd_rn((double)a, E), __dsub_rn((double)b, E)), 0.5);
-  }
-  __device__ EbInt shfl(int src) const { return {__shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src)}; }
-  __device__ EbInt shfl_up(int o) const { return {__shfl_up_sync(0xffffffffu, a, o), __shfl_up_sync(0xffffffffu, b, o)}; }
-};
-struct EbDbl {   // running (u = min Du, l = max Dl)
-  double u, l;
-  __device__ static EbDbl empty() {
-    return {__longlong_as_double(0x7ff0000000000000LL), __longlong_as_double(0xfff0000000000000LL)};
-  }
-  __device__ static EbDbl of(int d, double e, bool in) {
-    return in ? EbDbl{__dadd_rn((double)d, e), __dsub_rn((double)d, e)} : empty();   // compress.py:47-48
-  }
-  __device__ EbDbl join(const EbDbl &o) const { return {(o.u < u) ? o.u : u, (o.l > l) ? o.l : l}; }
-  __device__ bool broken(int) const { return __dsub_rn(u, l) < 0.0; }                 // compress.py:60
-  __device__ double mid(double) const { return __dmul_rn(__dadd_rn(u, l), 0.5); }     // compress.py:61
-  __device__ EbDbl shfl(int src) const { return {__shfl_sync(0xffffffffu, u, src), __shfl_sync(0xffffffffu, l, src)}; }
-  __device__ EbDbl shfl_up(int o) const { return {__shfl_up_sync(0xffffffffu, u, o), __shfl_up_sync(0xffffffffu, l, o)}; }
-};
-
-template <typename VAL>
-__device__ __forceinline__ void eb_plane_warp(const uint8_t *__restrict__ o, int16_t *__restrict__ d, int n, int C,
-                                              bool pwrel, double b0, double E, int G) {
-  const int lane = threadIdx.x & 31;
-  VAL carry = VAL::empty();   // state of the open segment [head, ...)
-  int head = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    const bool in = i < n;
-    const int dv = in ? (int)d[(long long)i * C] : 0;
-    const double e = pwrel ? __dmul_rn((double)(in ? (int)o[(long long)i * C] : 0), b0) : E;   // compress.py:45
-    const VAL mine = VAL::of(dv, e, in);
-    // ---- A: where does the carried segment end?
-    VAL pre = mine;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      VAL t = pre.shfl_up(off);
-      if (lane >= off) pre = pre.join(t);
-    }
-    pre = pre.join(carry);
-    const unsigned m = __ballot_sync(0xffffffffu, in && pre.broken(G));
-    if (m == 0) {   // the whole chunk joins the open segment
-      carry = pre.shfl(31);
-      continue;
-    }
-    const int b = __ffs(m) - 1;
-    {
-      const VAL seg = (b > 0) ? pre.shfl(b - 1) : carry;
-      const int16_t q = (int16_t)(long long)seg.mid(E);               // float -> int64 slice assignment truncates
-      for (int j = head + lane; j < base; j += 32) d[(long long)j * C] = q;   // part of the segment behind this chunk
-      if (lane < b && head <= i) d[(long long)i * C] = q;
-    }
-    // ---- B: for a segment starting at lane s, the first lane that breaks it (32 = still open at chunk end)
-    VAL run = mine;
-    int nb = 32;
-    bool done = !in;
-    for (int k = 1; k < 32; k++) {
-      const int t = lane + k;
-      const VAL vt = mine.shfl(t & 31);
-      const int tin_i = __shfl_sync(0xffffffffu, (int)in, t & 31);   // executed by every lane: no short-circuit
-      const bool tin = (t < 32) && (tin_i != 0);
-      if (!done) {
-        if (!tin) {
-          done = true;
-        } else {
-          const VAL nx = run.join(vt);
-          if (nx.broken(G)) {
-            done = true;
-            nb = t;
-          } else {
-            run = nx;
-          }
-        }
-      }
-      if (__all_sync(0xffffffffu, done)) break;
-    }
-    // ---- C: chase the links from lane b
-    int cur = b;
-    int16_t myq = 0;
-    bool have = false;
-    for (int guard = 0;; guard++) {
-      if (guard > 40) {   // cannot happen (links strictly increase); never hang the GPU on a logic error
-        if (lane == 0) printf("tezip_b200: error_bound link chase did not terminate (base %d cur %d)\n", base, cur);
-        __trap();
-      }
-      const int nxt = __shfl_sync(0xffffffffu, nb, cur);
-      const VAL seg = run.shfl(cur);
-      if (nxt >= 32) {   // stays open: becomes the carried segment
-        carry = seg;
-        head = base + cur;
-        break;
-      }
-      const int16_t q = (int16_t)(long long)seg.mid(E);
-      if (lane >= cur && lane < nxt) {
-        myq = q;
-        have = true;
-      }
-      cur = nxt;
-    }
-    if (have) d[(long long)i * C] = myq;
-  }
-  if (head < n) {   // compress.py:67
-    const int16_t q = (int16_t)(long long)carry.mid(E);
-    for (int j = head + lane; j < n; j += 32) d[(long long)j * C] = q;
-  }
-}
-
 __global__ void __launch_bounds__(128) error_bound_kernel(const uint8_t *__restrict__ frames,
                                                           int16_t *__restrict__ x,
                                                           const uint8_t *__restrict__ apply, long long nt, Geo g,
@@ -679,7 +544,7 @@ __global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restri
                                                          const uint8_t *__restrict__ frames,
                                                          const float *__restrict__ pool,
                                                          const int32_t *__restrict__ slot, Geo g, long long n,
-                                                         int has_prev, int prev_x,
+                                                         int has_prev, const int32_t *__restrict__ prev_x,
                                                          unsigned long long *__restrict__ hist,
                                                          unsigned long long *__restrict__ overflow) {
   __shared__ unsigned int sh[TZ_HIST_BINS];
@@ -693,7 +558,7 @@ __global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restri
     long long i0 = gi * 8;
     int v[8], y[8], prev;
     fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
-    if (i0 == 0 && has_prev == 1) prev = prev_x;
+    if (i0 == 0 && has_prev == 1) prev = *prev_x;
     delta8(v, prev, i0 == 0 && !has_prev, y);
     int cur = -1, cnt = 0;
 #pragma unroll
@@ -730,7 +595,7 @@ __global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restri
                                                          const uint8_t *__restrict__ frames,
                                                          const float *__restrict__ pool,
                                                          const int32_t *__restrict__ slot, Geo g, long long n,
-                                                         int has_prev, int prev_x,
+                                                         int has_prev, const int32_t *__restrict__ prev_x,
                                                          const int16_t *__restrict__ lut,
                                                          int16_t *__restrict__ out) {
   __shared__ int16_t sl[TZ_HIST_BINS];
@@ -744,7 +609,7 @@ __global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restri
     long long i0 = gi * 8;
     int v[8], y[8], prev;
     fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
-    if (i0 == 0 && has_prev == 1) prev = prev_x;
+    if (i0 == 0 && has_prev == 1) prev = *prev_x;
     delta8(v, prev, i0 == 0 && !has_prev, y);
     if (lut) {
 #pragma unroll
@@ -758,8 +623,6 @@ __global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------ decoder
-constexpr int DEC_THREADS = 256;
-constexpr int DEC_CHUNK = DEC_THREADS * 8;
 
 // decompress.py:31-36,236: rank -> symbol (LUT) -> y = 1600 - s; or y = body with -n streams.
 __device__ __forceinline__ void map8(const int16_t *sl, bool use_lut, int v[8]) {
@@ -799,43 +662,6 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_chunksum_kernel(const int1
     unsigned int t = 0;
     for (int w = 0; w < DEC_THREADS / 32; w++) t += wsum[w];
     sums[blockIdx.x] = t;
-  }
-}
-
-// exclusive scan of the chunk sums, single block (at most a few 10^4 chunks).
-__global__ void __launch_bounds__(1024) decode_scan_kernel(unsigned int *__restrict__ sums, long long nchunks) {
-  __shared__ unsigned int wtot[32];
-  __shared__ unsigned int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (long long base = 0; base < nchunks; base += 1024) {
-    long long i = base + threadIdx.x;
-    unsigned int v = (i < nchunks) ? sums[i] : 0;
-    unsigned int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
-    }
-    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      unsigned int w = wtot[threadIdx.x];
-      unsigned int winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
-        if (threadIdx.x >= o) winc += t;
-      }
-      wtot[threadIdx.x] = winc - w;   // exclusive warp offsets
-    }
-    __syncthreads();
-    unsigned int carry = carry_s;
-    unsigned int excl = carry + wtot[threadIdx.x >> 5] + inc - v;
-    if (i < nchunks) sums[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wtot[31] + inc;
-    __syncthreads();
   }
 }
 
@@ -1037,15 +863,11 @@ __global__ void __launch_bounds__(256) frames_nonzero_kernel(const uint8_t *__re
   if (threadIdx.x == 0) nonzero[f] = any ? 1 : 0;
 }
 
-static int stream_grid(long long work_items, int threads, int per_sm) {
-  long long blocks = (work_items + threads - 1) / threads;
-  long long cap = (long long)tz::sm_count() * per_sm;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+// last residual of a shard: the one-element halo of the 1-D delta across shards (compress.py:75), left on the device
+__global__ void last_residual_kernel(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
+                                     const int32_t *__restrict__ slot, Geo g, long long n, int32_t *__restrict__ out) {
+  out[0] = resid_at(frames, pool, slot, g, n - 1);
 }
-
-static bool fast_ok(const Geo &g) { return (g.rowlen % 8) == 0; }
 
 }  // namespace
 
@@ -1080,6 +902,16 @@ int tz_residual(const uint8_t *frames, const float *pred_pool, const int32_t *pr
   return TZ_OK;
 }
 
+int tz_last_residual(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt, int H,
+                     int W, int C, int Hp, int Wp, int32_t *out, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && pred_slot && out && nt > 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_last_residual: bad arguments");
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  last_residual_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, g, nt * g.frame_elems, out);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
 int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long long nt, int H, int W,
                    int C, int mode, double b0, double b1, void *stream) {
   TZ_REQUIRE(frames && x && apply && nt >= 0 && H > 0 && W > 0 && C > 0, "tz_error_bound: bad arguments");
@@ -1105,9 +937,10 @@ int tz_error_bound(const uint8_t *frames, int16_t *x, const uint8_t *apply, long
   return TZ_OK;
 }
 
-int tz_delta_hist(const int16_t *x, long long n, int has_prev, int prev_x, unsigned long long *hist,
+int tz_delta_hist(const int16_t *x, long long n, int has_prev, const int32_t *prev_x, unsigned long long *hist,
                   unsigned long long *overflow, void *stream) {
   TZ_REQUIRE(x && hist && overflow && n >= 0, "tz_delta_hist: bad arguments");
+  TZ_REQUIRE(has_prev >= 0 && has_prev <= 2 && (has_prev != 1 || prev_x), "tz_delta_hist: bad has_prev / prev_x");
   if (n == 0) return TZ_OK;
   Geo g = make_geo(1, 1, 1, 1, 1);
   int grid = stream_grid((n + 7) / 8, 256, 4);
@@ -1124,9 +957,10 @@ int tz_build_table(const unsigned long long *hist, int16_t *table, int16_t *lut,
   return TZ_OK;
 }
 
-int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const int16_t *lut, int16_t *out,
-                  void *stream) {
+int tz_delta_rank(const int16_t *x, long long n, int has_prev, const int32_t *prev_x, const int16_t *lut,
+                  int16_t *out, void *stream) {
   TZ_REQUIRE(x && out && n >= 0, "tz_delta_rank: bad arguments");
+  TZ_REQUIRE(has_prev >= 0 && has_prev <= 2 && (has_prev != 1 || prev_x), "tz_delta_rank: bad has_prev / prev_x");
   if (n == 0) return TZ_OK;
   Geo g = make_geo(1, 1, 1, 1, 1);
   int grid = stream_grid((n + 7) / 8, 256, 4);
@@ -1137,11 +971,12 @@ int tz_delta_rank(const int16_t *x, long long n, int has_prev, int prev_x, const
 }
 
 int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt,
-                       int H, int W, int C, int Hp, int Wp, int has_prev, int prev_x, int pass,
+                       int H, int W, int C, int Hp, int Wp, int has_prev, const int32_t *prev_x, int pass,
                        unsigned long long *hist, unsigned long long *overflow, const int16_t *lut,
                        int16_t *out, void *stream) {
   TZ_REQUIRE(frames && pred_pool && pred_slot && nt >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
              "tz_encode_lossless: bad arguments");
+  TZ_REQUIRE(has_prev >= 0 && has_prev <= 1 && (has_prev != 1 || prev_x), "tz_encode_lossless: bad has_prev / prev_x");
   TZ_REQUIRE(pass == 0 || pass == 1, "tz_encode_lossless: pass must be 0 or 1");
   if (nt == 0) return TZ_OK;
   Geo g = make_geo(H, W, C, Hp, Wp);

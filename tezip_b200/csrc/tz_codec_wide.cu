@@ -1,0 +1,646 @@
+// tezip_b200 -- codec kernels of the 16-bit container extension (BASELINE config 4: 1024x1024x1 u16 detector
+// frames).  The reference refuses such input (compress.py:106-110 converts everything to 8-bit RGB,
+// :183 stores a u8 key plane, :333 int16 residuals, :348 the 1600 offset, :394 int16 shape fields); the extension
+// restates the SAME pipeline with the widths the data needs (DESIGN.md "Container v2"):
+//   residual  x = trunc_f32(pred * 65535) - sample             int32, |x| <= 65535          (compress.py:304-314)
+//   delta     y[i] = x[i-1] - x[i] over the whole stream        int32, |y| <= 131070         (compress.py:73-77)
+//   symbol    s = 400000 - y  (the offset rule of compress.py:348: every symbol lies above every possible rank,
+//             268930 > 262141, so the sequential where() replacement of :84-90 is a pure LUT)
+//   table     symbols by count descending, ties ascending       int32[T], T <= 262141        (compress.py:352-361)
+//   codes     rank of s in the table, int32 little-endian
+// HBM-bound integer work like tz_codec.cu: 16-byte loads, 32-byte stores, a shared-memory histogram over the 16384
+// central bins (global 64-bit atomics for the tails), the rank LUT (1 MB) read through L1/L2.
+#include "tz_codec.cuh"
+
+namespace {
+
+constexpr int WIDE_BINS = TZ_WIDE_BINS;              // bin = s - (400000 - 131071) = 131071 - y
+constexpr int WIDE_CENTER = 131071;                  // bin of y = 0
+constexpr int WIN_BINS = 16384;                      // shared-memory window [WIDE_CENTER - 8192, WIDE_CENTER + 8192)
+constexpr int WIN_LO = WIDE_CENTER - WIN_BINS / 2;
+
+// float32 product, truncation toward zero (compress.py:307,310-311 with the 16-bit pixel maximum)
+__device__ __forceinline__ int q65535(float p) { return __float2int_rz(__fmul_rn(p, 65535.0f)); }
+
+__device__ __forceinline__ int resid16_at(const uint16_t *__restrict__ frames, const float *__restrict__ pool,
+                                          const int32_t *__restrict__ slot, const Geo &g, long long i) {
+  long long f = i / g.frame_elems;
+  int s = slot[f];
+  if (s < 0) return 0;
+  int r = (int)(i - f * g.frame_elems);
+  int row = r / g.rowlen;
+  int col = r - row * g.rowlen;
+  float p = pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col];
+  return q65535(p) - (int)frames[i];
+}
+
+template <bool FAST>
+__device__ __forceinline__ void resid16x8(const uint16_t *__restrict__ frames, const float *__restrict__ pool,
+                                          const int32_t *__restrict__ slot, const Geo &g, long long i0, long long n,
+                                          int v[8]) {
+  if (FAST) {   // rowlen % 8 == 0: the 8 samples share a frame and a row
+    long long f = i0 / g.frame_elems;
+    int s = slot[f];
+    if (s < 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = 0;
+      return;
+    }
+    int r = (int)(i0 - f * g.frame_elems);
+    int row = r / g.rowlen;
+    int col = r - row * g.rowlen;
+    uint4 a = *reinterpret_cast<const uint4 *>(frames + i0);
+    const float4 *pp =
+        reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
+    float4 p0 = pp[0], p1 = pp[1];
+    v[0] = q65535(p0.x) - (int)(a.x & 0xffff);
+    v[1] = q65535(p0.y) - (int)(a.x >> 16);
+    v[2] = q65535(p0.z) - (int)(a.y & 0xffff);
+    v[3] = q65535(p0.w) - (int)(a.y >> 16);
+    v[4] = q65535(p1.x) - (int)(a.z & 0xffff);
+    v[5] = q65535(p1.y) - (int)(a.z >> 16);
+    v[6] = q65535(p1.z) - (int)(a.w & 0xffff);
+    v[7] = q65535(p1.w) - (int)(a.w >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? resid16_at(frames, pool, slot, g, i0 + k) : 0;
+  }
+}
+
+__device__ __forceinline__ void load8_i32(const int32_t *__restrict__ x, long long i0, long long n, int v[8]) {
+  if (i0 + 8 <= n) {
+    int4 a = *reinterpret_cast<const int4 *>(x + i0), b = *reinterpret_cast<const int4 *>(x + i0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? x[i0 + k] : 0;
+  }
+}
+
+__device__ __forceinline__ void store8_i32(int32_t *__restrict__ out, long long i0, long long n, const int v[8]) {
+  if (i0 + 8 <= n) {   // one 32-byte store: a whole sector
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + i0), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (i0 + k < n) out[i0 + k] = v[k];
+  }
+}
+
+// SRC 0: x materialised (int32); 1 / 2: residual recomputed from frames + predictions (2 = vector path)
+template <int SRC>
+__device__ __forceinline__ void fetch16x8(const int32_t *__restrict__ x, const uint16_t *__restrict__ frames,
+                                          const float *__restrict__ pool, const int32_t *__restrict__ slot,
+                                          const Geo &g, long long i0, long long n, int v[8], int &prev, int has_prev) {
+  if (SRC == 0) {
+    load8_i32(x, i0, n, v);
+    prev = (i0 > 0 || has_prev == 2) ? x[i0 - 1] : 0;
+  } else {
+    resid16x8<SRC == 2>(frames, pool, slot, g, i0, n, v);
+    prev = (i0 > 0) ? resid16_at(frames, pool, slot, g, i0 - 1) : 0;
+  }
+}
+
+__device__ __forceinline__ void delta16x8(const int v[8], int prev, bool is_first_global, int y[8]) {
+  y[0] = is_first_global ? v[0] : prev - v[0];                      // compress.py:75 (int32: no wrap in range)
+#pragma unroll
+  for (int k = 1; k < 8; k++) y[k] = v[k - 1] - v[k];
+}
+
+// ------------------------------------------------------------------------------------------------ residual (lossy path)
+template <bool FAST>
+__global__ void __launch_bounds__(256) residual16_kernel(const uint16_t *__restrict__ frames,
+                                                         const float *__restrict__ pool,
+                                                         const int32_t *__restrict__ slot, int32_t *__restrict__ x,
+                                                         long long n, Geo g) {
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    int v[8];
+    resid16x8<FAST>(frames, pool, slot, g, gi * 8, n, v);
+    store8_i32(x, gi * 8, n, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ error_bound
+// compress.py:23-70 on int32 residual planes of 16-bit samples: the warp-serial scan of tz_codec.cuh (one warp per
+// (frame, channel) plane; same IEEE-double arithmetic, bounds in 0..65535 level units).  Config 4 is lossless; the
+// lossy modes are complete but not tuned (the 8-bit path's tiled kernel packs its state into int16 pairs).
+__global__ void __launch_bounds__(128) error_bound16_kernel(const uint16_t *__restrict__ frames,
+                                                            int32_t *__restrict__ x,
+                                                            const uint8_t *__restrict__ apply, long long nt, Geo g,
+                                                            int mode, double b0, double b1) {
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nt * g.C) return;
+  const long long f = t / g.C;
+  const int c = (int)(t - f * g.C);
+  if (!apply[f]) return;
+  const int lane = threadIdx.x & 31;
+  const int n = g.H * g.W;
+  const int C = g.C;
+  const uint16_t *o = frames + f * g.frame_elems + c;
+  int32_t *d = x + f * g.frame_elems + c;
+  double E = 0.0;
+  if (mode == TZ_MODE_ABS) {
+    E = fabs(b0);                                                        // :29
+  } else if (mode == TZ_MODE_REL || mode == TZ_MODE_ABSREL) {
+    int mx = 0, mn = 65535;                                              // :31-32 / :36-37
+    for (int i = lane; i < n; i += 32) {
+      int v = o[(long long)i * C];
+      mx = max(mx, v);
+      mn = min(mn, v);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if (mode == TZ_MODE_REL) {
+      E = __dmul_rn((double)(mx - mn), b0);                              // :33
+    } else {
+      double a = fabs(b0), r = __dmul_rn((double)(mx - mn), b1);         // :38-39
+      E = (a < r) ? a : r;                                               // :40-43
+    }
+  }
+  if (mode != TZ_MODE_PWREL) {   // the exact integer shortcut of tz_codec.cu (kernel comment there)
+    const double twoE = E + E;
+    const double sc = E * 68719476736.0;   // 2^36
+    const bool exact = (E < 4096.0) && (sc == floor(sc));
+    const bool clear = fabs(twoE - rint(twoE)) > 1e-6;
+    if (E >= 0.0 && (exact || clear)) {
+      const int G = twoE >= 300000.0 ? 300000 : (int)floor(twoE);
+      eb_plane_warp<EbInt, uint16_t, int32_t>(o, d, n, C, false, b0, E, G);
+      return;
+    }
+  }
+  eb_plane_warp<EbDbl, uint16_t, int32_t>(o, d, n, C, mode == TZ_MODE_PWREL, b0, E, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ delta + histogram
+template <int SRC>
+__global__ void __launch_bounds__(256) delta_hist16_kernel(const int32_t *__restrict__ x,
+                                                           const uint16_t *__restrict__ frames,
+                                                           const float *__restrict__ pool,
+                                                           const int32_t *__restrict__ slot, Geo g, long long n,
+                                                           int has_prev, const int32_t *__restrict__ prev_x,
+                                                           unsigned long long *__restrict__ hist,
+                                                           unsigned long long *__restrict__ overflow) {
+  extern __shared__ unsigned int sh[];   // WIN_BINS counters
+  for (int i = threadIdx.x; i < WIN_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  unsigned int ovf = 0;
+  auto add = [&](int bin, unsigned int cnt) {
+    const unsigned int w = (unsigned int)(bin - WIN_LO);
+    if (w < (unsigned int)WIN_BINS) atomicAdd(&sh[w], cnt);
+    else if ((unsigned int)bin < (unsigned int)WIDE_BINS) atomicAdd(&hist[bin], (unsigned long long)cnt);
+    else ovf += cnt;
+  };
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    long long i0 = gi * 8;
+    int v[8], y[8], prev;
+    fetch16x8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
+    if (i0 == 0 && has_prev == 1) prev = *prev_x;
+    delta16x8(v, prev, i0 == 0 && !has_prev, y);
+    int cur = -1;
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (i0 + k < n) {
+        const int bin = WIDE_CENTER - y[k];                              // s - 268929 with s = 400000 - y (:348)
+        if (bin == cur) {
+          cnt++;
+        } else {
+          if (cnt) add(cur, cnt);
+          cur = bin;
+          cnt = 1;
+        }
+      }
+    }
+    if (cnt) add(cur, cnt);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < WIN_BINS; i += blockDim.x) {
+    unsigned int c = sh[i];
+    if (c) atomicAdd(&hist[WIN_LO + i], (unsigned long long)c);
+  }
+  if (ovf) atomicAdd(overflow, (unsigned long long)ovf);
+}
+
+// ------------------------------------------------------------------------------------------------ table on the device
+// compress.py:352-361: compact the non-empty bins (any order: the keys are distinct, so the rank below does not
+// depend on it), then every key counts the keys that sort before it (count descending, ties by ascending symbol)
+// -- its rank IS its table position.  n^2 / 2 compares spread over the whole GPU: n = 10^4 symbols 0.01 ms,
+// the 262141-symbol worst case ~2 ms.
+__global__ void __launch_bounds__(256) table16_compact_kernel(const unsigned long long *__restrict__ hist,
+                                                              unsigned long long *__restrict__ keys,
+                                                              int32_t *__restrict__ lut, int32_t *__restrict__ meta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= WIDE_BINS) return;
+  lut[b] = TZ_WIDE_SYM_MIN + b;   // identity outside the table (where() leaves other values alone)
+  const unsigned long long c = hist[b];
+  if (c) keys[atomicAdd(&meta[0], 1)] = c * (unsigned long long)WIDE_BINS + (unsigned long long)(WIDE_BINS - 1 - b);
+}
+
+__global__ void __launch_bounds__(256) table16_rank_kernel(const unsigned long long *__restrict__ keys,
+                                                           const int32_t *__restrict__ meta,
+                                                           int32_t *__restrict__ table, int32_t *__restrict__ lut) {
+  __shared__ unsigned long long tile[1024];
+  const int n = meta[0];
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform
+    const int i = base + threadIdx.x;
+    const unsigned long long k = (i < n) ? keys[i] : 0ull;
+    int r = 0;
+    for (int t0 = 0; t0 < n; t0 += 1024) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < 1024; j += blockDim.x) tile[j] = (t0 + j < n) ? keys[t0 + j] : 0ull;
+      __syncthreads();
+      const int m = min(1024, n - t0);
+#pragma unroll 8
+      for (int j = 0; j < m; j++) r += tile[j] > k;
+    }
+    if (i < n) {
+      const int b = WIDE_BINS - 1 - (int)(k % (unsigned long long)WIDE_BINS);
+      table[r] = TZ_WIDE_SYM_MIN + b;
+      lut[b] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ delta + rank map
+template <int SRC>
+__global__ void __launch_bounds__(256) delta_rank16_kernel(const int32_t *__restrict__ x,
+                                                           const uint16_t *__restrict__ frames,
+                                                           const float *__restrict__ pool,
+                                                           const int32_t *__restrict__ slot, Geo g, long long n,
+                                                           int has_prev, const int32_t *__restrict__ prev_x,
+                                                           const int32_t *__restrict__ lut,
+                                                           int32_t *__restrict__ out) {
+  long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    long long i0 = gi * 8;
+    int v[8], y[8], prev;
+    fetch16x8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
+    if (i0 == 0 && has_prev == 1) prev = *prev_x;
+    delta16x8(v, prev, i0 == 0 && !has_prev, y);
+    if (lut) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int bin = WIDE_CENTER - y[k];
+        y[k] = ((unsigned int)bin < (unsigned int)WIDE_BINS) ? __ldg(lut + bin) : TZ_WIDE_OFFSET - y[k];
+      }
+    }
+    store8_i32(out, i0, n, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+// rank -> symbol (decompress.py:31-36 as a LUT over [0, WIDE_BINS); other values unchanged), y = 400000 - s (:236)
+__device__ __forceinline__ void map16x8(const int32_t *__restrict__ lut, bool use_lut, int v[8]) {
+  if (use_lut) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int r = v[k];
+      const int s = ((unsigned int)r < (unsigned int)WIDE_BINS) ? __ldg(lut + r) : r;
+      v[k] = TZ_WIDE_OFFSET - s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) decode16_chunksum_kernel(const int32_t *__restrict__ body, long long n,
+                                                                        int use_lut, const int32_t *__restrict__ lut,
+                                                                        unsigned int *__restrict__ sums) {
+  __shared__ unsigned int wsum[DEC_THREADS / 32];
+  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
+  int v[8];
+  load8_i32(body, i0, n, v);
+  map16x8(lut, use_lut != 0, v);
+  unsigned int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (i0 + k < n) s += (unsigned int)v[k];
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < DEC_THREADS / 32; w++) t += wsum[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// decompress.py:22-29 as a prefix sum (x[i] = x0 + y0 - S[i], uint32 wrap == int32 wrap), :252-256, :269 with 65535
+template <bool FAST>
+__global__ void __launch_bounds__(DEC_THREADS) decode16_reconstruct_kernel(
+    const int32_t *__restrict__ body, long long n, int use_lut, const int32_t *__restrict__ lut,
+    const unsigned int *__restrict__ chunk_prefix, int first_mode, int first_x, const float *__restrict__ pool,
+    const int32_t *__restrict__ slot, const uint16_t *__restrict__ key_plane, uint16_t *__restrict__ out,
+    int32_t *__restrict__ x_out, Geo g) {
+  __shared__ unsigned int wtot[DEC_THREADS / 32];
+  int y0;
+  {
+    const int r = body[0];
+    y0 = use_lut ? TZ_WIDE_OFFSET - (((unsigned int)r < (unsigned int)WIDE_BINS) ? __ldg(lut + r) : r) : r;
+  }
+  const int x0 = (first_mode == 0) ? y0 : first_x;
+  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
+  int v[8];
+  load8_i32(body, i0, n, v);
+  map16x8(lut, use_lut != 0, v);
+  unsigned int loc[8];
+  unsigned int run = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    run += (i0 + k < n) ? (unsigned int)v[k] : 0u;
+    loc[k] = run;
+  }
+  unsigned int inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wtot[w];
+  const unsigned int base = chunk_prefix[blockIdx.x] + woff + inc - run;
+  if (i0 >= n) return;
+  int xs[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) xs[k] = (int)((unsigned int)(x0 + y0) - (base + loc[k]));
+  if (x_out) store8_i32(x_out, i0, n, xs);
+  if (FAST && i0 + 8 <= n) {
+    long long f = i0 / g.frame_elems;
+    int s = slot[f];
+    int P[8];
+    if (s < 0) {
+      uint4 a = *reinterpret_cast<const uint4 *>(key_plane + i0);
+      P[0] = a.x & 0xffff; P[1] = a.x >> 16; P[2] = a.y & 0xffff; P[3] = a.y >> 16;
+      P[4] = a.z & 0xffff; P[5] = a.z >> 16; P[6] = a.w & 0xffff; P[7] = a.w >> 16;
+    } else {
+      int r = (int)(i0 - f * g.frame_elems);
+      int row = r / g.rowlen;
+      int col = r - row * g.rowlen;
+      const float4 *pp =
+          reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
+      float4 p0 = pp[0], p1 = pp[1];
+      P[0] = q65535(p0.x); P[1] = q65535(p0.y); P[2] = q65535(p0.z); P[3] = q65535(p0.w);
+      P[4] = q65535(p1.x); P[5] = q65535(p1.y); P[6] = q65535(p1.z); P[7] = q65535(p1.w);
+    }
+    unsigned int o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = (unsigned int)min(max(P[k] - xs[k], 0), 65535);
+    uint4 w;
+    w.x = o[0] | (o[1] << 16);
+    w.y = o[2] | (o[3] << 16);
+    w.z = o[4] | (o[5] << 16);
+    w.w = o[6] | (o[7] << 16);
+    *reinterpret_cast<uint4 *>(out + i0) = w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      long long i = i0 + k;
+      if (i < n) {
+        long long f = i / g.frame_elems;
+        int s = slot[f];
+        int P;
+        if (s < 0) {
+          P = key_plane[i];
+        } else {
+          int r = (int)(i - f * g.frame_elems);
+          int row = r / g.rowlen;
+          int col = r - row * g.rowlen;
+          P = q65535(pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col]);
+        }
+        out[i] = (uint16_t)min(max(P - xs[k], 0), 65535);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+// key-frame normalisation f32(k) / 65535 (compress.py:138 with the 16-bit maximum; IEEE division) + zero padding
+__global__ void __launch_bounds__(256) pad_normalize16_kernel(const uint16_t *__restrict__ frames,
+                                                              const int32_t *__restrict__ frame_idx,
+                                                              float *__restrict__ out, int B, Geo g) {
+  long long total = (long long)B * g.pframe_elems;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long b = i / g.pframe_elems;
+    int r = (int)(i - b * g.pframe_elems);
+    int row = r / g.prow;
+    int col = r - row * g.prow;
+    float v = 0.0f;
+    if (row < g.H && col < g.rowlen) {
+      long long f = frame_idx ? (long long)frame_idx[b] : b;
+      v = __fdiv_rn((float)frames[f * g.frame_elems + (long long)row * g.rowlen + col], 65535.0f);
+    }
+    out[i] = v;
+  }
+}
+
+// compress.py:245-246 for 16-bit samples: float64, fixed reduction order
+__global__ void __launch_bounds__(1024) window_sse16_kernel(const uint16_t *__restrict__ frames,
+                                                            const int32_t *__restrict__ frame_idx,
+                                                            const float *__restrict__ pred,
+                                                            double *__restrict__ sse, Geo g) {
+  __shared__ double red[1024];
+  const int b = blockIdx.x;
+  const long long f = frame_idx ? (long long)frame_idx[b] : (long long)b;
+  const float *p = pred + (long long)b * g.pframe_elems;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < g.pframe_elems; i += 1024) {
+    int row = (int)(i / g.prow);
+    int col = (int)(i - (long long)row * g.prow);
+    double a = 0.0;
+    if (row < g.H && col < g.rowlen)
+      a = (double)__fdiv_rn((float)frames[f * g.frame_elems + (long long)row * g.rowlen + col], 65535.0f);
+    double d = __dsub_rn(a, (double)p[i]);
+    acc = __dadd_rn(acc, __dmul_rn(d, d));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = __dadd_rn(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sse[b] = red[0];
+}
+
+// last residual of a shard (the one-element halo of the 1-D delta across shards, compress.py:75)
+__global__ void last_residual16_kernel(const uint16_t *__restrict__ frames, const float *__restrict__ pool,
+                                       const int32_t *__restrict__ slot, Geo g, long long n,
+                                       int32_t *__restrict__ out) {
+  out[0] = resid16_at(frames, pool, slot, g, n - 1);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int tz_pad_normalize16(const uint16_t *frames, const int32_t *frame_idx, float *out, int B, int H, int W, int C,
+                       int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && out && B >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_pad_normalize16: bad arguments");
+  if (B == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  int grid = stream_grid((long long)B * g.pframe_elems, 256, 8);
+  pad_normalize16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, frame_idx, out, B, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_residual16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, int32_t *x, long long nt,
+                  int H, int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && pred_slot && x && nt >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_residual16: bad arguments");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  int grid = stream_grid((n + 7) / 8, 256, 8);
+  if (fast_ok(g))
+    residual16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, x, n, g);
+  else
+    residual16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, x, n, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_last_residual16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, long long nt, int H,
+                       int W, int C, int Hp, int Wp, int32_t *out, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && pred_slot && out && nt > 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_last_residual16: bad arguments");
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  last_residual16_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(frames, pred_pool, pred_slot, g, nt * g.frame_elems, out);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_error_bound16(const uint16_t *frames, int32_t *x, const uint8_t *apply, long long nt, int H, int W, int C,
+                     int mode, double b0, double b1, void *stream) {
+  TZ_REQUIRE(frames && x && apply && nt >= 0 && H > 0 && W > 0 && C > 0, "tz_error_bound16: bad arguments");
+  TZ_REQUIRE(mode >= TZ_MODE_ABS && mode <= TZ_MODE_PWREL, "tz_error_bound16: unknown mode %d", mode);
+  if (b0 == 0.0) return TZ_OK;                                   // compress.py:24
+  if (mode == TZ_MODE_ABSREL && b1 == 0.0) return TZ_OK;         // compress.py:35
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, H, W);
+  long long planes = nt * C;
+  TZ_REQUIRE(planes < 2147483647LL / 32, "tz_error_bound16: too many planes (%lld)", planes);
+  TZ_REQUIRE((long long)H * W < 2147483647LL, "tz_error_bound16: plane too large");
+  const int threads = 128;
+  long long blocks = (planes * 32 + threads - 1) / threads;
+  error_bound16_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(frames, x, apply, nt, g, mode, b0, b1);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_encode16(const uint16_t *frames, const float *pred_pool, const int32_t *pred_slot, const int32_t *x,
+                long long nt, int H, int W, int C, int Hp, int Wp, int has_prev, const int32_t *prev_x, int pass,
+                unsigned long long *hist, unsigned long long *overflow, const int32_t *lut, int32_t *out,
+                void *stream) {
+  TZ_REQUIRE(nt >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W, "tz_encode16: bad arguments");
+  TZ_REQUIRE(x || (frames && pred_pool && pred_slot), "tz_encode16: needs x, or frames + pred_pool + pred_slot");
+  TZ_REQUIRE(pass == 0 || pass == 1, "tz_encode16: pass must be 0 or 1");
+  TZ_REQUIRE(has_prev >= 0 && has_prev <= 2 && (has_prev != 1 || prev_x), "tz_encode16: bad has_prev / prev_x");
+  TZ_REQUIRE(has_prev != 2 || x, "tz_encode16: has_prev == 2 needs a materialised x");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pass == 0) {
+    TZ_REQUIRE(hist && overflow, "tz_encode16: pass 0 needs hist and overflow");
+    static bool attr_set = false;
+    if (!attr_set) {
+      const int bytes = WIN_BINS * (int)sizeof(unsigned int);
+      TZ_CHECK_CUDA(cudaFuncSetAttribute(delta_hist16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      TZ_CHECK_CUDA(cudaFuncSetAttribute(delta_hist16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      TZ_CHECK_CUDA(cudaFuncSetAttribute(delta_hist16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      attr_set = true;
+    }
+    const size_t sm = WIN_BINS * sizeof(unsigned int);
+    int grid = stream_grid((n + 7) / 8, 256, 3);   // 64 KB of counters per CTA: three CTAs per SM
+    if (x)
+      delta_hist16_kernel<0><<<grid, 256, sm, st>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x, hist, overflow);
+    else if (fast_ok(g))
+      delta_hist16_kernel<2><<<grid, 256, sm, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, hist, overflow);
+    else
+      delta_hist16_kernel<1><<<grid, 256, sm, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, hist, overflow);
+  } else {
+    TZ_REQUIRE(out, "tz_encode16: pass 1 needs out");
+    int grid = stream_grid((n + 7) / 8, 256, 8);
+    if (x)
+      delta_rank16_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x, lut, out);
+    else if (fast_ok(g))
+      delta_rank16_kernel<2><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, lut, out);
+    else
+      delta_rank16_kernel<1><<<grid, 256, 0, st>>>(nullptr, frames, pred_pool, pred_slot, g, n, has_prev, prev_x, lut, out);
+  }
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+long long tz_build_table16_workspace_bytes(void) { return (long long)WIDE_BINS * (long long)sizeof(unsigned long long); }
+
+int tz_build_table16(const unsigned long long *hist, int32_t *table, int32_t *lut, int32_t *meta, void *workspace,
+                     void *stream) {
+  TZ_REQUIRE(hist && table && lut && meta && workspace, "tz_build_table16: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  TZ_CHECK_CUDA(cudaMemsetAsync(meta, 0, 2 * sizeof(int32_t), st));
+  table16_compact_kernel<<<WIDE_BINS / 256, 256, 0, st>>>(hist, (unsigned long long *)workspace, lut, meta);
+  TZ_CHECK_LAUNCH();
+  table16_rank_kernel<<<tz::sm_count() * 4, 256, 0, st>>>((const unsigned long long *)workspace, meta, table, lut);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+long long tz_reconstruct16_workspace_bytes(long long n) {
+  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
+  return (nchunks + 1) * (long long)sizeof(unsigned int);
+}
+
+int tz_reconstruct16(const int32_t *body, long long nt, int H, int W, int C, int Hp, int Wp, int table_len,
+                     const int32_t *rank_lut, int first_mode, int first_x, const float *pred_pool,
+                     const int32_t *pred_slot, const uint16_t *key_plane, uint16_t *out, int32_t *x_out,
+                     void *workspace, void *stream) {
+  TZ_REQUIRE(body && pred_pool && pred_slot && key_plane && out && workspace && nt >= 0 && H > 0 && W > 0 && C > 0 &&
+                 Hp >= H && Wp >= W,
+             "tz_reconstruct16: bad arguments");
+  TZ_REQUIRE(table_len < 0 || rank_lut, "tz_reconstruct16: rank_lut required when table_len >= 0");
+  if (nt == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  long long n = nt * g.frame_elems;
+  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
+  TZ_REQUIRE(nchunks < 2147483647LL, "tz_reconstruct16: stream too long for one call");
+  unsigned int *sums = (unsigned int *)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  int use_lut = table_len >= 0;
+  decode16_chunksum_kernel<<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(body, n, use_lut, rank_lut, sums);
+  TZ_CHECK_LAUNCH();
+  decode_scan_kernel<<<1, 1024, 0, st>>>(sums, nchunks);
+  TZ_CHECK_LAUNCH();
+  if (fast_ok(g))
+    decode16_reconstruct_kernel<true><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
+        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+  else
+    decode16_reconstruct_kernel<false><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
+        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_window_sse16(const uint16_t *frames, const int32_t *frame_idx, const float *pred, double *sse, int B, int H,
+                    int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && pred && sse && B >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W,
+             "tz_window_sse16: bad arguments");
+  if (B == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  window_sse16_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(frames, frame_idx, pred, sse, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+}  // extern "C"

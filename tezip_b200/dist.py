@@ -38,13 +38,24 @@ class ShardComm:
         return t if self.backend == "nccl" else t.cpu()
 
     def exchange_last_x(self, x_last):
-        dev = self.device if self.backend == "nccl" else "cpu"
-        mine = torch.tensor([int(x_last)], dtype=torch.int32, device=dev)
-        allx = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(allx, mine, group=self.group)
+        """x_last: device int32[1] (this shard's last residual).  -> (has_prev, device int32[1] holding the previous
+        shard's last residual, or None on rank 0).  No host synchronisation: the gathered array stays on the device
+        and the delta kernels read it through a pointer (tz_delta_hist's prev_x)."""
+        if not torch.is_tensor(x_last):
+            x_last = torch.tensor([int(x_last)], dtype=torch.int32, device=self.device if self.backend == "nccl" else "cpu")
+        mine = self._stage(x_last.reshape(1).to(torch.int32))
+        allx = torch.zeros(self.world, dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(allx, mine, group=self.group) if self.backend == "nccl" else \
+            allx.copy_(torch.cat(self._gather_list(mine)))
         if self.rank == 0:
-            return False, 0
-        return True, int(allx[self.rank - 1].item())
+            return False, None
+        prev = allx[self.rank - 1:self.rank]
+        return True, (prev if prev.device == x_last.device else prev.to(x_last.device))
+
+    def _gather_list(self, mine):
+        out = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return out
 
     def reduce_hist(self, hist):
         t = self._stage(hist)

@@ -9,11 +9,28 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MODES, TZ_HIST_BINS, TZ_SYMBOL_OFFSET, check, ptr
+from ._lib import MODES, TZ_HIST_BINS, TZ_SYMBOL_OFFSET, TZ_WIDE_BINS, TZ_WIDE_OFFSET, TZ_WIDE_SYM_MIN, check, ptr
 
 
 def _st(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def is_wide(t):
+    """True for the 16-bit sample / int32 code family (container v2), False for the reference's u8 / int16."""
+    return t.dtype in (torch.uint16, torch.int32)
+
+
+def _prev(dev, has_prev, prev_x):
+    """(has_prev, device pointer) for the delta halo: prev_x may be a device int32 tensor (stays on the device, the
+    sharded path) or a Python int (tests, single calls)."""
+    hp = int(has_prev)
+    if hp != 1:
+        return hp, None, None
+    if not torch.is_tensor(prev_x):
+        prev_x = torch.tensor([int(prev_x)], dtype=torch.int32, device=dev)
+    assert prev_x.is_cuda and prev_x.dtype == torch.int32 and prev_x.numel() >= 1
+    return hp, ptr(prev_x), prev_x     # the tensor is returned so that the caller keeps it alive across the launch
 
 
 _LUT_CACHE = {}
@@ -33,15 +50,25 @@ def pad_normalize(frames, frame_idx, Hp, Wp, out=None):
     B = n if frame_idx is None else frame_idx.numel()
     if out is None:
         out = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=frames.device)
+    if is_wide(frames):
+        check(_lib.load().tz_pad_normalize16(ptr(frames), ptr(frame_idx), ptr(out), B, H, W, C, Hp, Wp,
+                                             _st(frames.device)), "tz_pad_normalize16")
+        return out
     check(_lib.load().tz_pad_normalize(ptr(frames), ptr(frame_idx), ptr(norm_lut(frames.device)), ptr(out), B, H, W, C,
                                        Hp, Wp, _st(frames.device)), "tz_pad_normalize")
     return out
 
 
 def residual(frames, pred_pool, pred_slot, out=None):
-    """compress.py:293-314 -> int16 [n,H,W,C]."""
+    """compress.py:293-314 -> int16 [n,H,W,C] (int32 for 16-bit samples)."""
     n, H, W, C = frames.shape
     _s, Hp, Wp, _c = pred_pool.shape
+    if is_wide(frames):
+        if out is None:
+            out = torch.empty((n, H, W, C), dtype=torch.int32, device=frames.device)
+        check(_lib.load().tz_residual16(ptr(frames), ptr(pred_pool), ptr(pred_slot), ptr(out), n, H, W, C, Hp, Wp,
+                                        _st(frames.device)), "tz_residual16")
+        return out
     if out is None:
         out = torch.empty((n, H, W, C), dtype=torch.int16, device=frames.device)
     check(_lib.load().tz_residual(ptr(frames), ptr(pred_pool), ptr(pred_slot), ptr(out), n, H, W, C, Hp, Wp,
@@ -54,6 +81,10 @@ def error_bound(frames, x, apply, mode, value):
     n, H, W, C = frames.shape
     b0 = float(value[0])
     b1 = float(value[1]) if len(value) > 1 else 0.0
+    if is_wide(frames):
+        check(_lib.load().tz_error_bound16(ptr(frames), ptr(x), ptr(apply), n, H, W, C, MODES[mode], b0, b1,
+                                           _st(frames.device)), "tz_error_bound16")
+        return x
     check(_lib.load().tz_error_bound(ptr(frames), ptr(x), ptr(apply), n, H, W, C, MODES[mode], b0, b1,
                                      _st(frames.device)), "tz_error_bound")
     return x
@@ -61,8 +92,9 @@ def error_bound(frames, x, apply, mode, value):
 
 def finding_difference_hist(x, hist, overflow, has_prev=False, prev_x=0):
     """compress.py:73-77 + :348-355: accumulates the histogram of 1600 - y into hist (u64 as int64[4096])."""
-    check(_lib.load().tz_delta_hist(ptr(x), x.numel(), int(has_prev), int(prev_x), ptr(hist), ptr(overflow),
-                                    _st(x.device)), "tz_delta_hist")
+    hp, pp, _keep = _prev(x.device, has_prev, prev_x)
+    check(_lib.load().tz_delta_hist(ptr(x), x.numel(), hp, pp, ptr(hist), ptr(overflow), _st(x.device)),
+          "tz_delta_hist")
 
 
 def finding_difference_rank(x, lut, out=None, has_prev=False, prev_x=0):
@@ -71,8 +103,8 @@ def finding_difference_rank(x, lut, out=None, has_prev=False, prev_x=0):
         out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
     if out is not None and out.numel() != x.numel():
         raise ValueError("out must have as many elements as x")
-    check(_lib.load().tz_delta_rank(ptr(x), x.numel(), int(has_prev), int(prev_x), ptr(lut), ptr(out),
-                                    _st(x.device)), "tz_delta_rank")
+    hp, pp, _keep = _prev(x.device, has_prev, prev_x)
+    check(_lib.load().tz_delta_rank(ptr(x), x.numel(), hp, pp, ptr(lut), ptr(out), _st(x.device)), "tz_delta_rank")
     return out
 
 
@@ -80,10 +112,77 @@ def encode_lossless(frames, pred_pool, pred_slot, pass_, hist=None, overflow=Non
                     has_prev=False, prev_x=0):
     n, H, W, C = frames.shape
     _s, Hp, Wp, _c = pred_pool.shape
-    check(_lib.load().tz_encode_lossless(ptr(frames), ptr(pred_pool), ptr(pred_slot), n, H, W, C, Hp, Wp,
-                                         int(has_prev), int(prev_x), pass_, ptr(hist), ptr(overflow), ptr(lut),
-                                         ptr(out), _st(frames.device)), "tz_encode_lossless")
+    hp, pp, _keep = _prev(frames.device, has_prev, prev_x)
+    check(_lib.load().tz_encode_lossless(ptr(frames), ptr(pred_pool), ptr(pred_slot), n, H, W, C, Hp, Wp, hp, pp,
+                                         pass_, ptr(hist), ptr(overflow), ptr(lut), ptr(out), _st(frames.device)),
+          "tz_encode_lossless")
     return out
+
+
+def encode16(frames, pred_pool, pred_slot, x, pass_, hist=None, overflow=None, lut=None, out=None, has_prev=False,
+             prev_x=0):
+    """tz_encode16 (16-bit samples): pass 0 = histogram, pass 1 = rank map (or the raw delta stream, lut None); the
+    source is the materialised residual x (int32) when given, else frames + predictions (fused lossless)."""
+    n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    hp, pp, _keep = _prev(frames.device, has_prev, prev_x)
+    check(_lib.load().tz_encode16(ptr(frames), ptr(pred_pool), ptr(pred_slot), ptr(x), n, H, W, C, Hp, Wp, hp, pp,
+                                  pass_, ptr(hist), ptr(overflow), ptr(lut), ptr(out), _st(frames.device)),
+          "tz_encode16")
+    return out
+
+
+def finding_difference_rank16(x, lut, out, has_prev=False, prev_x=0):
+    """tz_encode16 pass 1 on a flat int32 residual stream (or a chunk of one: has_prev == 2)."""
+    hp, pp, _keep = _prev(x.device, has_prev, prev_x)
+    n = x.numel()
+    check(_lib.load().tz_encode16(None, None, None, ptr(x), n, 1, 1, 1, 1, 1, hp, pp, 1, None, None, ptr(lut), ptr(out),
+                                  _st(x.device)), "tz_encode16")
+    return out
+
+
+def last_residual(frames, pred_pool, pred_slot, out=None):
+    """The last residual of a shard as a device int32[1] (the delta halo its successor needs, compress.py:75)."""
+    n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    if out is None:
+        out = torch.empty(1, dtype=torch.int32, device=frames.device)
+    fn = "tz_last_residual16" if is_wide(frames) else "tz_last_residual"
+    check(getattr(_lib.load(), fn)(ptr(frames), ptr(pred_pool), ptr(pred_slot), n, H, W, C, Hp, Wp, ptr(out),
+                                   _st(frames.device)), fn)
+    return out
+
+
+_TABLE16_WS = {}
+
+
+def build_table16_device(hist, table, lut, meta):
+    """compress.py:352-361 for the wide symbol range (tz_build_table16): hist int64[TZ_WIDE_BINS] -> table int32,
+    lut int32[TZ_WIDE_BINS] (bin -> rank), meta int32[2] = (table length, 0)."""
+    lib = _lib.load()
+    key = str(hist.device)
+    if key not in _TABLE16_WS:
+        _TABLE16_WS[key] = torch.empty(int(lib.tz_build_table16_workspace_bytes()), dtype=torch.uint8, device=hist.device)
+    check(lib.tz_build_table16(ptr(hist), ptr(table), ptr(lut), ptr(meta), ptr(_TABLE16_WS[key]), _st(hist.device)),
+          "tz_build_table16")
+
+
+def build_table16(hist_np):
+    """Host form of the wide table: symbols (TZ_WIDE_SYM_MIN + bin) by count descending, ties ascending."""
+    ii = np.nonzero(hist_np)[0]
+    order = np.lexsort((ii, -hist_np[ii].astype(np.int64)))
+    return (ii[order] + TZ_WIDE_SYM_MIN).astype(np.int32)
+
+
+def decode_lut16(table):
+    """rank -> symbol over [0, TZ_WIDE_BINS), identity beyond the table (decompress.py:31-36; the wide offset keeps
+    every symbol above every rank, so the sequential replacement is a plain scatter)."""
+    t = np.asarray(table).astype(np.int64)
+    if len(t) and (int(t.min()) < len(t) or len(np.unique(t)) != len(t)):
+        raise _lib.TezipError("corrupt wide table: a symbol lies inside the rank range")
+    lut = np.arange(TZ_WIDE_BINS, dtype=np.int32)
+    lut[:len(t)] = t.astype(np.int32)
+    return lut
 
 
 def build_table_device(hist, table, lut, meta):
@@ -164,6 +263,14 @@ def reconstruct(body, shape, Hp, Wp, table_len, rank_lut, pred_pool, pred_slot, 
     n, H, W, C = shape
     dev = body.device
     lib = _lib.load()
+    if is_wide(body):
+        ws = torch.empty(int(lib.tz_reconstruct16_workspace_bytes(n * H * W * C)), dtype=torch.uint8, device=dev)
+        out = torch.empty((n, H, W, C), dtype=torch.uint16, device=dev)
+        x = torch.empty(n * H * W * C, dtype=torch.int32, device=dev) if want_x else None
+        check(lib.tz_reconstruct16(ptr(body), n, H, W, C, Hp, Wp, int(table_len), ptr(rank_lut), int(first_mode),
+                                   int(first_x), ptr(pred_pool), ptr(pred_slot), ptr(key_plane), ptr(out), ptr(x),
+                                   ptr(ws), _st(dev)), "tz_reconstruct16")
+        return (out, x) if want_x else out
     ws = torch.empty(int(lib.tz_reconstruct_workspace_bytes(n * H * W * C)), dtype=torch.uint8, device=dev)
     out = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
     x = torch.empty(n * H * W * C, dtype=torch.int16, device=dev) if want_x else None
@@ -179,6 +286,10 @@ def window_sse(frames, frame_idx, pred, out=None):
     B, Hp, Wp, _c = pred.shape
     if out is None:
         out = torch.empty(B, dtype=torch.float64, device=frames.device)
+    if is_wide(frames):
+        check(_lib.load().tz_window_sse16(ptr(frames), ptr(frame_idx), ptr(pred), ptr(out), B, H, W, C, Hp, Wp,
+                                          _st(frames.device)), "tz_window_sse16")
+        return out
     check(_lib.load().tz_window_sse(ptr(frames), ptr(frame_idx), ptr(norm_lut(frames.device)), ptr(pred), ptr(out), B,
                                     H, W, C, Hp, Wp, _st(frames.device)), "tz_window_sse")
     return out
