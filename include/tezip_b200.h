@@ -176,6 +176,20 @@ int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int H
                    const int32_t *pred_slot, const uint8_t *key_plane, uint8_t *out, int16_t *x_out,
                    void *workspace, void *stream);
 
+/* Fused lossy encode, pass 0 (compress.py:293-319 + :339-340,348-355 in ONE data pass): x = error_bound(residual)
+ * is written once (int16 [nt,H,W,C]) and the histogram of the delta symbols is accumulated on the way; the rank map
+ * (tz_delta_rank on x) is the second and last pass.  Same results, bit for bit, as tz_residual + tz_error_bound +
+ * tz_delta_hist.  apply: device u8[nt] as in tz_error_bound.  counter: device u32[1], caller-zeroed (the last CTA to
+ * finish adds the symbols that straddle frame boundaries).  has_prev: 0, 1 (*prev_x, device) as in tz_delta_hist, or
+ * 3 = the caller accounts for the first symbol of the stream itself (a shard whose halo arrives later: follow up with
+ * tz_delta_hist(x, 1, has_prev, prev_x, ...)).  tz_encode_lossy_supported(): plane-wide bounds (abs / rel / absrel),
+ * 1..4 channels, W*C a multiple of 8; otherwise use the separate entry points. */
+int tz_encode_lossy_supported(int H, int W, int C, int mode);
+int tz_encode_lossy(const uint8_t *frames, const float *pred_pool, const int32_t *pred_slot, const uint8_t *apply,
+                    int16_t *x, long long nt, int H, int W, int C, int Hp, int Wp, int mode, double b0, double b1,
+                    int has_prev, const int32_t *prev_x, unsigned long long *hist, unsigned long long *overflow,
+                    unsigned int *counter, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ 16-bit samples
  * Container v2 (BASELINE config 4: 1024x1024x1 u16 frames).  The reference cannot hold
  * such data: compress.py:106-110 turns every input into 8-bit RGB, :183 keeps a u8 key plane, :333 int16 residuals,

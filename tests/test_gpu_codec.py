@@ -194,3 +194,68 @@ def test_device_table_matches_host(cuda_lib):
         assert bool(bad) == collides
         if not bad:
             assert np.array_equal(lut.cpu().numpy(), ops.encode_lut(want_table))
+
+
+@pytest.mark.parametrize("H,W,C", [(128, 160, 3), (41, 56, 3), (1, 8, 3), (64, 32, 1), (33, 8, 1), (70, 96, 3),
+                                   (96, 1024, 1)], ids=lambda v: str(v))
+def test_fused_lossy_pass_equals_separate_kernels(cuda_lib, H, W, C):
+    """tz_encode_lossy (residual + error bound + delta histogram in one data pass, speculative segment scan) against
+    tz_residual + tz_error_bound + tz_delta_hist: x and the histogram must be identical, for short segments (noise),
+    long segments (flat + spikes, random walks, ramps: segments crossing lane, tile and plane-tail boundaries),
+    constant planes, window-start frames (x = 0) and frames without error bound (warm-up)."""
+    import torch
+    from tezip_b200 import ops
+    from tezip_b200._lib import TZ_HIST_BINS
+    dev = torch.device("cuda", 0)
+    nt, n = 9, H * W
+    rng = np.random.default_rng(H * 7919 + W * 13 + C)
+
+    def planes(kind):
+        if kind == "noise":
+            return rng.integers(-3, 4, size=(nt, n, C))
+        if kind == "wide":
+            return rng.integers(-100, 101, size=(nt, n, C))
+        if kind == "flat":
+            d = np.zeros((nt, n, C), np.int64)
+            for f in range(nt):
+                for c in range(C):
+                    k = max(1, n // 700)
+                    d[f, rng.integers(0, n, size=k), c] = rng.integers(-30, 31, size=k)
+            return d
+        if kind == "walk":
+            return np.clip(np.cumsum(rng.integers(-1, 2, size=(nt, n, C)), axis=1), -100, 100)
+        if kind == "ramp":
+            return np.broadcast_to(((np.arange(n) // 37) % 60 - 30)[None, :, None], (nt, n, C)).copy()
+        return np.full((nt, n, C), 5)
+
+    for kind in ("noise", "wide", "flat", "walk", "ramp", "const"):
+        d = planes(kind).reshape(nt, H, W, C)
+        a = rng.integers(100, 156, size=(nt, H, W, C))
+        frames = torch.from_numpy(a.astype(np.uint8)).to(dev)
+        pool = torch.from_numpy(((d + a + 0.5) / 255.0).astype(np.float32)).to(dev)      # trunc(pool * 255) = d + a
+        slot_np = np.arange(nt, dtype=np.int32)
+        slot_np[[0, 5]] = -1                                # window starts: x = 0
+        apply_np = (slot_np >= 0).astype(np.uint8)
+        apply_np[1] = 0                                     # a warm-up frame: residual, no error bound
+        slot, apply = torch.from_numpy(slot_np).to(dev), torch.from_numpy(apply_np).to(dev)
+        for mode, bound in (("abs", [2.0]), ("abs", [0.5]), ("abs", [2.55]), ("abs", [7.0]), ("abs", [40000.0]),
+                            ("rel", [0.013]), ("absrel", [4.0, 0.02]), ("abs", [1.0000001])):
+            x_ref = ops.residual(frames, pool, slot)
+            assert np.array_equal(x_ref.cpu().numpy()[slot_np >= 0], (d[slot_np >= 0]).astype(np.int16))
+            ops.error_bound(frames, x_ref, apply, mode, bound)
+            h_ref = torch.zeros(TZ_HIST_BINS + 1, dtype=torch.int64, device=dev)
+            ops.finding_difference_hist(x_ref, h_ref[:-1], h_ref[-1:])
+            h = torch.zeros(TZ_HIST_BINS + 2, dtype=torch.int64, device=dev)
+            x = ops.encode_lossy(frames, pool, slot, apply, mode, bound, h[:TZ_HIST_BINS], h[TZ_HIST_BINS:-1],
+                                 h[-1:].view(torch.int32))
+            assert torch.equal(x, x_ref), (kind, mode, bound)
+            assert torch.equal(h[:TZ_HIST_BINS + 1], h_ref), (kind, mode, bound)
+            # has_prev = 3: everything but the first symbol of the stream
+            h3 = torch.zeros(TZ_HIST_BINS + 2, dtype=torch.int64, device=dev)
+            ops.encode_lossy(frames, pool, slot, apply, mode, bound, h3[:TZ_HIST_BINS], h3[TZ_HIST_BINS:-1],
+                             h3[-1:].view(torch.int32), has_prev=3)
+            assert int(h3[:TZ_HIST_BINS].sum()) == x.numel() - 1
+            ops.finding_difference_hist(x.view(-1)[:1], h3[:TZ_HIST_BINS], h3[TZ_HIST_BINS:-1], 1, 7)
+            hp = torch.zeros(TZ_HIST_BINS + 1, dtype=torch.int64, device=dev)
+            ops.finding_difference_hist(x_ref, hp[:-1], hp[-1:], 1, 7)
+            assert torch.equal(h3[:TZ_HIST_BINS + 1], hp)

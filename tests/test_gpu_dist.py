@@ -68,3 +68,38 @@ def test_sharded_encode_equals_unsharded(cuda_lib, mode, bound):
         assert np.array_equal(dec, frames)
     else:
         assert np.abs(dec.astype(int) - frames.astype(int)).max() <= 2
+
+
+def test_one_frame_trailing_shard_and_zero_key_frame(cuda_lib):
+    """Advisor cases: 11 frames, window 5, 3 ranks -> the last rank owns ONE frame (a lone key) and must encode it;
+    an all-zero key frame is refused at compress time (the decoder could not find it, decompress.py:123-127)."""
+    import torch
+    from tezip_b200 import codec
+    from tezip_b200._lib import TezipError
+    from tezip_b200.dist import shard_ranges
+    stack, H, W, nt, Wn, world = TINY, 24, 40, 11, 5, 3
+    _o, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, 24, 40, max_batch=4)
+    frames = synth.make_frames(nt, H, W, 3, seed=31)
+    fr = torch.from_numpy(frames).cuda()
+    whole = codec.encode_frames(fr, net, 0, Wn, None, "abs", [0.0], True)
+    ranges = shard_ranges(nt, 0, Wn, world)
+    assert ranges[-1] == (10, 11)
+    comm = _FakeComm(world)
+    for phase in (0, 1):
+        comm.phase = phase
+        encs = []
+        for r, (a, b) in enumerate(ranges):
+            comm.rank, comm.calls = r, 0
+            encs.append(codec.encode_frames(fr[a:b].contiguous(), net, 0, Wn, None, "abs", [0.0], True, comm=comm))
+    assert np.array_equal(torch.cat([e.body for e in encs]).cpu().numpy(), whole.body.cpu().numpy())
+    black = fr.clone()
+    black[5] = 0                                            # frame 5 is a key frame of the schedule
+    with pytest.raises(TezipError):
+        codec.encode_frames(black, net, 0, Wn, None, "abs", [0.0], True)
+    black[5] = fr[5]
+    black[6] = 0                                            # a black NON-key frame is fine
+    enc = codec.encode_frames(black, net, 0, Wn, None, "abs", [0.0], True)
+    out, _ = codec.decode_arrays(enc.key_plane, enc.body, enc.table, enc.shape, 0, net)
+    assert torch.equal(out, black)
+    net.close()

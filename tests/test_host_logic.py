@@ -208,3 +208,31 @@ def test_keras_weight_converter_orders_by_weight_names(tmp_path):
         conv.prednet_weights(Node({"x": Node()}))
     with pytest.raises(ValueError):                                       # two layers with weights: not this model
         conv.prednet_weights(Node({"a": layer, "b": layer}, layer_names=[b"a", b"b"]))
+
+
+def test_shard_layouts_from_the_advisor_cases():
+    """Round-1 advisor findings: a trailing one-frame window is a legal shard (its rank encodes a lone key frame);
+    with fewer windows than ranks the decode ranges give rank 0 a real window and leave the TRAILING ranks empty."""
+    from tezip_b200 import codec
+    from tezip_b200.dist import shard_ranges, key_aligned_ranges
+    assert shard_ranges(11, 0, 5, 3) == [(0, 5), (5, 10), (10, 11)]
+    assert codec.swp_keys(1, 0, 5, shard=True) == [0]
+    with pytest.raises(codec.TezipError):
+        codec.swp_keys(1, 0, 5)
+    plan = codec.plan_from_keys(1, 0, [0])
+    assert plan.steps == [] and plan.n_slots == 1 and list(plan.pred_slot) == [-1]
+    assert key_aligned_ranges([0, 1, 2, 7, 12], 15, 2, 4) == [(0, 7), (7, 12), (12, 15), (15, 15)]
+    for keys, nt, p, world in (([0, 5, 10, 15], 20, 0, 2), ([0, 5, 10, 15, 20, 25, 30], 33, 0, 3), ([0, 1, 4], 9, 1, 8)):
+        rs = key_aligned_ranges(keys, nt, p, world)
+        assert rs[0][0] == 0 and rs[-1][1] == nt and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert rs[0][1] > p                                   # rank 0 owns a real window, not just warm-up frames
+        assert all(a in keys for a, b in rs[1:] if b > a)     # every non-empty range starts on a key frame
+
+
+def test_zstd_decoder_refuses_absurd_declared_sizes(monkeypatch):
+    from tezip_b200 import container
+    blob = container.zstd_compress(np.zeros(1 << 20, np.uint8))
+    assert container.zstd_decompress(blob).size == 1 << 20
+    monkeypatch.setenv("TEZIP_MAX_DECODED_BYTES", "1000")
+    with pytest.raises(RuntimeError):
+        container.zstd_decompress(blob)

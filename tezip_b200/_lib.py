@@ -55,6 +55,9 @@ SIGNATURES = {
     "tz_delta_rank": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
     "tz_encode_lossless": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int,
                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_encode_lossy_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "tz_encode_lossy": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl,
+                                c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tz_pad_normalize16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_residual16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "tz_last_residual16": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

@@ -31,10 +31,11 @@ def padding_size(num):
     return num if num % 8 == 0 else (int(num / 8) + 1) * 8
 
 
-def swp_keys(nt, p, window):
+def swp_keys(nt, p, window, shard=False):
     """Static-window key frames (compress.py:189-190,217-220,249-263): warm-up frames 0..p-1, then
-    p, p+W, p+2W, ..."""
-    if nt < p + 2:
+    p, p+W, p+2W, ...  shard=True: the frames are one rank's part of a longer sequence -- a trailing one-frame
+    window (a lone key frame) is then a legal shard."""
+    if nt < p + (1 if shard else 2):
         raise TezipError("need at least p+2 frames (the reference crashes otherwise, compress.py:267)")
     if window < 1:
         raise TezipError("window size must be >= 1")
@@ -318,7 +319,7 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         raise TezipError("error bounds must be non-negative")
     staged = None
     if threshold is None:
-        plan = plan_from_keys(nt, p, swp_keys(nt, p, window))
+        plan = plan_from_keys(nt, p, swp_keys(nt, p, window, shard=comm is not None))
         pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np = plan.keys, plan.pred_slot, plan.apply_eb
         # the schedule is static: upload it and emit the key plane before the first PredNet step is queued, so that
@@ -347,7 +348,23 @@ def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
     key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))
     if sink is not None:
         sink.key_plane(key_plane)
-    return pred_slot, apply, key_plane
+    # An all-zero key frame (a fade to black) cannot be told from a non-key frame by the decoder
+    # (decompress.py:123-127): the reference then silently decodes the wrong window.  The check costs one pass over
+    # the key plane and a tiny asynchronous copy; encode_with_pool looks at the answer once everything is queued.
+    nz = ops.frames_nonzero(key_plane)
+    nz_host = torch.empty(nt, dtype=torch.uint8).pin_memory()
+    nz_host.copy_(nz, non_blocking=True)
+    return pred_slot, apply, key_plane, (nz_host, is_key, torch.cuda.current_stream(dev).record_event())
+
+
+def check_key_frames(staged):
+    """Raises if a scheduled key frame is all zero (see stage_plan)."""
+    nz_host, is_key, ev = staged[3]
+    ev.synchronize()
+    bad = np.nonzero((nz_host.numpy() == 0) & (is_key != 0))[0]
+    if bad.size:
+        raise TezipError("frame %d is a key frame but all-zero: the container cannot mark it (decompress.py:123-127 "
+                         "finds key frames as 'not all-zero'); drop or perturb the frame" % int(bad[0]))
 
 
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
@@ -360,14 +377,22 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
     wide = ops.is_wide(frames)
     nbins = TZ_WIDE_BINS if wide else TZ_HIST_BINS
     code_dtype = torch.int32 if wide else torch.int16
-    pred_slot, apply_dev, key_plane = staged if staged is not None else stage_plan(frames, keys, pred_slot_np,
-                                                                                   apply_np, sink)
+    if staged is None:
+        staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink)
+    pred_slot, apply_dev, key_plane = staged[:3]
     N = nt * H * W * C
     body = torch.empty(N, dtype=code_dtype, device=dev)
     table = None
     x = None
     lossless = is_lossless(mode, bound)
-    if not lossless or keep_x:
+    # lossy, 8-bit, plane-wide bound: ONE data pass computes residual + error bound + delta histogram (tz_encode_lossy)
+    fused_lossy = (not lossless) and entropy and ops.encode_lossy_supported(frames, mode)
+    hist_ovf = torch.zeros(nbins + 2, dtype=torch.int64, device=dev) if entropy else None   # hist | overflow | counter
+    if fused_lossy:
+        x = ops.encode_lossy(frames, pool, pred_slot, apply_dev, mode, list(bound), hist_ovf[:nbins],
+                             hist_ovf[nbins:nbins + 1], hist_ovf[nbins + 1:].view(torch.int32),
+                             has_prev=3 if comm is not None else 0)
+    elif not lossless or keep_x:
         x = ops.residual(frames, pool, pred_slot)                                        # compress.py:293-314
         if not lossless:
             ops.error_bound(frames, x, apply_dev, mode, list(bound))                    # compress.py:315-319
@@ -382,7 +407,10 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
         has_prev, prev_x = comm.exchange_last_x(x_last)
 
     def hist_pass(hist, ovf):
-        if wide:
+        if fused_lossy:
+            if comm is not None:     # the stream's first symbol, now that the halo is here
+                ops.finding_difference_hist(x.view(-1)[:1], hist, ovf, has_prev, prev_x)
+        elif wide:
             ops.encode16(frames, pool, pred_slot, x, 0, hist=hist, overflow=ovf, has_prev=has_prev, prev_x=prev_x)
         elif x is not None:
             ops.finding_difference_hist(x, hist, ovf, has_prev, prev_x)                  # :339-340,348-355
@@ -391,11 +419,10 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
                                 prev_x=prev_x)
 
     if entropy:
-        hist_ovf = torch.zeros(nbins + 1, dtype=torch.int64, device=dev)   # one buffer: one D2H, one reduce
-        hist, ovf = hist_ovf[:nbins], hist_ovf[nbins:]
+        hist, ovf = hist_ovf[:nbins], hist_ovf[nbins:nbins + 1]            # one buffer: one D2H, one reduce
         hist_pass(hist, ovf)
         if comm is not None:
-            comm.reduce_hist(hist_ovf)
+            comm.reduce_hist(hist_ovf[:nbins + 1])
         # table and symbol -> rank LUT on the device: the rank-map pass is queued right behind the histogram pass,
         # the host reads the table (and the overflow / collision flags) only after everything has been launched
         if wide:
@@ -460,6 +487,7 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
             table = tm_host[:int(meta_np[0])].numpy().copy()
             if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
                 rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
+    check_key_frames(staged)
     if sink is not None:
         sink.finish()
     return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),

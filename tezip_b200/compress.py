@@ -30,7 +30,8 @@ def io_workers():
 
 def load_images(DATA_DIR, workers=None, paths=None):
     """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB.
-    One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
+    16-bit grayscale images (PIL mode I;16 -- the reference stops at compress.py:106-110) -> u16 [nt,H,W,1], written
+    as a version-2 container.  One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
     pool, so the array goes to the GPU with one asynchronous copy."""
     from concurrent.futures import ThreadPoolExecutor
     from PIL import Image, UnidentifiedImageError
@@ -40,18 +41,25 @@ def load_images(DATA_DIR, workers=None, paths=None):
     try:
         first = Image.open(file_paths[0])
         image_mode = first.mode
-        if image_mode not in ('RGB', 'L'):
+        wide = image_mode in ('I;16', 'I;16L')
+        if image_mode not in ('RGB', 'L') and not wide:
             _die("ERROR: input image is {0}. Only RGB and grayscale are supported.".format(image_mode))
         isRGB = image_mode == 'RGB'
         w, h = first.size
-        buf = torch.empty((len(file_paths), h, w, 3), dtype=torch.uint8)
+        buf = torch.empty((len(file_paths), h, w, 1), dtype=torch.uint16) if wide else \
+            torch.empty((len(file_paths), h, w, 3), dtype=torch.uint8)
         if torch.cuda.is_available():
             buf = buf.pin_memory()
         frames = buf.numpy()
 
         def decode(i):
             img = Image.open(file_paths[i])
-            frames[i] = np.asarray(img if isRGB else img.convert('RGB'))    # shape mismatch -> ValueError
+            if wide:
+                if img.mode not in ('I;16', 'I;16L'):
+                    raise ValueError("mixed image modes")
+                frames[i, :, :, 0] = np.asarray(img, dtype=np.uint16)
+            else:
+                frames[i] = np.asarray(img if isRGB else img.convert('RGB'))    # shape mismatch -> ValueError
 
         with ThreadPoolExecutor(workers or io_workers()) as pool:
             list(pool.map(decode, range(len(file_paths))))
@@ -67,9 +75,13 @@ def save_images(frames, file_names, isRGB, OUTPUT_DIR, workers=None):
     Appendix B)."""
     from concurrent.futures import ThreadPoolExecutor
     from PIL import Image
-    print("save as RGB" if isRGB else "save as gray")
+    wide = frames.dtype == np.uint16
+    print("save as 16-bit gray" if wide else "save as RGB" if isRGB else "save as gray")
 
     def encode(j):
+        if wide:
+            Image.fromarray(np.ascontiguousarray(frames[j, :, :, 0])).save(os.path.join(OUTPUT_DIR, file_names[j]))
+            return
         img = Image.fromarray(frames[j])
         (img if isRGB else img.convert("L")).save(os.path.join(OUTPUT_DIR, file_names[j]))
 
@@ -103,19 +115,24 @@ def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE
         _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
     ranges = tzdist.shard_ranges(nt, PREPROCESS, WINDOW_SIZE, world)
     a, b = ranges[rank]
-    if b <= a:
-        _die("ERROR: fewer windows than GPUs; use fewer processes")
+    # every rank evaluates the same layout test, so that they all leave together (a rank that exits alone would leave
+    # its peers blocked in the first collective)
+    if nt < PREPROCESS + 2 or any(rb <= ra for ra, rb in ranges):
+        _die("ERROR: fewer windows than GPUs (or fewer than p+2 frames); use fewer processes")
     frames, files, isRGB = load_images(DATA_DIR, paths=file_paths[a:b])
     n_win = max(1, (b - a + WINDOW_SIZE - 1) // WINDOW_SIZE)
     net = load_predictor(WEIGHTS_DIR, max_batch=min(n_win, 256), device=local)
     dev = net.device
     comm = tzdist.ShardComm(device=dev)
+    enc, err = None, None
     try:
         enc = codec.encode_frames(torch.from_numpy(frames).to(dev, non_blocking=True), net,
                                   PREPROCESS if rank == 0 else 0, WINDOW_SIZE, None, MODE, list(BOUND_VALUE),
                                   ENTROPY_RUN, comm=comm)
     except TezipError as e:
-        _die(str(e))
+        err = str(e)
+    if not tzdist.all_ok(err is None):      # agree before the stream gather
+        _die(err or "ERROR: another rank failed")
     fe = frames[0].size
     sizes = [(rb - ra) * fe for ra, rb in ranges]
     body = tzdist.gather_varlen(enc.body, sizes)
@@ -168,5 +185,5 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, M
     kb, eb = container.write_container(OUTPUT_DIR, files, isRGB, key_plane, payload, workers=zstd_workers)
     if VERBOSE:
         print("zstd+write:{0}".format(time.time() - t0) + "[sec]")
-        print("key frames:", len(enc.keys), "ratio:", frames.size / float(kb + eb))
+        print("key frames:", len(enc.keys), "ratio:", frames.nbytes / float(kb + eb))
     net.close()

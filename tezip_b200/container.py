@@ -12,6 +12,7 @@ import os
 import numpy as np
 
 ZSTD_LEVEL = 9                       # compress.py:276,398
+MAX_DECODED_BYTES = 1 << 37          # 128 GiB: a 32767-frame 1024x1024x1 v2 stream is 2^37 bytes
 KEY_FILE, ENTROPY_FILE, NAMES_FILE = "key_frame.dat", "entropy.dat", "filename.txt"
 _ZSTD_c_compressionLevel, _ZSTD_c_contentSizeFlag, _ZSTD_c_nbWorkers = 100, 200, 400
 
@@ -67,7 +68,15 @@ def zstd_decompress(data):
     size = z.ZSTD_getFrameContentSize(src.ctypes.data, src.size)
     if size >= (1 << 62):
         raise RuntimeError("zstd frame does not carry its content size")
-    dst = np.empty(max(int(size), 1), np.uint8)
+    # the header is untrusted input: refuse absurd sizes instead of attempting the allocation
+    cap = int(os.environ.get("TEZIP_MAX_DECODED_BYTES", str(MAX_DECODED_BYTES)))
+    if int(size) > cap:
+        raise RuntimeError("zstd frame declares %d bytes of content, more than the limit of %d "
+                           "(TEZIP_MAX_DECODED_BYTES)" % (int(size), cap))
+    try:
+        dst = np.empty(max(int(size), 1), np.uint8)
+    except MemoryError:
+        raise RuntimeError("cannot allocate %d bytes for the decoded stream" % int(size))
     r = z.ZSTD_decompress(dst.ctypes.data, int(size), src.ctypes.data, src.size)
     if z.ZSTD_isError(r) or r != size:
         raise RuntimeError("zstd decompression failed")
@@ -75,23 +84,28 @@ def zstd_decompress(data):
 
 
 def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
-    """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd)."""
+    """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd).
+    Container v2 (16-bit samples): key_plane u16 and payload int32, both little-endian, same three files."""
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, NAMES_FILE), "w", encoding="UTF-8") as f:     # compress.py:133-136
         f.write("%d\n" % int(is_rgb))
         for nm in names:
             f.write("%s\n" % nm)
-    kb = zstd_compress(np.ascontiguousarray(key_plane, np.uint8), ZSTD_LEVEL, workers)     # compress.py:271-278
+    wide = np.asarray(payload).dtype == np.int32
+    if wide != (np.asarray(key_plane).dtype == np.uint16):
+        raise ValueError("key plane and stream disagree about the sample width")
+    kb = zstd_compress(np.ascontiguousarray(key_plane, "<u2" if wide else np.uint8), ZSTD_LEVEL, workers)   # compress.py:271-278
     with open(os.path.join(out_dir, KEY_FILE), "wb") as f:
         f.write(kb)
-    eb = zstd_compress(np.ascontiguousarray(payload, "<i2"), ZSTD_LEVEL, workers)          # compress.py:394-400
+    eb = zstd_compress(np.ascontiguousarray(payload, "<i4" if wide else "<i2"), ZSTD_LEVEL, workers)       # compress.py:394-400
     with open(os.path.join(out_dir, ENTROPY_FILE), "wb") as f:
         f.write(eb)
     return len(kb), len(eb)
 
 
 def read_container(comp_dir):
-    """-> (names, is_rgb, key_plane u8 flat, payload int16)  (decompress.py:48-56,87-103)."""
+    """-> (names, is_rgb, key_plane u8 flat, payload int16)  (decompress.py:48-56,87-103); a container-v2 stream
+    (recognised by the magic that ends it) -> key_plane u16 flat, payload int32."""
     with open(os.path.join(comp_dir, NAMES_FILE), "r", encoding="UTF-8") as f:
         names = [s.strip() for s in f.readlines()]
     is_rgb = True
@@ -100,5 +114,8 @@ def read_container(comp_dir):
     with open(os.path.join(comp_dir, KEY_FILE), "rb") as f:
         key_plane = zstd_decompress(f.read())
     with open(os.path.join(comp_dir, ENTROPY_FILE), "rb") as f:
-        payload = zstd_decompress(f.read()).view("<i2")
-    return names, is_rgb, key_plane, payload
+        raw = zstd_decompress(f.read())
+    from .codec import is_v2_payload
+    if is_v2_payload(raw):
+        return names, is_rgb, key_plane.view("<u2"), raw.view("<i4")
+    return names, is_rgb, key_plane, raw.view("<i2")

@@ -6,89 +6,6 @@
 
 namespace {
 
-// compress.py:293-314 for one sample (generic addressing).
-__device__ __forceinline__ int resid_at(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
-                                        const int32_t *__restrict__ slot, const Geo &g, long long i) {
-  long long f = i / g.frame_elems;
-  int s = slot[f];
-  if (s < 0) return 0;
-  int r = (int)(i - f * g.frame_elems);
-  int row = r / g.rowlen;
-  int col = r - row * g.rowlen;
-  float p = pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col];
-  return q255(p) - (int)frames[i];
-}
-
-// Loads the residuals of 8 consecutive samples i0..i0+7 (i0 % 8 == 0) into v[0..7].
-// Fast path (rowlen % 8 == 0): one 8-byte frame load + two 16-byte prediction loads.
-template <bool FAST>
-__device__ __forceinline__ void resid8(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
-                                       const int32_t *__restrict__ slot, const Geo &g, long long i0,
-                                       long long n, int v[8]) {
-  if (FAST) {
-    long long f = i0 / g.frame_elems;
-    int s = slot[f];
-    if (s < 0) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = 0;
-      return;
-    }
-    int r = (int)(i0 - f * g.frame_elems);
-    int row = r / g.rowlen;
-    int col = r - row * g.rowlen;
-    uint2 a = *reinterpret_cast<const uint2 *>(frames + i0);
-    const float4 *pp =
-        reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
-    float4 p0 = pp[0], p1 = pp[1];
-    v[0] = q255(p0.x) - (int)(a.x & 0xff);
-    v[1] = q255(p0.y) - (int)((a.x >> 8) & 0xff);
-    v[2] = q255(p0.z) - (int)((a.x >> 16) & 0xff);
-    v[3] = q255(p0.w) - (int)(a.x >> 24);
-    v[4] = q255(p1.x) - (int)(a.y & 0xff);
-    v[5] = q255(p1.y) - (int)((a.y >> 8) & 0xff);
-    v[6] = q255(p1.z) - (int)((a.y >> 16) & 0xff);
-    v[7] = q255(p1.w) - (int)(a.y >> 24);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? resid_at(frames, pool, slot, g, i0 + k) : 0;
-  }
-}
-
-__device__ __forceinline__ void load8_i16(const int16_t *__restrict__ x, long long i0, long long n, int v[8]) {
-  if (i0 + 8 <= n) {
-    uint4 a = *reinterpret_cast<const uint4 *>(x + i0);
-    v[0] = (int16_t)(a.x & 0xffff); v[1] = (int16_t)(a.x >> 16);
-    v[2] = (int16_t)(a.y & 0xffff); v[3] = (int16_t)(a.y >> 16);
-    v[4] = (int16_t)(a.z & 0xffff); v[5] = (int16_t)(a.z >> 16);
-    v[6] = (int16_t)(a.w & 0xffff); v[7] = (int16_t)(a.w >> 16);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? (int)x[i0 + k] : 0;
-  }
-}
-
-__device__ __forceinline__ void store8_i16(int16_t *__restrict__ out, long long i0, long long n, const int v[8]) {
-  if (i0 + 8 <= n) {
-    uint4 a;
-    a.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
-    a.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
-    a.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
-    a.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
-    *reinterpret_cast<uint4 *>(out + i0) = a;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (i0 + k < n) out[i0 + k] = (int16_t)v[k];
-  }
-}
-
-// compress.py:75: y[i] = x[i-1] - x[i] in int16 arithmetic; y[0] = x[0] (or prev_x - x[0] on a shard).
-__device__ __forceinline__ void delta8(const int v[8], int prev, bool is_first_global, int y[8]) {
-  y[0] = is_first_global ? v[0] : (int)(int16_t)(prev - v[0]);
-#pragma unroll
-  for (int k = 1; k < 8; k++) y[k] = (int)(int16_t)(v[k - 1] - v[k]);
-}
-
 // ------------------------------------------------------------------------------------------------ residual
 // compress.py:293-314.  One thread per 8 samples.
 template <bool FAST>

@@ -26,38 +26,53 @@ def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, VERBOSE):
     dev = torch.device("cuda", local)
     meta = [None]
     key_full = body_full = None
+    fail = None
     if rank == 0:
-        file_names, isRGB, key_plane, payload = container.read_container(DATA_DIR)
-        body, table, shape, p = codec.parse_payload(payload)
-        if len(file_names) != shape[1]:
-            print("ERROR：The lengths of filename.txt and images do not match.")
-            _die("number of images", shape[1])
+        try:
+            file_names, isRGB, key_plane, payload = container.read_container(DATA_DIR)
+            body, table, shape, p = codec.parse_payload(payload)
+            if len(file_names) != shape[1]:
+                fail = "ERROR：The lengths of filename.txt and images do not match. number of images %d" % shape[1]
+        except (TezipError, RuntimeError, OSError) as e:
+            fail = str(e)
+    status = [fail]
+    tdist.broadcast_object_list(status, src=0)      # every rank leaves together if rank 0 could not read the container
+    if status[0] is not None:
+        _die(status[0])
+    if rank == 0:
         _one, nt, H, W, C = shape
         key_full = torch.from_numpy(np.ascontiguousarray(key_plane)).to(dev)
         body_full = torch.from_numpy(np.ascontiguousarray(body)).to(dev)
         nz = ops.frames_nonzero(key_full.view(nt, H, W, C)).cpu().numpy()
         keys = [int(i) for i in np.nonzero(nz)[0]]
         ranges = tzdist.key_aligned_ranges(keys, nt, p, world)
-        meta = [(file_names, isRGB, None if table is None else np.asarray(table), shape, p, ranges)]
+        meta = [(file_names, isRGB, None if table is None else np.asarray(table), shape, p, ranges,
+                 body.dtype == np.int32)]
     tdist.broadcast_object_list(meta, src=0)
-    file_names, isRGB, table, shape, p, ranges = meta[0]
+    file_names, isRGB, table, shape, p, ranges, _wide = meta[0]
     _one, nt, H, W, C = shape
     fe = H * W * C
     sizes = [(b - a) * fe for a, b in ranges]
     a, b = ranges[rank]
-    key_part = tzdist.scatter_varlen(key_full, sizes, torch.uint8, dev)
-    body_part = tzdist.scatter_varlen(body_full, sizes, torch.int16, dev)
+    wide = meta[0][6]
+    key_part = tzdist.scatter_varlen(key_full, sizes, torch.uint16 if wide else torch.uint8, dev)
+    body_part = tzdist.scatter_varlen(body_full, sizes, torch.int32 if wide else torch.int16, dev)
     if b > a:
         n_keys_guess = max(1, (b - a) // 4)
         net = load_predictor(WEIGHTS_DIR, max_batch=min(n_keys_guess, 256), device=local)
+        err = None
         try:
             out, _plan = codec.decode_arrays(key_part.contiguous(), body_part.contiguous(), table, (1, b - a, H, W, C),
                                              p if rank == 0 else 0, net, first_mode=0 if rank == 0 else 1, first_x=0)
         except TezipError as e:
-            _die(str(e))
-        save_images(out.cpu().numpy(), file_names[a:b], isRGB, OUTPUT_DIR)
+            err = str(e)
+        if err is None:
+            save_images(out.cpu().numpy(), file_names[a:b], isRGB, OUTPUT_DIR)
         net.close()
-    tdist.barrier()
+    else:
+        err = None
+    if not tzdist.all_ok(err is None):
+        _die(err or "ERROR: another rank failed")
 
 
 def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, GPU_FLAG, VERBOSE):

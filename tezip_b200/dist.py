@@ -137,8 +137,19 @@ def key_aligned_ranges(keys, nt, p, world):
     n_win = len(starts)
     out = []
     for r in range(world):
-        w0, w1 = n_win * r // world, n_win * (r + 1) // world
+        # ceil split: with fewer windows than ranks the LEADING ranks get one window each (rank 0 must own a real
+        # window: a range of warm-up frames only cannot be decoded), the trailing ranks get empty ranges
+        w0, w1 = -(-n_win * r // world), -(-n_win * (r + 1) // world)
         a = 0 if r == 0 else (starts[w0] if w0 < n_win else nt)
         b = nt if r == world - 1 else (starts[w1] if w1 < n_win else nt)
         out.append((min(a, nt), min(b, nt)))
     return out
+
+
+def all_ok(ok, group=None):
+    """True on every rank only if `ok` is true on every rank (ranks must fail together: one that exits alone leaves
+    its peers blocked in the next collective)."""
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())

@@ -24,7 +24,7 @@ def is_wide(t):
 def _prev(dev, has_prev, prev_x):
     """(has_prev, device pointer) for the delta halo: prev_x may be a device int32 tensor (stays on the device, the
     sharded path) or a Python int (tests, single calls)."""
-    hp = int(has_prev)
+    hp = int(has_prev)                      # 0 / 1 / 2 (chunked) / 3 (tz_encode_lossy: first symbol by the caller)
     if hp != 1:
         return hp, None, None
     if not torch.is_tensor(prev_x):
@@ -117,6 +117,28 @@ def encode_lossless(frames, pred_pool, pred_slot, pass_, hist=None, overflow=Non
                                          pass_, ptr(hist), ptr(overflow), ptr(lut), ptr(out), _st(frames.device)),
           "tz_encode_lossless")
     return out
+
+
+def encode_lossy_supported(frames, mode):
+    _n, H, W, C = frames.shape
+    return (not is_wide(frames)) and bool(_lib.load().tz_encode_lossy_supported(H, W, C, MODES[mode]))
+
+
+def encode_lossy(frames, pred_pool, pred_slot, apply, mode, value, hist, overflow, counter, x=None, has_prev=False,
+                 prev_x=0):
+    """compress.py:293-319 + :339-340,348-355 in one data pass (tz_encode_lossy): returns x = error_bound(residual)
+    (int16 [n,H,W,C]) and accumulates the delta-symbol histogram.  counter: device int32[1], zeroed by the caller."""
+    n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    if x is None:
+        x = torch.empty((n, H, W, C), dtype=torch.int16, device=frames.device)
+    b0 = float(value[0])
+    b1 = float(value[1]) if len(value) > 1 else 0.0
+    hp, pp, _keep = _prev(frames.device, has_prev, prev_x)
+    check(_lib.load().tz_encode_lossy(ptr(frames), ptr(pred_pool), ptr(pred_slot), ptr(apply), ptr(x), n, H, W, C, Hp,
+                                      Wp, MODES[mode], b0, b1, hp, pp, ptr(hist), ptr(overflow), ptr(counter),
+                                      _st(frames.device)), "tz_encode_lossy")
+    return x
 
 
 def encode16(frames, pred_pool, pred_slot, x, pass_, hist=None, overflow=None, lut=None, out=None, has_prev=False,

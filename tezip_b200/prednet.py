@@ -44,7 +44,7 @@ def _load_hdf5_weights(path, cfg):
         import h5py
     except ImportError:
         raise _lib.TezipError("reading %s needs h5py, which is not installed; convert it once with "
-                              "scripts/convert_weights.py where h5py exists" % path)
+                              "scripts/convert_keras_weights.py where h5py exists" % path)
     with h5py.File(path, "r") as f:
         g = f["model_weights"] if "model_weights" in f else f           # train.py:109 saves a full-model file
         layer = [k for k in g.keys() if "prednet" in k.lower()][0]
