@@ -517,7 +517,7 @@ def run_native(args):
         pool_c = torch.empty((2 * Wn + 2, H, W, C), dtype=torch.float32, device=dev)
         _k, slot_c, _a, _n = codec.run_dwp(net, frames_dev[:2 * Wn].contiguous(), 0, 1e30, pool_c, 1)
         idx = torch.arange(1, Wn + 1, dtype=torch.int32, device=dev)
-        sse = ops.window_sse(frames_dev, idx, pool_c[torch.from_numpy(slot_c[1:Wn + 1].astype(np.int64)).to(dev)])
+        sse = ops.window_sse(frames_dev, idx, pool_c[slot_c[1:Wn + 1].to(torch.int64)])
         thr = float(sse.sum().item() / (Wn * H * W * C))
         chains, win = args.chains, None
 

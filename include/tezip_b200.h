@@ -245,6 +245,19 @@ int tz_window_sse16(const uint16_t *frames, const int32_t *frame_idx, const floa
 int tz_window_sse(const uint8_t *frames, const int32_t *frame_idx, const float *lut, const float *pred,
                   double *sse, int B, int H, int W, int C, int Hp, int Wp, void *stream);
 
+/* Dynamic windows without a host round trip per step (compress.py:214-266 for B chains in lock step; the state lives
+ * in device arrays of B entries).  tz_dwp_gather builds the inputs of the next PredNet step: X[b] =
+ * pad8(f32(frames[key[b]]) / pixel_max) if idx[b] == key[b] + 1 (compress.py:219), else pred_pool[last[b]] (:222).
+ * frames: u8 (bits = 8) or u16 (bits = 16).  tz_dwp_update takes the close decision of :245-263 per chain after
+ * tz_window_sse (sse_step[b] of frame idx[b]): cumulative mean squared error over the window > threshold (or the
+ * static (idx - p) % window == 0 test) -> idx[b] becomes a key (is_key[idx] = 1, pred_slot[idx] = -1), else
+ * pred_slot[idx] = slot0 + b, apply[idx] = 1; idx[b] += 1.  denom = Hp*Wp*C. */
+int tz_dwp_gather(const void *frames, int bits, const float *pred_pool, const int32_t *key, const int32_t *idx,
+                  const int32_t *last, float *X, int B, int H, int W, int C, int Hp, int Wp, void *stream);
+int tz_dwp_update(const double *sse_step, int32_t *key, int32_t *idx, int32_t *last, double *sse, int32_t *cnt,
+                  int32_t *pred_slot, uint8_t *apply, uint8_t *is_key, int B, int slot0, double denom,
+                  int has_threshold, double threshold, int window, int p, void *stream);
+
 /* key-frame plane (compress.py:183,190,220,261): out[f] = is_key[f] ? frames[f] : 0. */
 int tz_key_plane(const uint8_t *frames, const uint8_t *is_key, uint8_t *out, long long nt,
                  long long frame_bytes, void *stream);

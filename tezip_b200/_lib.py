@@ -74,6 +74,9 @@ SIGNATURES = {
     "tz_reconstruct": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tz_window_sse": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "tz_dwp_gather": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "tz_dwp_update": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_int, c_dbl,
+                              c_int, c_int, c_vp]),
     "tz_key_plane": (c_int, [c_vp, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "tz_frames_nonzero": (c_int, [c_vp, c_vp, c_ll, c_ll, c_vp]),
     "tz_memcpy2d_async": (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_ll, c_vp]),

@@ -110,74 +110,59 @@ def run_plan(net, frames, plan, pool):
                 net.next_chained(out)
 
 
-def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None):
+def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None, shard=False):
     """Dynamic-window scheduler (compress.py:214-266 with THRESHOLD): a chain closes its window at frame idx
     when the mean squared error over the padded frames key+1..idx exceeds `threshold`; idx then becomes the
     next key and its prediction is dropped.  n_chains > 1 splits [p, nt) into contiguous sub-ranges that run
     as a batch, each starting with a forced key frame (container-legal; key placement then differs from the
-    sequential reference at the sub-range starts).  Returns (keys, pred_slot, apply_eb, n_slots)."""
+    sequential reference at the sub-range starts); n_chains = 1 is the reference's sequential scan.
+
+    The whole scan runs on the device without a host round trip per step: every chain advances one frame per step
+    whether or not its window closes, so the batch size of every step is known up front; which input a chain reads
+    (key frame or its previous prediction), the close decision and the frame -> slot table are device state
+    (tz_dwp_gather / tz_window_sse / tz_dwp_update).  Returns DEVICE tensors (is_key u8[nt], pred_slot int32[nt],
+    apply u8[nt]) and the number of pool slots used."""
     nt = frames.shape[0]
-    if nt < p + 2:
+    if nt < p + (1 if shard else 2):     # (one rank's part of a longer sequence may be a lone key frame)
         raise TezipError("need at least p+2 frames (the reference crashes otherwise, compress.py:267)")
     dev = frames.device
     Hp, Wp, C = net.frame_shape()
     denom = float(Hp * Wp * C)
     n_chains = max(1, min(int(n_chains), nt - p))
     edges = [p + (nt - p) * c // n_chains for c in range(n_chains + 1)]
-    chains = [{"key": edges[c], "idx": edges[c] + 1, "end": edges[c + 1], "last": -1, "sse": 0.0, "cnt": 0}
-              for c in range(n_chains) if edges[c + 1] > edges[c]]
-    keys = set(range(p)) | {c["key"] for c in chains}
-    pred_slot = np.full(nt, -1, np.int32)
-    apply_eb = np.zeros(nt, np.uint8)
+    spans = [(edges[c], edges[c + 1]) for c in range(n_chains) if edges[c + 1] > edges[c]]
+    spans.sort(key=lambda ab: -(ab[1] - ab[0]))           # stable: the chains still running are always a prefix
+    starts = np.array([a for a, _b in spans], np.int32)
+    lens = np.array([b - a for a, b in spans], np.int64)
+    is_key_np = np.zeros(nt, np.uint8)
+    is_key_np[:p] = 1
+    is_key_np[starts] = 1
+    pred_slot_np = np.full(nt, -1, np.int32)
     if p > 1:
-        pred_slot[1:p] = 0
+        pred_slot_np[1:p] = 0
+    is_key = torch.from_numpy(is_key_np).to(dev)
+    pred_slot = torch.from_numpy(pred_slot_np).to(dev)
+    apply_eb = torch.zeros(nt, dtype=torch.uint8, device=dev)
+    key = torch.from_numpy(starts).to(dev)
+    idx = key + 1
+    last = torch.full_like(key, -1)
+    sse = torch.zeros(len(spans), dtype=torch.float64, device=dev)
+    cnt = torch.zeros(len(spans), dtype=torch.int32, device=dev)
     net.p0(out=pool[0])
-    cursor = 1
     mb = net.max_batch
-    chain_base = None   # pool slot of the first output of the previous step when that step was one next() call
-    while True:
-        act = [c for c in chains if c["idx"] < c["end"]]
-        if not act:
-            break
-        B = len(act)
+    X = torch.empty((len(spans), Hp, Wp, C), dtype=torch.float32, device=dev)
+    cursor = 1
+    for step in range(int(lens.max()) - 1):
+        B = int(np.count_nonzero(lens - 1 > step))
+        ops.dwp_gather(frames, pool, key, idx, last, X, B)                                 # compress.py:219 / :222
         out = pool[cursor:cursor + B]
-        from_key = [i for i, c in enumerate(act) if c["idx"] == c["key"] + 1]
-        from_pred = [i for i, c in enumerate(act) if c["idx"] != c["key"] + 1]
-        # The common step: no window closed last time, so the inputs are exactly the first B predictions of the
-        # previous (single) next() call, in order -> chained step, no gather (compress.py:222)
-        if chain_base is not None and not from_key and B <= mb and \
-                all(c["last"] == chain_base + i for i, c in enumerate(act)):
-            net.next_chained(out)
-        else:
-            X = torch.empty((B, Hp, Wp, C), dtype=torch.float32, device=dev)
-            if from_key:
-                kidx = torch.tensor([act[i]["key"] for i in from_key], dtype=torch.int32, device=dev)
-                X[torch.tensor(from_key, device=dev)] = ops.pad_normalize(frames, kidx, Hp, Wp)   # compress.py:219
-            if from_pred:
-                src = torch.tensor([act[i]["last"] for i in from_pred], device=dev)
-                X[torch.tensor(from_pred, device=dev)] = pool[src]                               # compress.py:222
-            for b0 in range(0, B, mb):
-                net.next(X[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])
-        chain_base = cursor if B <= mb else None
-        fidx = torch.tensor([c["idx"] for c in act], dtype=torch.int32, device=dev)
-        sse = ops.window_sse(frames, fidx, out).cpu().numpy()                               # compress.py:245-246
-        for i, c in enumerate(act):
-            c["sse"] += float(sse[i])
-            c["cnt"] += 1
-            stop_point = c["sse"] / (c["cnt"] * denom)
-            idx = c["idx"]
-            closes = (threshold is not None and stop_point > threshold) or \
-                     (window is not None and (idx - p) % window == 0)                       # compress.py:249
-            if closes:
-                keys.add(idx)                                                               # compress.py:256-263
-                c["key"], c["sse"], c["cnt"], c["last"] = idx, 0.0, 0, -1
-            else:
-                pred_slot[idx] = cursor + i
-                apply_eb[idx] = 1
-                c["last"] = cursor + i
-            c["idx"] = idx + 1
+        for b0 in range(0, B, mb):
+            net.next(X[b0:min(b0 + mb, B)], out=out[b0:min(b0 + mb, B)])                   # compress.py:224-229
+        sse_step = ops.window_sse(frames, idx[:B], out)                                    # compress.py:245-246
+        ops.dwp_update(sse_step, key, idx, last, sse, cnt, pred_slot, apply_eb, is_key, B, cursor, denom, threshold,
+                       window, p)                                                          # compress.py:249-263
         cursor += B
-    return sorted(keys), pred_slot, apply_eb, cursor
+    return is_key, pred_slot, apply_eb, cursor
 
 
 # ------------------------------------------------------------------------------------------------ compress
@@ -248,7 +233,11 @@ def side_stream(device):
 class HostSink:
     """Streams the results of an encode to pinned host buffers while the GPU keeps working: the key plane as soon as
     the schedule is known (before any PredNet step), the int16 stream in chunks as the rank-map kernel produces them.
-    Copies run on a side stream; `finish()` makes the current stream wait for them."""
+    Copies run on a side stream; `finish()` makes the current stream wait for them.
+
+    Key plane: nine frames in ten of it are zero (compress.py:183), so only the KEY FRAMES cross the bus when the
+    schedule is known on the host (static windows): the host plane is zeroed once, and afterwards only frames that
+    were keys of the previous call into the same buffer but are not any more are cleared."""
 
     def __init__(self, key_host, body_host, device, chunks=4, wait_copies=True):
         self.key_host, self.body_host, self.chunks = key_host, body_host, max(1, int(chunks))
@@ -260,10 +249,42 @@ class HostSink:
     def _after_current(self):
         self.stream.wait_event(torch.cuda.current_stream(self.device).record_event())
 
-    def key_plane(self, t):
+    def key_plane(self, t, keys=None):
         self._after_current()
-        with torch.cuda.stream(self.stream):
-            self.key_host.view(-1).copy_(t.view(-1), non_blocking=True)
+        kh = self.key_host
+        if keys is None or not kh.is_pinned() or len(keys) * 2 > t.shape[0]:
+            kh._tz_key_state = None
+            with torch.cuda.stream(self.stream):
+                kh.view(-1).copy_(t.view(-1), non_blocking=True)
+            return
+        nt = t.shape[0]
+        fb = t[0].numel() * t.element_size()
+        ident = (kh.numel() * kh.element_size(), nt)
+        old = getattr(kh, "_tz_key_state", None)     # kept on the caller's tensor object: a new buffer starts clean
+        kview = kh.view(nt, -1)
+        keyset = frozenset(int(k) for k in keys)
+        if old is None or old[0] != ident:
+            kview.zero_()                                   # first use of this buffer: one host memset
+        else:
+            for fidx in old[1] - keyset:
+                kview[fidx].zero_()
+        kh._tz_key_state = (ident, keyset)
+        lib = _lib.load()
+        st = ctypes.c_void_p(self.stream.cuda_stream)
+        ks = sorted(keyset)
+        # runs of equally spaced keys -> one strided DMA each (p, p+W, p+2W, ... is a single run)
+        i = 0
+        while i < len(ks):
+            j = i + 1
+            stride = ks[j] - ks[i] if j < len(ks) else 1
+            while j + 1 < len(ks) and ks[j + 1] - ks[j] == stride:
+                j += 1
+            n_run = j - i + 1 if j < len(ks) else 1
+            off = ks[i] * fb
+            check(lib.tz_memcpy2d_async(ctypes.c_void_p(kh.data_ptr() + off), stride * fb,
+                                        ctypes.c_void_p(t.data_ptr() + off), stride * fb, fb, n_run, st),
+                  "tz_memcpy2d_async")
+            i += n_run
 
     def body_chunk(self, t, a, b):
         self._after_current()
@@ -332,9 +353,16 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         if frames_ready is not None:
             torch.cuda.current_stream(dev).wait_event(frames_ready)
         pool = torch.empty((pool_slots_upper_bound(nt), Hp, Wp, C), dtype=torch.float32, device=dev)
-        keys, pred_slot_np, apply_np, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window)
-    return encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
-                            comm, sink, staged)
+        is_key, pred_slot, apply_dev, _n = run_dwp(net, frames, p, threshold, pool, dwp_chains, window,
+                                                   shard=comm is not None)
+        staged = stage_device(frames, is_key, pred_slot, apply_dev, sink)
+        keys = pred_slot_np = apply_np = None          # read back once, after everything has been queued
+    enc = encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
+                           comm, sink, staged)
+    if keys is None:
+        enc.keys = [int(k) for k in np.nonzero(staged[3][1].numpy())[0]]
+        enc.pred_slot = staged[1].cpu().numpy()
+    return enc
 
 
 def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
@@ -345,23 +373,33 @@ def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
     apply = torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev)
     is_key = np.zeros(nt, np.uint8)
     is_key[list(keys)] = 1
-    key_plane = ops.key_plane(frames, torch.from_numpy(is_key).to(dev))
+    return stage_device(frames, torch.from_numpy(is_key).to(dev), pred_slot, apply, sink, keys_host=sorted(keys))
+
+
+def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
+    """The key plane from a schedule that already lives on the device (is_key u8[nt]).  keys_host: the key list when
+    the host knows it (static windows): the sink then copies only the key frames to the host."""
+    dev = frames.device
+    nt = frames.shape[0]
+    key_plane = ops.key_plane(frames, is_key)
     if sink is not None:
-        sink.key_plane(key_plane)
+        sink.key_plane(key_plane, keys_host)
     # An all-zero key frame (a fade to black) cannot be told from a non-key frame by the decoder
     # (decompress.py:123-127): the reference then silently decodes the wrong window.  The check costs one pass over
-    # the key plane and a tiny asynchronous copy; encode_with_pool looks at the answer once everything is queued.
+    # the key plane and two tiny asynchronous copies; encode_with_pool looks at the answer once everything is queued.
     nz = ops.frames_nonzero(key_plane)
     nz_host = torch.empty(nt, dtype=torch.uint8).pin_memory()
+    ik_host = torch.empty(nt, dtype=torch.uint8).pin_memory()
     nz_host.copy_(nz, non_blocking=True)
-    return pred_slot, apply, key_plane, (nz_host, is_key, torch.cuda.current_stream(dev).record_event())
+    ik_host.copy_(is_key, non_blocking=True)
+    return pred_slot, apply, key_plane, (nz_host, ik_host, torch.cuda.current_stream(dev).record_event())
 
 
 def check_key_frames(staged):
     """Raises if a scheduled key frame is all zero (see stage_plan)."""
-    nz_host, is_key, ev = staged[3]
+    nz_host, ik_host, ev = staged[3]
     ev.synchronize()
-    bad = np.nonzero((nz_host.numpy() == 0) & (is_key != 0))[0]
+    bad = np.nonzero((nz_host.numpy() == 0) & (ik_host.numpy() != 0))[0]
     if bad.size:
         raise TezipError("frame %d is a key frame but all-zero: the container cannot mark it (decompress.py:123-127 "
                          "finds key frames as 'not all-zero'); drop or perturb the frame" % int(bad[0]))
@@ -490,8 +528,9 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
     check_key_frames(staged)
     if sink is not None:
         sink.finish()
-    return Encoded((1, nt, H, W, C), p, list(keys), key_plane, body, table, np.asarray(pred_slot_np),
-                   pool if keep_pool else None, x if keep_x else None)
+    return Encoded((1, nt, H, W, C), p, None if keys is None else list(keys), key_plane, body, table,
+                   None if pred_slot_np is None else np.asarray(pred_slot_np), pool if keep_pool else None,
+                   x if keep_x else None)
 
 
 # ------------------------------------------------------------------------------------------------ decompress

@@ -101,11 +101,13 @@ def load_predictor(WEIGHTS_DIR, max_batch, device=0):
 
 
 def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE, BOUND_VALUE, VERBOSE, ENTROPY_RUN,
-                zstd_workers=0):
-    """compress.run under torchrun (one process per GPU, static windows): every rank decodes and encodes the images
-    of its own window-aligned shard (dist.shard_ranges), the ranks exchange the 1-element delta halo and sum the
-    symbol histogram (dist.ShardComm), rank 0 gathers the streams and writes the single container
-    (SURVEY.md 8(e)).  The container is byte-identical before zstd to the one a single process writes."""
+                zstd_workers=0, THRESHOLD=None, dwp_chains=1):
+    """compress.run under torchrun (one process per GPU): every rank decodes and encodes the images of its own shard,
+    the ranks exchange the 1-element delta halo and sum the symbol histogram (dist.ShardComm), rank 0 gathers the
+    streams and writes the single container.  Static windows (-w): window-aligned shards
+    (dist.shard_ranges); the container is byte-identical before zstd to the one a single process writes.  Dynamic
+    windows (-t): contiguous frame ranges, every range starting with a forced key frame (container-legal: the
+    decoder finds key frames in the key plane), and inside a rank `dwp_chains` sub-ranges run as a batch."""
     import torch.distributed as tdist
     from . import dist as tzdist
     rank, world, local = tzdist.init_from_env()
@@ -113,22 +115,25 @@ def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE
     nt = len(file_paths)
     if nt == 0:
         _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
-    ranges = tzdist.shard_ranges(nt, PREPROCESS, WINDOW_SIZE, world)
+    if THRESHOLD is None:
+        ranges = tzdist.shard_ranges(nt, PREPROCESS, WINDOW_SIZE, world)
+    else:
+        ranges = tzdist.shard_ranges(nt, PREPROCESS, max(1, -(-(nt - PREPROCESS) // world)), world)
     a, b = ranges[rank]
     # every rank evaluates the same layout test, so that they all leave together (a rank that exits alone would leave
     # its peers blocked in the first collective)
     if nt < PREPROCESS + 2 or any(rb <= ra for ra, rb in ranges):
         _die("ERROR: fewer windows than GPUs (or fewer than p+2 frames); use fewer processes")
     frames, files, isRGB = load_images(DATA_DIR, paths=file_paths[a:b])
-    n_win = max(1, (b - a + WINDOW_SIZE - 1) // WINDOW_SIZE)
+    n_win = max(1, (b - a + WINDOW_SIZE - 1) // WINDOW_SIZE) if THRESHOLD is None else max(1, dwp_chains)
     net = load_predictor(WEIGHTS_DIR, max_batch=min(n_win, 256), device=local)
     dev = net.device
     comm = tzdist.ShardComm(device=dev)
     enc, err = None, None
     try:
         enc = codec.encode_frames(torch.from_numpy(frames).to(dev, non_blocking=True), net,
-                                  PREPROCESS if rank == 0 else 0, WINDOW_SIZE, None, MODE, list(BOUND_VALUE),
-                                  ENTROPY_RUN, comm=comm)
+                                  PREPROCESS if rank == 0 else 0, WINDOW_SIZE, THRESHOLD, MODE, list(BOUND_VALUE),
+                                  ENTROPY_RUN, dwp_chains=dwp_chains, comm=comm)
     except TezipError as e:
         err = str(e)
     if not tzdist.all_ok(err is None):      # agree before the stream gather
@@ -156,12 +161,10 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, M
         _die("ERROR: tezip_b200 has no CPU path; a B200 (sm_100) GPU is required.")
     from . import dist as tzdist
     if tzdist.launched_by_torchrun():
-        if THRESHOLD is not None:
-            _die("ERROR: multi-GPU compression shards static windows; use -w (or one process for -t).")
         if not os.path.exists(OUTPUT_DIR):
             os.makedirs(OUTPUT_DIR, exist_ok=True)
         return run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE, BOUND_VALUE, VERBOSE,
-                           ENTROPY_RUN, zstd_workers)
+                           ENTROPY_RUN, zstd_workers, THRESHOLD, dwp_chains)
     if not os.path.exists(OUTPUT_DIR):
         os.mkdir(OUTPUT_DIR)
     frames, files, isRGB = load_images(DATA_DIR)

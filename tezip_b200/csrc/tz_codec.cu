@@ -780,6 +780,70 @@ __global__ void __launch_bounds__(256) frames_nonzero_kernel(const uint8_t *__re
   if (threadIdx.x == 0) nonzero[f] = any ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------ DWP on the device
+// The dynamic-window scheduler (compress.py:214-266) for B chains that advance in lock step, without a host round
+// trip per step: the inputs of the next PredNet step are gathered by chain state (key frame -> normalised + padded,
+// compress.py:219; otherwise the chain's previous prediction, :222), and after the step one thread per chain takes the
+// close decision of :245-263 and updates the state, the key flags and the frame -> pool-slot table.
+template <typename PIX>
+__global__ void __launch_bounds__(256) dwp_gather_kernel(const PIX *__restrict__ frames, const float *__restrict__ pool,
+                                                         const int32_t *__restrict__ key,
+                                                         const int32_t *__restrict__ idx,
+                                                         const int32_t *__restrict__ last, float *__restrict__ X, Geo g,
+                                                         float inv_unused) {
+  const int b = blockIdx.y;
+  const bool from_key = idx[b] == key[b] + 1;
+  float *dst = X + (long long)b * g.pframe_elems;
+  if (from_key) {
+    const PIX *src = frames + (long long)key[b] * g.frame_elems;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)g.pframe_elems; i += gridDim.x * blockDim.x) {
+      const int row = i / g.prow, col = i - row * g.prow;
+      float v = 0.0f;
+      if (row < g.H && col < g.rowlen) {
+        const PIX s = src[(long long)row * g.rowlen + col];
+        // compress.py:138: float32(sample) / pixel maximum (IEEE division == the 256-entry table of tz_pad_normalize)
+        v = sizeof(PIX) == 1 ? __fdiv_rn((float)s, 255.0f) : __fdiv_rn((float)s, 65535.0f);
+      }
+      dst[i] = v;
+    }
+  } else {
+    const float4 *src = reinterpret_cast<const float4 *>(pool + (long long)last[b] * g.pframe_elems);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)(g.pframe_elems >> 2); i += gridDim.x * blockDim.x)
+      d4[i] = src[i];
+  }
+}
+
+__global__ void dwp_update_kernel(const double *__restrict__ sse_step, int32_t *__restrict__ key,
+                                  int32_t *__restrict__ idx, int32_t *__restrict__ last, double *__restrict__ sse,
+                                  int32_t *__restrict__ cnt, int32_t *__restrict__ pred_slot,
+                                  uint8_t *__restrict__ apply, uint8_t *__restrict__ is_key, int B, int slot0,
+                                  double denom, int has_threshold, double threshold, int window, int p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double s = __dadd_rn(sse[b], sse_step[b]);
+  const int c = cnt[b] + 1;
+  const int i = idx[b];
+  const double stop_point = __ddiv_rn(s, __dmul_rn((double)c, denom));                  // compress.py:245-246
+  const bool closes = (has_threshold && stop_point > threshold) || (window > 0 && ((i - p) % window) == 0);   // :249
+  if (closes) {            // :251-263: frame i becomes the next key, its prediction is dropped
+    is_key[i] = 1;
+    key[b] = i;
+    sse[b] = 0.0;
+    cnt[b] = 0;
+    last[b] = -1;
+    pred_slot[i] = -1;
+    apply[i] = 0;
+  } else {
+    pred_slot[i] = slot0 + b;
+    apply[i] = 1;
+    last[b] = slot0 + b;
+    sse[b] = s;
+    cnt[b] = c;
+  }
+  idx[b] = i + 1;
+}
+
 // last residual of a shard: the one-element halo of the 1-D delta across shards (compress.py:75), left on the device
 __global__ void last_residual_kernel(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
                                      const int32_t *__restrict__ slot, Geo g, long long n, int32_t *__restrict__ out) {
@@ -960,6 +1024,37 @@ int tz_window_sse(const uint8_t *frames, const int32_t *frame_idx, const float *
   Geo g = make_geo(H, W, C, Hp, Wp);
   TZ_REQUIRE(g.pframe_elems < 2147483647LL, "tz_window_sse: frame too large");
   window_sse_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(frames, frame_idx, lut, pred, sse, g);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_dwp_gather(const void *frames, int bits, const float *pred_pool, const int32_t *key, const int32_t *idx,
+                  const int32_t *last, float *X, int B, int H, int W, int C, int Hp, int Wp, void *stream) {
+  TZ_REQUIRE(frames && pred_pool && key && idx && last && X && B >= 0 && H > 0 && W > 0 && C > 0 && Hp >= H && Wp >= W &&
+                 (bits == 8 || bits == 16), "tz_dwp_gather: bad arguments");
+  if (B == 0) return TZ_OK;
+  Geo g = make_geo(H, W, C, Hp, Wp);
+  TZ_REQUIRE(g.pframe_elems < 2147483647LL && (g.pframe_elems % 4) == 0 && B <= 65535, "tz_dwp_gather: frame too large");
+  int gx = (int)((g.pframe_elems / 4 + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, B);
+  if (bits == 8)
+    dwp_gather_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)frames, pred_pool, key, idx, last, X, g, 0.f);
+  else
+    dwp_gather_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t *)frames, pred_pool, key, idx, last, X, g, 0.f);
+  TZ_CHECK_LAUNCH();
+  return TZ_OK;
+}
+
+int tz_dwp_update(const double *sse_step, int32_t *key, int32_t *idx, int32_t *last, double *sse, int32_t *cnt,
+                  int32_t *pred_slot, uint8_t *apply, uint8_t *is_key, int B, int slot0, double denom,
+                  int has_threshold, double threshold, int window, int p, void *stream) {
+  TZ_REQUIRE(sse_step && key && idx && last && sse && cnt && pred_slot && apply && is_key && B >= 0 && denom > 0.0,
+             "tz_dwp_update: bad arguments");
+  if (B == 0) return TZ_OK;
+  dwp_update_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sse_step, key, idx, last, sse, cnt, pred_slot, apply,
+                                                                      is_key, B, slot0, denom, has_threshold, threshold,
+                                                                      window, p);
   TZ_CHECK_LAUNCH();
   return TZ_OK;
 }

@@ -317,6 +317,25 @@ def window_sse(frames, frame_idx, pred, out=None):
     return out
 
 
+def dwp_gather(frames, pred_pool, key, idx, last, X, B):
+    """Inputs of the next DWP step for B chains (tz_dwp_gather): X[b] = the normalised, padded key frame of chain b
+    if it has just opened a window (compress.py:219), else its previous prediction pool[last[b]] (compress.py:222)."""
+    _n, H, W, C = frames.shape
+    _s, Hp, Wp, _c = pred_pool.shape
+    check(_lib.load().tz_dwp_gather(ptr(frames), 16 if is_wide(frames) else 8, ptr(pred_pool), ptr(key), ptr(idx),
+                                    ptr(last), ptr(X), int(B), H, W, C, Hp, Wp, _st(frames.device)), "tz_dwp_gather")
+    return X
+
+
+def dwp_update(sse_step, key, idx, last, sse, cnt, pred_slot, apply, is_key, B, slot0, denom, threshold, window, p):
+    """The close decision of compress.py:245-263 for B chains on the device (tz_dwp_update)."""
+    check(_lib.load().tz_dwp_update(ptr(sse_step), ptr(key), ptr(idx), ptr(last), ptr(sse), ptr(cnt), ptr(pred_slot),
+                                    ptr(apply), ptr(is_key), int(B), int(slot0), float(denom),
+                                    0 if threshold is None else 1, 0.0 if threshold is None else float(threshold),
+                                    0 if window is None else int(window), int(p), _st(sse_step.device)),
+          "tz_dwp_update")
+
+
 def key_plane(frames, is_key, out=None):
     n = frames.shape[0]
     fb = frames[0].numel() * frames.element_size()
