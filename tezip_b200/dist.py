@@ -63,13 +63,25 @@ class ShardComm:
         if t is not hist:
             hist.copy_(t)
 
-    def stream_offsets(self, n_local):
+    def stream_offsets_async(self, n_local):
+        """All-gather of the shards' stream lengths, queued without a host synchronisation.  Returns a callable that
+        yields (offsets, sizes) -- offsets = exclusive prefix sum = each shard's position in entropy.dat -- and only
+        then waits for the collective."""
         dev = self.device if self.backend == "nccl" else "cpu"
-        mine = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
-        alln = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(alln, mine, group=self.group)
-        sizes = np.array([int(t.item()) for t in alln], np.int64)
-        return np.concatenate([[0], np.cumsum(sizes)[:-1]]), sizes
+        mine = torch.full((1,), int(n_local), dtype=torch.int64, device=dev)
+        alln = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        if self.backend == "nccl":
+            dist.all_gather_into_tensor(alln, mine, group=self.group)
+        else:
+            alln.copy_(torch.cat(self._gather_list(mine)))
+
+        def result():
+            sizes = alln.cpu().numpy().astype(np.int64)
+            return np.concatenate([[0], np.cumsum(sizes)[:-1]]), sizes
+        return result
+
+    def stream_offsets(self, n_local):
+        return self.stream_offsets_async(n_local)()
 
 
 # ------------------------------------------------------------------------------------------------ file drivers
