@@ -188,14 +188,6 @@ __device__ __forceinline__ void tc2_commit(uint32_t bar) {   // arrives on the s
                : "memory");
 }
 
-// Programmatic dependent launch: every kernel of next() is launched with programmatic stream serialisation, lets its
-// successor start as soon as all of its own CTAs are running (launch_dependents, first instruction) and waits for its
-// predecessor's memory (griddepcontrol.wait) only where it first touches data the predecessor wrote.  A successor CTA
-// becomes resident when a CTA of this grid exits (one CTA per SM), so its barrier init, TMEM allocation, tensor-map
-// fetch and stationary-weight TMA loads run under this grid's tail instead of after it.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ------------------------------------------------------------------------------------------------ kernel arguments
 constexpr int TC_MAX_THREADS = 512;   // 4 role warps (producer, MMA, 2 idle) + up to 12 epilogue warps
 constexpr int TC_MAX_STAGES = 12;
@@ -316,7 +308,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t afull0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1]);   // pair mode: 2 halo slots
   const uint32_t aempty0 = afull0 + 16;
 
-  pdl_launch_dependents();
   constexpr bool two = TWO;                               // CTA-pair mode (launched as clusters of 2)
   uint32_t crank = 0;                                     // 0 = leader (issues the MMAs)
   if constexpr (TWO) crank = cluster_ctarank();
@@ -519,7 +510,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
-      pdl_wait();   // the activations (and, transitively, every buffer the epilogue writes) belong to the predecessor
       for (int t = t_first; t < n_tiles; t += t_step) {
         int mt = fast_div(t, P.m_tiles_n);
         const int nt = t - mt * P.n_tiles_n;
@@ -1186,8 +1176,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(256) e0_tc_kernel(const float *__restrict__ in, const float *__restrict__ p0,
                                                     __half *__restrict__ x0, long long total, long long frame, int C,
                                                     int cstride) {
-  pdl_launch_dependents();
-  pdl_wait();
   long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= total) return;
   int c = (int)(id % C);
@@ -1228,8 +1216,6 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
                                                     int epad) {
   constexpr int TW = 32, TH = 16, PT = TH / 8;   // output pixels per block; a warp is one image row, PT rows per thread
   __shared__ float tile[TH + 2][(TW + 2) * C];
-  pdl_launch_dependents();
-  pdl_wait();
   const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const float *src = r0 + (long long)b * H * W * C;
   // rows of the patch are contiguous in memory ((TW+2)*C floats): consecutive threads read consecutive floats
@@ -1402,7 +1388,6 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   if (epi == 1) {
     A.R = n_real;
     n_unit = largest_divisor_le(n_real, 64);
-    if (const char *env = getenv("TZ_NC_CAP")) n_unit = largest_divisor_le(n_real, atoi(env));   // experiment: N-tile width
   } else {
     n_unit = largest_divisor_le(n_real, 256);
   }
@@ -1763,12 +1748,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (A.pool_cols || A.phase_r) es[1] = es[2] = 2;   // every other pixel of every other row: the box extent stays 18 x 34
-    // a box that takes only part of every pixel's channel row (a0 reads the 32-byte e block of 128-byte X_0 rows)
-    // must not be promoted to 128-byte L2 requests: that fetches the whole row from DRAM (measured: 4x the operand bytes)
-    const bool narrow = (A.KC * 2 < cx * 2) && A.kchunks * A.KC * 2 <= 64 && !(getenv("TZ_L2PROMO") && getenv("TZ_L2PROMO")[0] == '1');
     CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                     narrow ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(A, layer %d) failed: %d", l, (int)r);
@@ -1910,40 +1891,6 @@ void tc_destroy(tz_prednet *h) {
   h->tc = nullptr;
 }
 
-// TZ_PDL=0 launches every kernel of next() with plain stream order (A/B switch for the programmatic dependent launch).
-static bool pdl_enabled() {
-  static const bool on = !(getenv("TZ_PDL") && getenv("TZ_PDL")[0] == '0');
-  return on;
-}
-
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
-                              Args &&...args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (cluster > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = (unsigned)cluster;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    na++;
-  }
-  if (pdl_enabled()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    na++;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = (unsigned)na;
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
-
 static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
   ConvArgs A = c->args;
   A.B = B;
@@ -1962,30 +1909,35 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
     int clusters = T->sm_count / 2;
     if (n_tiles < clusters) clusters = (int)n_tiles;
     grid = 2 * clusters;
-    const dim3 blk(128 + 32 * A.epi_warps);
-    cudaError_t e = (c->epi == 0)
-        ? launch_pdl(conv_tc_kernel<0, true>, dim3(grid), blk, c->smem_bytes, st, 2, c->tmA, c->tmB, c->tmC, A)
-        : launch_pdl(conv_tc_kernel<1, true>, dim3(grid), blk, c->smem_bytes, st, 2, c->tmA, c->tmB, c->tmC, A);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128 + 32 * A.epi_warps);
+    cfg.dynamicSmemBytes = c->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, c->tmC, A)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, c->tmC, A);
     if (e != cudaSuccess) {
       set_error("cluster launch failed: %s", cudaGetErrorString(e));
       return TZ_ECUDA;
     }
-  } else {
-    const dim3 blk(128 + 32 * A.epi_warps);
-    cudaError_t e;
-    if (c->epi == 0)
-      e = A.pool_cols
-              ? launch_pdl(conv_tc_kernel<0, false, true>, dim3(grid), blk, c->smem_bytes, st, 1, c->tmA, c->tmB, c->tmC, A)
-              : launch_pdl(conv_tc_kernel<0, false>, dim3(grid), blk, c->smem_bytes, st, 1, c->tmA, c->tmB, c->tmC, A);
+  } else if (c->epi == 0)
+    if (A.pool_cols)
+      conv_tc_kernel<0, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
     else
-      e = A.phase_r
-              ? launch_pdl(conv_tc_kernel<1, false, false, true>, dim3(grid), blk, c->smem_bytes, st, 1, c->tmA, c->tmB, c->tmC, A)
-              : launch_pdl(conv_tc_kernel<1, false>, dim3(grid), blk, c->smem_bytes, st, 1, c->tmA, c->tmB, c->tmC, A);
-    if (e != cudaSuccess) {
-      set_error("conv launch failed: %s", cudaGetErrorString(e));
-      return TZ_ECUDA;
-    }
-  }
+      conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
+  else
+    if (A.phase_r)
+      conv_tc_kernel<1, false, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
+    else
+      conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
   TZ_CHECK_LAUNCH();
   if (dbg_on) {   // diagnostics only: synchronous
     long long hbuf[256 * 8];
@@ -2016,12 +1968,8 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
   } else {
     const int C = h->S[0];
     long long total = (long long)B * h->H[0] * h->W[0] * C;
-    cudaError_t e = launch_pdl(e0_tc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, 1, in,
-                               (const float *)h->Ahat0[0], T->X[0], total, (long long)h->H[0] * h->W[0] * C, C, T->cx[0]);
-    if (e != cudaSuccess) {
-      set_error("e0 launch failed: %s", cudaGetErrorString(e));
-      return TZ_ECUDA;
-    }
+    e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], T->X[0], total,
+                                                                 (long long)h->H[0] * h->W[0] * C, C, T->cx[0]);
     TZ_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[ne++], st);
   }
@@ -2042,20 +1990,14 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
       Ahat0W<3> wb;
       memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
       memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
-      if (launch_pdl(ahat0_kernel<3>, grid, dim3(256), 0, st, 1, (const float *)T->r0, wb, out, h->H[0], h->W[0],
-                     h->cfg.pixel_max, (const float *)h->Ahat0[0], T->X[0], T->cx[0], T->epad[0]) != cudaSuccess) {
-        set_error("ahat0 launch failed");
-        return TZ_ECUDA;
-      }
+      ahat0_kernel<3><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
+                                            T->cx[0], T->epad[0]);
     } else {
       Ahat0W<1> wb;
       memcpy(wb.w, T->ahat0_w, sizeof(wb.w));
       memcpy(wb.b, T->ahat0_b, sizeof(wb.b));
-      if (launch_pdl(ahat0_kernel<1>, grid, dim3(256), 0, st, 1, (const float *)T->r0, wb, out, h->H[0], h->W[0],
-                     h->cfg.pixel_max, (const float *)h->Ahat0[0], T->X[0], T->cx[0], T->epad[0]) != cudaSuccess) {
-        set_error("ahat0 launch failed");
-        return TZ_ECUDA;
-      }
+      ahat0_kernel<1><<<grid, 256, 0, st>>>(T->r0, wb, out, h->H[0], h->W[0], h->cfg.pixel_max, h->Ahat0[0], T->X[0],
+                                            T->cx[0], T->epad[0]);
     }
     TZ_CHECK_LAUNCH();
     h->x0_staged = true;
