@@ -222,9 +222,11 @@ def pack_payload(body, table, shape, p):
 _SIDE_STREAMS = {}
 
 
-def side_stream(device):
-    """One cached copy stream per device (creating streams per call costs more than the copies it hides)."""
-    key = str(device)
+def side_stream(device, kind="out"):
+    """Cached copy streams per device (creating streams per call costs more than the copies it hides): one for
+    device->host results ("out") and one for host->device inputs ("in"), so that the upload of the NEXT sequence never
+    queues behind the download of the previous one when calls are pipelined."""
+    key = (str(device), kind)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -310,6 +312,19 @@ def _host_scratch(device, wide=False):
     return _HOST_SCRATCH[key]
 
 
+_FLAG_SCRATCH = {}
+
+
+def _flag_scratch(device, nt):
+    """Two pinned u8[nt] landing buffers per device (allocating pinned memory per call costs a cudaHostAlloc, which
+    also serialises with collectives in flight)."""
+    key = str(device)
+    cur = _FLAG_SCRATCH.get(key)
+    if cur is None or cur.shape[1] < nt:
+        cur = _FLAG_SCRATCH[key] = torch.empty((2, max(nt, 1024)), dtype=torch.uint8).pin_memory()
+    return cur[0, :nt], cur[1, :nt]
+
+
 def is_lossless(mode, bound):
     """compress.py:24,35: BOUND_VALUE[0] == 0 (or absrel with BOUND_VALUE[1] == 0) leaves diff untouched."""
     return float(bound[0]) == 0.0 or (mode == "absrel" and float(bound[1]) == 0.0)
@@ -388,8 +403,7 @@ def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
     # (decompress.py:123-127): the reference then silently decodes the wrong window.  The check costs one pass over
     # the key plane and two tiny asynchronous copies; encode_with_pool looks at the answer once everything is queued.
     nz = ops.frames_nonzero(key_plane)
-    nz_host = torch.empty(nt, dtype=torch.uint8).pin_memory()
-    ik_host = torch.empty(nt, dtype=torch.uint8).pin_memory()
+    nz_host, ik_host = _flag_scratch(dev, nt)     # cached pinned buffers: consumed by check_key_frames() in this call
     nz_host.copy_(nz, non_blocking=True)
     ik_host.copy_(is_key, non_blocking=True)
     return pred_slot, apply, key_plane, (nz_host, ik_host, torch.cuda.current_stream(dev).record_event())
@@ -641,7 +655,7 @@ def upload_frames(frames_host, dev, p, window, threshold):
                                     height, ctypes.c_void_p(stream.cuda_stream)), "tz_memcpy2d_async")
 
     copy2d(0, fb, n_full + (1 if rem else 0), main)                 # first frame of every window
-    side = side_stream(dev)
+    side = side_stream(dev, "in")
     side.wait_event(main.record_event())                            # `frames` may reuse memory the main stream still reads
     copy2d(fb, (window - 1) * fb, n_full, side)                     # frames 1..window-1 of the full windows
     if rem > 1:
@@ -656,7 +670,7 @@ def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, firs
     main = torch.cuda.current_stream(dev)
     key_plane = key_host.to(dev, non_blocking=True)
     body = torch.empty(body_host.numel(), dtype=body_host.dtype, device=dev)   # allocated on the main stream's pool
-    side = side_stream(dev)
+    side = side_stream(dev, "in")
     side.wait_event(main.record_event())      # after the key plane copy (same copy engine) and any earlier use of `body`
     with torch.cuda.stream(side):
         body.copy_(body_host, non_blocking=True)

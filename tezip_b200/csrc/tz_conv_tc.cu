@@ -18,7 +18,6 @@
 // Determinism: one kernel configuration per layer, no split-K, no atomics; each output element is a fixed-order
 // sum over K inside the tensor core, independent of batch size, tile position and grid size.
 #include "tz_prednet.cuh"
-#include <type_traits>
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -26,9 +25,6 @@
 
 #ifndef TZ_EPI_DEBUG
 #define TZ_EPI_DEBUG 0
-#endif
-#ifndef TZ_PHASE_PROTO
-#define TZ_PHASE_PROTO 0
 #endif
 
 namespace tz {
@@ -209,21 +205,8 @@ struct ConvArgs {
                                  // so G epilogues are in flight and their latency overlaps
   int acc_stages, acc_stride;    // TMEM accumulator ring: stages, columns per stage
   int mma_issuers;               // halo + stationary weights: 2 warps issue the MMAs of alternate tiles, else 1
-  int pool_cols;                 // A path, halo + stationary weights: the four pixels of a 2x2 pooling window are
-                                 // four COLUMN groups of one accumulator row (tile = 8x16 POOLED pixels), see make_conv
-  uint32_t desc_hi_pc;           // pool_cols: high word of the A descriptors (groups one sub-box row of 9 pixels apart)
-  uint32_t pc_slot;              // pool_cols: bytes per parity sub-box slot inside a stage
-  // phase_r (R path, layer with an up-sampled input): the accumulator holds four column groups, one per output-pixel
-  // parity; the e block is gathered by parity as in pool_cols, the up(r_{l+1}) block is read from the LOW-resolution
-  // r_{l+1} with 2x2 taps whose weights are the sums of the 3x3 taps that fall on the same low-resolution pixel
-  int phase_r, r_chunks;         // r_chunks = R_{l+1} / 16
-  int kblocks_total;             // stationary K16 weight blocks: 9 (e taps) + 4 phases * 4 taps * r_chunks
-  uint32_t pr_slot, desc_hi_pr;  // bytes per low-resolution chunk box (18 rows x 10 pixels x 16 ch) / its descriptor
-  __half *rl_out;                // if set: r is ALSO written at its own resolution, [B, H, W, rl_cstride] fp16
-  int rl_cstride;
-  int halo;                      // 1: halo + stationary-weights mode; 2: halo pair mode (see conv_tc_kernel)
-  int sub_tiles, tile_h;         // M tiles per scheduled tile (2 in pair mode) and its height in pixels
-  int sub_stride;                // TMEM columns between the accumulators of the two M tiles of a pair
+  int halo;                      // 0: im2col; 1: halo + stationary weights; 4: CTA pair + halo (see conv_tc_kernel)
+  int tile_h;                    // tile height in pixels
   uint32_t a_slot, a_tx;         // pair mode: bytes of one halo slot (1024-aligned) and of the TMA box
   uint32_t b_block, b_region;    // halo mode: bytes of one [n_tile x 64] weight block; bytes of all 9*kchunks blocks
   uint32_t a_stride, stage_stride, tx_bytes;
@@ -286,13 +269,9 @@ __device__ __forceinline__ void issue_halo_chunk(uint32_t d_tmem, uint32_t a_lo,
 // ------------------------------------------------------------------------------------------------ the kernel
 // TWO = CTA-pair instantiation (launched as clusters of 2): kernels that contain cta_group::2 instructions can only
 // be launched with a matching cluster size, so the one-CTA modes use the TWO = false instantiation.
-// POOLC = the pooling-in-accumulator-columns variant of the one-CTA A path (its own instantiation: its epilogue
-// keeps prefetched Ahat0 values live across the accumulator wait, which the other variants have no registers for).
-// PHASE = the parity-phase variant of the one-CTA R path (see ConvArgs::phase_r); tmC is its low-resolution map.
-template <int EPI, bool TWO, bool POOLC = false, bool PHASE = false>  // EPI 0: A path (pool + E), 1: R path (LSTM)
+template <int EPI, bool TWO>  // EPI 0: A path (pool + E), 1: R path (LSTM)
 __global__ void __launch_bounds__(TC_MAX_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const ConvArgs P) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1 + 4];
   __shared__ uint32_t tmem_base_s;
@@ -318,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = two ? ((tiles_img * tiles_b + 1) >> 1) * P.n_tiles_n : tiles_img * tiles_b * P.n_tiles_n;
   const int t_first = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int kblocks = PHASE ? P.kblocks_total : 9 * P.kchunks;
+  const int kblocks = 9 * P.kchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; s++) {
@@ -399,76 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t b_lo = (((smem0 + ch * P.b_block) >> 4) & 0x3FFFu) | (1u << 16);
-        if (PHASE) {
-          if (elect_one()) {
-            const uint32_t slot16 = P.pc_slot >> 4, rslot16 = P.pr_slot >> 4, bb16 = P.b_block >> 4;
-            const uint32_t r_lo = a_lo + 4u * slot16;
-            // straight-line issue (the issue loop's scalar work is what bounds narrow MMAs): everything below unrolls
-            // to MMAs whose descriptor offsets are sums of loop-invariant values; NRC is the usual R_{l+1} / 16
-            auto issue_all = [&](auto nrc_tag) {
-              constexpr uint32_t NRC = decltype(nrc_tag)::value;
-              const uint32_t nrc = NRC ? NRC : (uint32_t)P.r_chunks;
-#pragma unroll
-              for (uint32_t pp = 0; pp < 4; pp++) {   // output parity (qy, qx) -> column group pp
-                const uint32_t dcol = d_tmem + pp * (uint32_t)P.n_tile;
-                const uint32_t qy = pp >> 1, qx = pp & 1u;
-#pragma unroll
-                for (int tap = 0; tap < 9; tap++) {   // e block: 3x3 taps on the parity sub-boxes
-                  const uint32_t q = qy + (uint32_t)(tap / 3), o = qx + (uint32_t)(tap % 3);
-                  const uint32_t sb = (((q + 1u) & 1u) << 1) | ((o + 1u) & 1u);
-                  const uint32_t al = a_lo + sb * slot16 + ((q >> 1) * 9u + (o >> 1)) * 2u;
-                  tc_mma_f16(dcol, make_desc(al, P.desc_hi_pc), make_desc(b_lo + (uint32_t)tap * bb16, hi), idesc, tap != 0);
-                }
-#pragma unroll
-                for (int t4 = 0; t4 < 4; t4++) {      // r block: 2x2 taps on the low-resolution boxes
-                  const uint32_t off = ((qy + (uint32_t)(t4 >> 1)) * 10u + qx + (uint32_t)(t4 & 1)) * 2u;
-#pragma unroll
-                  for (uint32_t c = 0; c < (NRC ? NRC : 1u); c++) {
-                    if (NRC) {
-                      tc_mma_f16(dcol, make_desc(r_lo + c * rslot16 + off, P.desc_hi_pr),
-                                 make_desc(b_lo + (9u + (pp * 4u + (uint32_t)t4) * NRC + c) * bb16, hi), idesc, 1);
-                    } else {
-                      for (uint32_t cc = 0; cc < nrc; cc++)
-                        tc_mma_f16(dcol, make_desc(r_lo + cc * rslot16 + off, P.desc_hi_pr),
-                                   make_desc(b_lo + (9u + (pp * 4u + (uint32_t)t4) * nrc + cc) * bb16, hi), idesc, 1);
-                    }
-                  }
-                }
-              }
-            };
-            if (P.r_chunks == 3) issue_all(std::integral_constant<uint32_t, 3>{});
-            else issue_all(std::integral_constant<uint32_t, 0>{});
-            tc_commit(empty0 + 8 * s);
-            tc_commit(tfull0 + 8 * a);
-          }
-        } else if (POOLC) {
-          if (elect_one()) {
-            // 4 window positions x 9 taps (x ksteps): A starts at box pixel (py+dy+1, px+dx+1) = (q, o)
-            const uint32_t pix16 = rowb >> 4, ks = (uint32_t)P.ksteps;
-            const uint32_t slot16 = P.pc_slot >> 4;
-#pragma unroll
-            for (int pp = 0; pp < 4; pp++) {   // straight-line: 36 * ksteps MMAs, offsets are small multiples of two values
-              const uint32_t dcol = d_tmem + (uint32_t)pp * (uint32_t)P.n_tile;
-#pragma unroll
-              for (int tap = 0; tap < 9; tap++) {
-                // q = py + dy + 1, o = px + dx + 1 in 0..3: odd sub-box for q = 0, 2, shift one row for q >= 2
-                const uint32_t q = (uint32_t)((pp >> 1) + tap / 3), o = (uint32_t)((pp & 1) + tap % 3);
-                const uint32_t sb = (((q + 1u) & 1u) << 1) | ((o + 1u) & 1u);
-                const uint32_t al = a_lo + sb * slot16 + ((q >> 1) * 9u + (o >> 1)) * pix16;
-                const uint32_t bl = b_lo + (uint32_t)tap * btap16;
-                if (ks == 1) {
-                  tc_mma_f16(dcol, make_desc(al, P.desc_hi_pc), make_desc(bl, hi), idesc, tap != 0 || ch != 0);
-                } else {
-                  for (uint32_t k = 0; k < ks; k++)
-                    tc_mma_f16(dcol, make_desc(al + 2 * k, P.desc_hi_pc), make_desc(bl + 2 * k, hi), idesc,
-                               (tap | (int)k) != 0 || ch != 0);
-                }
-              }
-            }
-            tc_commit(empty0 + 8 * s);
-            if (ch + 1 == kch) tc_commit(tfull0 + 8 * a);
-          }
-        } else if (elect_one()) {
+        if (elect_one()) {
           if (P.ksteps == 4)
             issue_halo_chunk<4>(d_tmem, a_lo, ahi_halo, b_lo, hi, rowb >> 4, btap16, idesc, ch == 0);
           else if (P.ksteps == 2)
@@ -570,61 +480,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
         } else if (P.halo == 1) {
           // halo mode: per chunk ONE box of (TH+2) x 16 pixels; the nine taps read it through shifted descriptors
-          if (PHASE) {   // one stage per region: 4 parity sub-boxes of e + r_chunks low-resolution boxes of r_{l+1}
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            if (elect_one()) {
-              const uint32_t full = full0 + 8 * s;
-              mbar_expect_tx(full, P.tx_bytes);
-              const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
-#pragma unroll
-              for (int sb = 0; sb < 4; sb++)
-                tma_load_4d(sa + (uint32_t)sb * P.pc_slot, &tmA, full, 0, 2 * w0 - (sb & 1), 2 * h0 - (sb >> 1), b0);
-              for (int c = 0; c < P.r_chunks; c++)
-                tma_load_4d(sa + 4u * P.pc_slot + (uint32_t)c * P.pr_slot, &tmC, full, 16 * c, w0 - 1, h0 - 1, b0);
-            }
-            __syncwarp();
-            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-          } else
           for (int c = 0; c < P.cin_pad; c += P.KC) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
             if (elect_one()) {
               const uint32_t full = full0 + 8 * s;
               mbar_expect_tx(full, P.tx_bytes);
-              if (POOLC) {   // sub-box (by, bx): rows 2*h0 - by + 2j, pixels 2*w0 - bx + 2i
-                const uint32_t sa = smem0 + P.b_region + s * P.stage_stride;
-#pragma unroll
-                for (int sb = 0; sb < 4; sb++)
-                  tma_load_4d(sa + (uint32_t)sb * P.pc_slot, &tmA, full, c, 2 * w0 - (sb & 1), 2 * h0 - (sb >> 1), b0);
-              } else
-                tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
+              tma_load_4d(smem0 + P.b_region + s * P.stage_stride, &tmA, full, c, w0 - 1, h0 - 1, b0);
             }
             __syncwarp();
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-          }
-        } else {
-          // halo pair mode (large weight matrices): per 64-channel chunk ONE halo box of 34 image rows x 10 pixels
-          // feeds two stacked 8x16 M tiles for all nine taps, and every streamed [N_tile x 64] weight block is
-          // used by both M tiles before it is released
-          int kc = 0;
-          for (int c = 0; c < P.cin_pad; c += 64, kc += 64) {
-            mbar_wait(aempty0 + 8 * sl, pha ^ 1u);
-            if (elect_one()) {
-              mbar_expect_tx(afull0 + 8 * sl, P.a_tx);
-              tma_load_4d(smem0 + sl * P.a_slot, &tmA, afull0 + 8 * sl, c, w0 - 1, h0 - 1, b0);
-            }
-            __syncwarp();
-            sl ^= 1u;
-            pha ^= (sl == 0);
-            int kcoord = kc;
-            for (int tap = 0; tap < 9; tap++, kcoord += P.cin_pad) {
-              mbar_wait(empty0 + 8 * s, ph ^ 1u);
-              if (elect_one()) {
-                mbar_expect_tx(full0 + 8 * s, P.tx_bytes);
-                tma_load_2d(pair_bbase + s * P.stage_stride, &tmB, full0 + 8 * s, kcoord, n0);
-              }
-              __syncwarp();
-              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-            }
           }
         }
         }   // one-CTA modes
@@ -646,7 +510,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // function of the absolute shared-memory address bits (what TMA wrote), and the descriptor base_offset stays 0
       // -- measured on B200: base_offset = dx gives wrong results, 0 matches the im2col path to rounding.
       const uint32_t ahi_pair = ((1280u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);
-      const uint32_t ahi_pair32 = ((640u >> 4) & 0x3FFFu) | (hi & 0xFFFFC000u);   // 10 pixels of 64 B
       const uint32_t pair_bbase = smem0 + 2 * P.a_slot;
       long long w_tempty = 0, w_full = 0, w_afull = 0, c0 = 0, t_start = 0;
       const bool dbg = P.dbg != nullptr && lane == 0;
@@ -675,26 +538,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_fence_after();
               const uint32_t b_base = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
               if (elect_one()) {
-                if (P.ksteps == 4) {   // 64-channel chunks: 128-byte pixels
 #pragma unroll
-                  for (int j = 0; j < 3; j++) {
-                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
-                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+                for (int j = 0; j < 3; j++) {   // 64-channel chunks: 128-byte pixels
+                  const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                  const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
-                                  acc | (uint32_t)(tg | j | k));
-                  }
-                } else {               // 32-channel chunks (channel counts that are multiples of 32 only): 64-byte pixels
-#pragma unroll
-                  for (int j = 0; j < 3; j++) {
-                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 4u;
-                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
-#pragma unroll
-                    for (int k = 0; k < 2; k++)
-                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair32), make_desc(b_lo + 2 * k, hi), idesc,
-                                  acc | (uint32_t)(tg | j | k));
-                  }
+                  for (int k = 0; k < 4; k++)
+                    tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                                acc | (uint32_t)(tg | j | k));
                 }
                 tc2_commit(empty0 + 8 * s);
               }
@@ -737,40 +588,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             acc = 1;
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-          }
-        } else {
-          uint32_t acc = 0;
-          for (int ch = 0; ch < P.kchunks; ch++) {
-            if (dbg) c0 = clock64();
-            mbar_wait(afull0 + 8 * sl, pha);
-            if (dbg) w_afull += clock64() - c0;
-            tc_fence_after();
-            const uint32_t a_base = (((smem0 + sl * P.a_slot) >> 4) & 0x3FFFu) | (1u << 16);
-#pragma unroll
-            for (int tap = 0; tap < 9; tap++) {
-              if (dbg) c0 = clock64();
-              mbar_wait(full0 + 8 * s, ph);
-              if (dbg) w_full += clock64() - c0;
-              tc_fence_after();
-              const uint32_t a_lo = a_base + (uint32_t)((tap / 3) * 10 + (tap % 3)) * 8u;   // 128 B per halo pixel
-              const uint32_t b_lo = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
-              if (elect_one()) {
-#pragma unroll
-                for (int sub = 0; sub < 2; sub++)   // second M tile: 16 image rows = 20480 bytes further down the halo
-#pragma unroll
-                  for (int k = 0; k < 4; k++)
-                    tc_mma_f16(d_tmem + sub * (uint32_t)P.sub_stride, make_desc(a_lo + sub * 1280 + 2 * k, ahi_pair),
-                               make_desc(b_lo + 2 * k, hi), idesc, acc | (uint32_t)(tap | k));
-                tc_commit(empty0 + 8 * s);
-              }
-              __syncwarp();
-              if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
-            }
-            acc = 1;
-            if (elect_one()) tc_commit(aempty0 + 8 * sl);
-            __syncwarp();
-            sl ^= 1u;
-            pha ^= (sl == 0);
           }
         }
         if (elect_one()) tc_commit(tfull0 + 8 * a);    // accumulator complete
@@ -825,19 +642,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tbi = fast_div(mq, P.m_tiles_h);
       const int thi = mq - tbi * P.tiles_h;
       const int w_tile = (twi << P.tw_log) + tw, b = (tbi << P.tb_log) + tb;
-      // pool_cols: Ahat0 of this lane's pooled pixel for the first two of this warp's chunks is requested BEFORE
-      // waiting for the accumulator: its L2 latency (~1000 cycles) then hides behind the MMAs of the tile
-      float alp[POOLC ? 2 : 1][8];
-      if (EPI == 0 && POOLC) {
-        const int hp = thi * P.tile_h + th;
-        if ((b < P.B) && (2 * hp < P.H) && (2 * w_tile < P.W)) {
-          const float *ahp = P.ahat_next + ((long long)hp * (P.W >> 1) + w_tile) * P.S_next + nt * P.n_tile;
-          const int nr = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
-#pragma unroll
-          for (int c = 0; c < 2; c++)
-            if (8 * (part + c * nparts) < nr) ldg256(ahp + 8 * (part + c * nparts), alp[c]);
-        }
-      }
       if (edbg) ec0 = clock64();
       mbar_wait(tfull0 + 8 * a, aph);
       if (edbg) {
@@ -847,56 +651,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         e_tiles++;
       }
       tc_fence_after();
-      for (int sub = 0; sub < P.sub_tiles; sub++) {
-      // PHASE: column group `sub` holds the output pixels of parity (sub >> 1, sub & 1) of the region
-      const int h = PHASE ? 2 * (thi * P.tile_h + th) + (sub >> 1) : thi * P.tile_h + (sub << P.th_log) + th;
-      const int w = PHASE ? 2 * w_tile + (sub & 1) : w_tile;
-      const bool valid = POOLC ? (b < P.B) && (2 * h < P.H) && (2 * w < P.W) : (b < P.B) && (h < P.H) && (w < P.W);
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride +
-                            sub * (uint32_t)P.sub_stride;
-      if (EPI == 0 && POOLC) {
-        // (w, h) are POOLED coordinates here.  a = relu(max over the four column groups + bias); e = [relu(ahat - a),
-        // relu(a - ahat)]: 32 contiguous bytes per lane, no cross-lane traffic.
-        const int Ho = P.H >> 1, Wo = P.W >> 1;
-        const long long opix = ((long long)b * Ho + h) * Wo + w;
-        const float *ah = P.ahat_next + ((long long)h * Wo + w) * P.S_next;
-        __half *dst = P.xe_out + opix * P.xe_cstride;
-        const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
-        auto pchunk = [&](int j0, const float *al) {
-          const int ch0 = nt * P.n_tile + j0;
-          float mx[8], v1[8], v2[8], v3[8];
-          tc_ld8(trow + 0 * P.n_tile + j0, mx);
-          tc_ld8(trow + 1 * P.n_tile + j0, v1);
-          tc_ld8(trow + 2 * P.n_tile + j0, v2);
-          tc_ld8(trow + 3 * P.n_tile + j0, v3);
-          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.bias + ch0));
-          const float4 b1 = __ldg(reinterpret_cast<const float4 *>(P.bias + ch0 + 4));
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          tc_ld_wait();
-          if (valid) {
-            __align__(16) __half up[8], dn[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float m4 = fmaxf(fmaxf(mx[j], v1[j]), fmaxf(v2[j], v3[j]));
-              const float a_ = fmaxf(__fadd_rn(m4, bb[j]), 0.0f);
-              up[j] = __float2half_rn(fmaxf(__fsub_rn(al[j], a_), 0.0f));
-              dn[j] = __float2half_rn(fmaxf(__fsub_rn(a_, al[j]), 0.0f));
-            }
-            *reinterpret_cast<uint4 *>(dst + ch0) = *reinterpret_cast<const uint4 *>(up);
-            *reinterpret_cast<uint4 *>(dst + P.S_next + ch0) = *reinterpret_cast<const uint4 *>(dn);
-          }
-        };
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int j0 = 8 * (part + c * nparts);
-          if (j0 < n_real) pchunk(j0, alp[c]);
-        }
-        for (int j0 = 8 * (part + 2 * nparts); j0 < n_real; j0 += 8 * nparts) {   // more than two chunks per warp
-          float al[8];
-          if (valid) ldg256(ah + nt * P.n_tile + j0, al);
-          pchunk(j0, al);
-        }
-      } else if (EPI == 0) {
+      const int h = thi * P.tile_h + th;
+      const int w = w_tile;
+      const bool valid = (b < P.B) && (h < P.H) && (w < P.W);
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + a * (uint32_t)P.acc_stride;
+      if (EPI == 0) {
         // a = maxpool2x2(relu(conv + bias));  e = [relu(ahat - a), relu(a - ahat)]  -> fp16 into X_{l+1}
         const int Ho = P.H >> 1, Wo = P.W >> 1;
         const bool writer = valid && ((tw & 1) == 0) && ((th & 1) == 0);
@@ -1099,19 +858,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool second = jp + 8 < P.NC;
           lstm_chunk(jp, hv);
           if (second) lstm_chunk(jp + 8, hv + 8);
-#if TZ_PHASE_PROTO   // prototype builds only (TZ_NVCC_FLAGS=-DTZ_PHASE_PROTO=1): the default LSTM epilogue has no registers to spare
-          if (valid && P.rl_out) {   // r at its own resolution, for a phase_r consumer
-            __half *dl = P.rl_out + (((long long)b * P.H + h) * P.W + w) * P.rl_cstride + nt * P.NC + jp;
-            if ((jp + 16 <= P.NC) && ((P.rl_cstride | (nt * P.NC + jp)) & 15) == 0) {
-              const uint4 lo = *reinterpret_cast<const uint4 *>(hv), hi4 = *reinterpret_cast<const uint4 *>(hv + 8);
-              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dl), "r"(lo.x), "r"(lo.y),
-                           "r"(lo.z), "r"(lo.w), "r"(hi4.x), "r"(hi4.y), "r"(hi4.z), "r"(hi4.w)
-                           : "memory");
-            } else {
-              for (int j = 0; j < 16 && jp + j < P.NC; j++) dl[j] = hv[j];
-            }
-          }
-#endif
           if (valid && P.xr_out) {
             // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
             const int H2 = P.H * 2, W2 = P.W * 2;
@@ -1140,7 +886,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      }   // sub tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1286,7 +1031,7 @@ __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restr
 
 // ------------------------------------------------------------------------------------------------ host side
 struct ConvTc {
-  CUtensorMap tmA, tmB, tmC;   // tmC: low-resolution r map of the phase_r variant (a copy of tmA otherwise)
+  CUtensorMap tmA, tmB;
   ConvArgs args;
   int epi;
   uint32_t smem_bytes;
@@ -1304,7 +1049,6 @@ struct TcState {
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
   int sm_count;
-  __half *RL1;                // r_1 at its own resolution (phase_r prototype), else nullptr
   float ahat0_w[9 * 3 * 3], ahat0_b[3];   // host copy of the layer-0 A-hat kernel (C = R_0 = S_0 <= 3), passed by value
 };
 
@@ -1355,12 +1099,9 @@ static void pick_tile(int H, int W, bool pool, int *tw_log, int *th_log, int *tb
 
 // cmap[i] = input-channel row of the fp32 kernel that multiplies channel i of the activation buffer X (-1: none,
 // the packed weight is zero).  The conv reads channels [0, round_up(cmap.size(), 16)) of X.
-// rmap/RL: phase_r request -- rmap[i] = row of wsrc that multiplies channel i of up(r_{l+1}), RL = the tensor that
-// holds r_{l+1} at its own resolution ([maxB, H/2, W/2, rmap.size()] fp16); cmap then covers the e block only.
 static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx, const std::vector<int> &cmap,
                      const std::vector<float> &wsrc /*fp32 [3][3][cin_w][cout_w]*/, int cin_w, int cout_w,
-                     int n_real /*output channels or R*/, const std::vector<int> *rmap = nullptr,
-                     __half *RL = nullptr) {
+                     int n_real /*output channels or R*/) {
   const int cin_real = (int)cmap.size();
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -1391,32 +1132,21 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   } else {
     n_unit = largest_divisor_le(n_real, 256);
   }
-  // ---- experiment (TZ_HALO=5): CTA-pair mode also for the small-weight convs (channels rounded up to 64)
+  // A/B switch, read at create time: TZ_HALO=0 im2col feeding only, TZ_HALO=1 no CTA pairs.
+  const char *halo_env = getenv("TZ_HALO");
+  // ---- A-path convs whose stationary weights would need more than the 112 KB that leave room for four halo stages
+  // (a1 of the (3,48,96,192) net: 166 KB) run faster as a CTA pair with streamed weights, even with the input
+  // channels rounded up to 64 (measured: 0.080 vs 0.086 ms); smaller ones do not (a0 0.158 vs 0.101 ms).
   {
-    const char *env = getenv("TZ_HALO");
     const int c64 = round_up(cin_real, 64);
-    const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
-    // A-path convs whose stationary weights would need more than the 112 KB that leave room for four halo stages
-    // (a1 of the (3,48,96,192) net: 166 KB) run faster as a CTA pair with streamed weights, even with the input
-    // channels rounded up to 64 (measured: 0.080 vs 0.086 ms); smaller ones do not (a0 0.158 vs 0.101 ms).
-    const bool big_a = epi == 0 && !env && (size_t)ntile_c * 9u * (size_t)A.cin_pad * 2u > 112u * 1024u;
-    if (((env && env[0] == '5') || big_a) && c64 <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
-        (ntile_c % 16) == 0) {
+    const int ntile_c = round_up(n_unit, 16);
+    const bool big_a = epi == 0 && !halo_env && (size_t)ntile_c * 9u * (size_t)A.cin_pad * 2u > 112u * 1024u;
+    if (big_a && c64 <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256) {
       A.halo = 4;
-      if ((cin_real % 32) == 0 && (cin_real % 64) != 0 && getenv("TZ_PAIR_KC32")) {
-        // Experiment: 32-channel chunks instead of rounding the channels up to 64.  a1 (96 channels) then issues 54
-        // instead of 72 M256 MMAs per tile, but runs SLOWER (0.101 vs 0.082 ms): three chunks mean twelve barrier
-        // round trips per tile instead of eight, each weight stage carrying only ~300 cycles of MMAs.
-        A.cin_pad = cin_real;
-        A.KC = 32;
-        A.kchunks = cin_real / 32;
-        A.ksteps = 2;
-      } else {
       A.cin_pad = c64;
       A.KC = 64;
       A.kchunks = c64 / 64;
       A.ksteps = 4;
-      }
       A.tw_log = 3;
       A.th_log = 4;
       A.tb_log = 0;
@@ -1427,14 +1157,12 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   // ---- halo + stationary-weights mode: small weight matrices only (they must fit in shared memory next to the
   // halo tiles), image width a multiple of the 8-pixel tile width.
   if (!A.halo) {
-    const char *env = getenv("TZ_HALO");
-    const bool want = !(env && env[0] == '0');
+    const bool want = !(halo_env && halo_env[0] == '0');
     const int cin64 = A.cin_pad;            // channels read: cin rounded up to 16, walked in chunks of KC
     // Stationary weights may take what two halo stages leave free: one wide N tile halves the MMA count of a split
     // one (measured, a1 of the (3,48,96,192) net: N = 96 in one tile 0.098 ms, two tiles of 48 0.129 ms).
-    const char *envb = getenv("TZ_WBUDGET_KB");   // experiment: cap of the stationary weights in KB
     const uint32_t halo_stage = (16u * 18u * 2u * (uint32_t)A.KC + 1023u) & ~1023u;
-    const uint32_t budget = envb ? (uint32_t)atoi(envb) * 1024u : 224u * 1024u - 2u * halo_stage;
+    const uint32_t budget = 224u * 1024u - 2u * halo_stage;
     if (want && cin64 <= cx && (A.W % 8) == 0) {
       for (int split = 1; split <= 2; split++) {
         if (n_real % split) continue;
@@ -1459,8 +1187,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   // halo box of its own 8x16 M tile and HALF of every streamed weight block, so per SM both the TMA fill and the
   // tensor core's shared-memory reads of B are halved (shared-memory bandwidth is what bounds the one-CTA modes).
   if (!A.halo) {
-    const char *env = getenv("TZ_HALO");
-    const bool want2 = !(env && (env[0] == '0' || env[0] == '1' || env[0] == '3'));   // default; TZ_HALO=3: one-CTA pair mode
+    const bool want2 = !halo_env;
     const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
     if (want2 && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
         (ntile_c % 16) == 0) {
@@ -1475,37 +1202,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       A.tiles_h = (A.H + 15) >> 4;
     }
   }
-  // ---- halo pair mode: large weight matrices, two stacked M tiles share every streamed weight block
-  if (!A.halo) {
-    // Measured on B200 (round 1, (3,48,96,192) net, B=100): with N tiles of <= 128 columns and two accumulator
-    // stages gates2 0.32 -> 0.28 ms, gates1 0.35 -> 0.34 ms vs the im2col path (TZ_HALO=1 selects the latter).
-    const char *env = getenv("TZ_HALO");
-    const bool want = !(env && (env[0] == '0' || env[0] == '1'));
-    // N tiles of at most 128 columns: the two M tiles of a pair then use 256 TMEM columns, which leaves room for a
-    // second accumulator stage (epilogue of pair i overlaps the MMAs of pair i+1)
-    int unit_p = n_unit;
-    if (epi == 1) unit_p = largest_divisor_le(n_real, 32);
-    else for (unit_p = 128; unit_p >= 16; unit_p -= 16) if (n_real % unit_p == 0) break;
-    if (unit_p < 16 && epi == 0) unit_p = n_unit;
-    const int ntile_c = (epi == 1) ? round_up(4 * round_up(unit_p, 8), 16) : round_up(unit_p, 16);
-    const uint32_t bst = ((uint32_t)ntile_c * 128u + 1023u) & ~1023u;
-    const uint32_t aslot = (10u * 34u * 128u + 1023u) & ~1023u;
-    if (want && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 32) == 0 && ntile_c <= 256 &&
-        2u * aslot + 3u * bst + 1024u <= 226u * 1024u) {
-      A.halo = 2;
-      n_unit = unit_p;
-      A.KC = 64;
-      A.kchunks = A.cin_pad / 64;
-      A.ksteps = 4;
-      A.tw_log = 3;
-      A.th_log = 4;
-      A.tb_log = 0;
-      A.tiles_w = (A.W + 7) >> 3;
-      A.tiles_h = A.H / 32;
-    }
-  }
-  A.sub_tiles = (A.halo == 2) ? 2 : 1;
-  A.tile_h = (1 << A.th_log) * A.sub_tiles;
+  A.tile_h = 1 << A.th_log;
   if (epi == 1) {
     A.NC = n_unit;
     A.NCp = round_up(A.NC, 8);
@@ -1519,39 +1216,8 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       return TZ_EINVAL;
     }
   }
-  // ---- pooling in accumulator columns (A path, halo + stationary weights, KC = 16 or 32).  TMA gathers the input
-  // tile by pixel parity: the tensor map has element strides {1, 2, 2, 1}, so one copy brings the even (or odd)
-  // columns of the even (or odd) rows of the 18 x 34-pixel halo region as a dense 9 x 17 sub-box -- space-to-depth
-  // on the fly, four copies per chunk.  For window position (py, px) and tap (dy, dx) the input pixel of pooled
-  // pixel (Y, X) is (2Y + py + dy, 2X + px + dx): a fixed sub-box (the parities of py+dy, px+dx) read at a fixed
-  // shift of 0 or 1 rows / pixels -- an ordinary shifted descriptor.  The MMA of that (position, tap) accumulates
-  // into column group 2*py+px, so one accumulator row holds all four candidates of a pooled pixel: the epilogue
-  // takes the maximum in registers (no shuffles, every lane a writer, 4x fewer tiles).
-  A.pool_cols = 0;
-  // Opt-in (TZ_POOLCOL=1): correct (the parity tests pass with it) but only ~10 % faster than the shuffle epilogue on
-  // a0 (0.093 vs 0.102 ms): in situ the 36 N=48 MMAs of a tile take ~2.7 k cycles and the epilogue ~2.8 k, and with
-  // room for only two accumulator stages (4 x 48 columns each) they overlap poorly.
-  if (epi == 0 && A.halo == 1 && getenv("TZ_POOLCOL") && (A.KC == 16 || A.KC == 32) && 4 * A.n_tile <= 256 &&
-      (A.H % 2) == 0 && (A.W % 2) == 0) {
-    A.pool_cols = 1;
-    A.tiles_w = (A.W / 2 + 7) >> 3;
-    A.tiles_h = (A.H / 2 + 15) >> 4;
-  }
-  A.phase_r = 0;
-  if (rmap) {
-    if (!(epi == 1 && A.halo == 1 && A.KC == 16 && A.kchunks == 1 && (rmap->size() % 16) == 0 && (A.H % 2) == 0 &&
-          (A.W % 2) == 0 && 4 * A.n_tile <= 128 && A.n_tiles_n == 1)) {
-      set_error("internal: phase_r requested for a conv it does not fit");
-      return TZ_EINVAL;
-    }
-    A.phase_r = 1;
-    A.r_chunks = (int)rmap->size() / 16;
-    A.kblocks_total = 9 + 16 * A.r_chunks;
-    A.tiles_w = (A.W / 2 + 7) >> 3;
-    A.tiles_h = (A.H / 2 + 15) >> 4;
-  }
   rows_total = A.n_tiles_n * A.n_tile;
-  const int Ktot = A.phase_r ? 16 * A.kblocks_total : 9 * A.cin_pad;
+  const int Ktot = 9 * A.cin_pad;
   // ---- pack weights: row n (tile-major; gates interleaved per tile), K-major, k = tap*cin_pad + c
   std::vector<float> wp((size_t)rows_total * Ktot, 0.0f);
   for (int nt = 0; nt < A.n_tiles_n; nt++)
@@ -1569,23 +1235,6 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       for (int tap = 0; tap < 9; tap++)
         for (int ci = 0; ci < cin_real; ci++)
           if (cmap[ci] >= 0) dst[tap * A.cin_pad + ci] = wsrc[((size_t)tap * cin_w + cmap[ci]) * cout_w + src_col];
-      if (A.phase_r) {
-        // block 9 + (phase*4 + t4)*r_chunks + chunk: output parity (qy, qx), low-resolution tap (a, b) = (t4>>1, t4&1).
-        // A 3x3 tap dy lands on low-resolution row offset a when: qy = 0: dy = -1 -> a = 0, dy = 0, +1 -> a = 1;
-        // qy = 1: dy = -1, 0 -> a = 0, dy = +1 -> a = 1 (rows 2Y+qy+dy of the up-sampled image are row (2Y+qy+dy)>>1).
-        auto lands = [](int q, int d /*-1..1*/, int a) { return ((q + d + 2) >> 1) - 1 == a - 1 + q; };
-        const int nrc = A.r_chunks;
-        for (int pp = 0; pp < 4; pp++)
-          for (int t4 = 0; t4 < 4; t4++)
-            for (int i = 0; i < (int)rmap->size(); i++) {
-              float acc = 0.0f;
-              for (int dy = -1; dy <= 1; dy++)
-                for (int dx = -1; dx <= 1; dx++)
-                  if (lands(pp >> 1, dy, t4 >> 1) && lands(pp & 1, dx, t4 & 1))
-                    acc += wsrc[((size_t)((dy + 1) * 3 + dx + 1) * cin_w + (*rmap)[i]) * cout_w + src_col];
-              dst[16 * (9 + (pp * 4 + t4) * nrc + i / 16) + (i % 16)] = acc;
-            }
-      }
     }
   float *tmp = nullptr;
   TZ_CHECK_CUDA(cudaMalloc(&tmp, wp.size() * sizeof(float)));
@@ -1627,34 +1276,12 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     A.stages = stages;
     c->smem_bytes = 2u * A.a_slot + (uint32_t)stages * A.stage_stride + 1024u;
-  } else if (A.halo == 2) {
-    A.a_tx = 10u * 34u * 128u;     // 34 image rows x 10 pixels x 64 channels fp16
-    A.a_slot = (A.a_tx + 1023u) & ~1023u;
-    A.a_stride = 0;
-    A.stage_stride = (b_bytes + 1023u) & ~1023u;
-    A.tx_bytes = b_bytes;
-    stages = (int)((226u * 1024u - 1024u - 2u * A.a_slot) / A.stage_stride);
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    A.stages = stages;
-    c->smem_bytes = 2u * A.a_slot + (uint32_t)stages * A.stage_stride + 1024u;
   } else if (A.halo) {
     A.b_block = ((uint32_t)A.n_tile * row_bytes + 1023u) & ~1023u;
     A.b_region = 9u * (uint32_t)A.kchunks * A.b_block;
     A.a_stride = 0;
     A.stage_stride = (16u * 18u * row_bytes + 1023u) & ~1023u;   // one halo tile: 18 image rows x 16 pixels x KC channels
     A.tx_bytes = 16u * 18u * row_bytes;
-    if (A.pool_cols) {   // four parity sub-boxes of 17 rows x 9 pixels: a 16 x 32 input tile + halo
-      A.pc_slot = (9u * 17u * row_bytes + 1023u) & ~1023u;
-      A.stage_stride = 4u * A.pc_slot;
-      A.tx_bytes = 4u * 9u * 17u * row_bytes;
-    }
-    if (A.phase_r) {     // the same four sub-boxes of e + r_chunks boxes of 18 rows x 10 low-resolution pixels x 16 ch
-      A.b_region = (uint32_t)A.kblocks_total * A.b_block;
-      A.pc_slot = (9u * 17u * 32u + 1023u) & ~1023u;
-      A.pr_slot = (10u * 18u * 32u + 1023u) & ~1023u;
-      A.stage_stride = 4u * A.pc_slot + (uint32_t)A.r_chunks * A.pr_slot;
-      A.tx_bytes = 4u * 9u * 17u * 32u + (uint32_t)A.r_chunks * 10u * 18u * 32u;
-    }
     stages = (int)((224u * 1024u - A.b_region) / A.stage_stride);
     if (stages > 4) stages = 4;
     if (stages < 2) {
@@ -1671,35 +1298,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     A.epi_groups = 1;
     A.acc_stages = 2;
     A.acc_stride = 256;
-    A.sub_stride = 0;
-    if (A.halo == 4) {
-      A.epi_groups = 1;
-      A.acc_stages = 2;
-      A.acc_stride = 256;
-    } else if (A.halo == 2) {
-      if (A.n_tile <= 128) {   // pair = columns [0, N) and [128, 128 + N) of a 256-column stage; two stages
-        A.acc_stages = 2;
-        A.acc_stride = 256;
-        A.sub_stride = 128;
-      } else {                 // the two M tiles of a pair occupy TMEM columns [0, N) and [256, 256 + N)
-        A.acc_stages = 1;
-        A.acc_stride = 0;
-        A.sub_stride = 256;
-      }
-    } else if (A.phase_r) {        // four column groups (output parities) of n_tile per stage, one region per warp group
-      A.epi_warps = 12;
-      A.epi_groups = 3;
-      A.acc_stages = 4;
-      A.acc_stride = 128;
-      A.sub_tiles = 4;
-      A.sub_stride = A.n_tile;
-      A.tile_h = 16;
-    } else if (A.pool_cols) {      // four column groups of n_tile per stage
-      A.epi_warps = 12;
-      A.epi_groups = 1;
-      A.acc_stages = 2;
-      A.acc_stride = 256;
-    } else if (A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
+    if (A.halo != 4 && A.n_tile <= 64) {   // narrow tiles: the epilogue is latency-bound, keep three of them in flight
       A.epi_warps = 12;
       A.epi_groups = 3;
       A.acc_stages = 6;
@@ -1718,8 +1317,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     // the same issuer, i.e. one chunk per tile and even ring sizes (otherwise a wait one full phase ahead returns
     // at once -- seen as a launch failure on a1, three chunks per tile, when this was unconditional).
     const char *env = getenv("TZ_MMA_ISSUERS");   // A/B switch
-    // (not in the pooled variant: its two accumulator stages pipeline better when one tile's MMAs finish first)
-    A.mma_issuers = (A.halo == 1 && !A.pool_cols && A.kchunks == 1 && (A.stages % 2) == 0 && (A.acc_stages % 2) == 0 &&
+    A.mma_issuers = (A.halo == 1 && A.kchunks == 1 && (A.stages % 2) == 0 && (A.acc_stages % 2) == 0 &&
                      !(env && env[0] == '1')) ? 2 : 1;
   }
   // ---- descriptors
@@ -1728,46 +1326,22 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   const uint32_t layout_type = A.KC == 64 ? 2u : A.KC == 32 ? 4u : 6u;   // UMMA SWIZZLE_128B / 64B / 32B
   const uint32_t sbo = 8u * row_bytes;                                   // 8-row core-matrix group stride
   A.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
-  if (A.pool_cols || A.phase_r)   // 8-row groups (pooled rows) are one sub-box row of 9 pixels apart
-    A.desc_hi_pc = (((9u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
-  if (A.phase_r)                  // low-resolution boxes: rows of 10 pixels
-    A.desc_hi_pr = (((10u * 32u) >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
   A.idesc = (1u << 4) | ((uint32_t)(A.n_tile >> 3) << 17) | (((A.halo == 4 ? 256u : 128u) >> 4) << 24);   // f32 acc, f16 x f16, K-major
   {
     cuuint64_t dims[4] = {(cuuint64_t)cx, (cuuint64_t)A.W, (cuuint64_t)A.H, (cuuint64_t)h->cfg.max_batch};
     cuuint64_t strides[3] = {(cuuint64_t)cx * 2, (cuuint64_t)cx * 2 * A.W, (cuuint64_t)cx * 2 * A.W * A.H};
     cuuint32_t box[4] = {(cuuint32_t)A.KC, 1u << A.tw_log, 1u << A.th_log, 1u << A.tb_log};
     if (A.halo) {   // (tile height + 2) image rows of 16 pixels each (8-wide tile + halo, padded to a 16-pixel pitch)
-      box[1] = (A.halo == 2 || A.halo == 4) ? 10 : 16;
+      box[1] = (A.halo == 4) ? 10 : 16;
       box[2] = (cuuint32_t)A.tile_h + 2;
       box[3] = 1;
-      if (A.pool_cols || A.phase_r) {
-        box[1] = 18;
-        box[2] = 34;
-      }
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (A.pool_cols || A.phase_r) es[1] = es[2] = 2;   // every other pixel of every other row: the box extent stays 18 x 34
     CUresult r = enc(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, X, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(A, layer %d) failed: %d", l, (int)r);
-      return TZ_ECUDA;
-    }
-  }
-  c->tmC = c->tmA;
-  if (A.phase_r) {   // r_{l+1} at its own resolution: [maxB, H/2, W/2, R_up], one box = 18 rows x 10 pixels x 16 channels
-    const int Ru = (int)rmap->size();
-    cuuint64_t dims[4] = {(cuuint64_t)Ru, (cuuint64_t)(A.W / 2), (cuuint64_t)(A.H / 2), (cuuint64_t)h->cfg.max_batch};
-    cuuint64_t strides[3] = {(cuuint64_t)Ru * 2, (cuuint64_t)Ru * 2 * (A.W / 2), (cuuint64_t)Ru * 2 * (A.W / 2) * (A.H / 2)};
-    cuuint32_t box[4] = {16, 10, 18, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&c->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, RL, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(R, layer %d) failed: %d", l, (int)r);
       return TZ_ECUDA;
     }
   }
@@ -1812,9 +1386,7 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     TZ_CHECK_CUDA(cudaMemcpy(T->ahat0_b, h->b_ahat[0], sizeof(float) * C, cudaMemcpyDeviceToHost));
   }
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
@@ -1824,22 +1396,7 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     for (int i = 0; i < 2 * h->S[l]; i++) gmap[i] = h->R[l] + i;                                  // e_l
     if (l < L - 1)
       for (int i = 0; i < h->R[l + 1]; i++) gmap[T->epad[l] + i] = h->R[l] + 2 * h->S[l] + i;    // up(r_{l+1})
-    // Opt-in prototype (TZ_PHASE0=1): layer 0 reads r_1 at its own resolution with parity-collapsed taps
-    const bool phase0 = TZ_PHASE_PROTO && l == 0 && L >= 2 && getenv("TZ_PHASE0") && (h->R[1] % 16) == 0 && T->epad[0] == 16 &&
-                        (h->H[0] % 2) == 0 && (h->W[0] % 8) == 0 && h->R[0] <= 8;
-    int rc;
-    if (phase0) {
-      T->RL1 = (__half *)dev_alloc(h, (size_t)mb * h->H[1] * h->W[1] * h->R[1] * sizeof(__half));
-      if (!T->RL1) return TZ_ENOMEM;
-      TZ_CHECK_CUDA(cudaMemset(T->RL1, 0, (size_t)mb * h->H[1] * h->W[1] * h->R[1] * sizeof(__half)));
-      std::vector<int> emap(T->epad[0], -1), rmap(h->R[1]);
-      for (int i = 0; i < 2 * h->S[0]; i++) emap[i] = h->R[0] + i;
-      for (int i = 0; i < h->R[1]; i++) rmap[i] = h->R[0] + 2 * h->S[0] + i;
-      rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], emap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l],
-                     &rmap, T->RL1);
-    } else {
-      rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
-    }
+    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
     if (rc) return rc;
     ConvArgs &G = T->gconv[l].args;
     G.bm = h->BM[l];
@@ -1854,10 +1411,6 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       TZ_CHECK_CUDA(cudaDeviceSynchronize());
       G.bm = bp;
       G.bm_packed = 1;
-    }
-    if (l == 1 && T->RL1) {   // the layer-0 phase_r consumer reads r_1 from here
-      G.rl_out = T->RL1;
-      G.rl_cstride = h->R[1];
     }
     if (l > 0) {
       G.xr_out = T->X[l - 1];
@@ -1922,22 +1475,17 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, c->tmC, A)
-                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, c->tmC, A);
+    cudaError_t e = (c->epi == 0) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, c->tmA, c->tmB, A)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, c->tmA, c->tmB, A);
     if (e != cudaSuccess) {
       set_error("cluster launch failed: %s", cudaGetErrorString(e));
       return TZ_ECUDA;
     }
-  } else if (c->epi == 0)
-    if (A.pool_cols)
-      conv_tc_kernel<0, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
-    else
-      conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
-  else
-    if (A.phase_r)
-      conv_tc_kernel<1, false, false, true><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
-    else
-      conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, c->tmC, A);
+  } else if (c->epi == 0) {
+    conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  } else {
+    conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  }
   TZ_CHECK_LAUNCH();
   if (dbg_on) {   // diagnostics only: synchronous
     long long hbuf[256 * 8];
