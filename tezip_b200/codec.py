@@ -53,6 +53,7 @@ class Plan:
     apply_eb: np.ndarray             # uint8 [nt]: 1 where error_bound runs (compress.py:315-319)
     steps: list = field(default_factory=list)   # [(key_idx int32[B] | None, slot0, B)] for k = 1, 2, ...
     n_slots: int = 1
+    dev: dict = field(default_factory=dict)     # (device, name) -> device copy of a table (cached_plan)
 
 
 def plan_from_keys(nt, p, keys):
@@ -84,6 +85,31 @@ def plan_from_keys(nt, p, keys):
     return Plan(nt, p, keys, windows, pred_slot, apply_eb, steps, slot)
 
 
+_PLAN_CACHE = {}
+
+
+def cached_plan(nt, p, keys):
+    """plan_from_keys() memoised on (nt, p, keys): a streaming compressor calls with the same schedule again and
+    again, and building it (Python loops over the windows, ~0.1 ms per 1000 frames) happens while the GPU idles at
+    the start of every call.  The Plan also carries the device copies of its tables (plan.dev)."""
+    key = (int(nt), int(p), tuple(int(k) for k in keys))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= 32:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        plan = _PLAN_CACHE[key] = plan_from_keys(nt, p, keys)
+    return plan
+
+
+def _plan_dev(plan, device, name, make):
+    """Device copy of one of the plan's (read-only) tables, uploaded once per device."""
+    k = (str(device), name)
+    t = plan.dev.get(k)
+    if t is None:
+        t = plan.dev[k] = make().to(device)
+    return t
+
+
 def run_plan(net, frames, plan, pool):
     """Fills pool[1:] with the predictions of every non-key frame; pool[0] = P0.
 
@@ -97,7 +123,8 @@ def run_plan(net, frames, plan, pool):
     key_idx_all, _slot0, B1 = plan.steps[0]
     for g0 in range(0, B1, mb):
         g1 = min(g0 + mb, B1)
-        idx = torch.from_numpy(np.ascontiguousarray(key_idx_all[g0:g1])).to(frames.device)
+        idx = _plan_dev(plan, frames.device, ("key_idx", g0, g1),
+                        lambda: torch.from_numpy(np.ascontiguousarray(key_idx_all[g0:g1])))
         x = ops.pad_normalize(frames, idx, net.Hp, net.Wp)                  # compress.py:219 / decompress.py:161
         for k, (_kidx, slot0, B) in enumerate(plan.steps):
             nb = min(B, g1) - g0                                            # windows of this group longer than k + 1
@@ -355,12 +382,12 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         raise TezipError("error bounds must be non-negative")
     staged = None
     if threshold is None:
-        plan = plan_from_keys(nt, p, swp_keys(nt, p, window, shard=comm is not None))
+        plan = cached_plan(nt, p, swp_keys(nt, p, window, shard=comm is not None))
         pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np = plan.keys, plan.pred_slot, plan.apply_eb
         # the schedule is static: upload it and emit the key plane before the first PredNet step is queued, so that
         # nothing on the host waits behind the predictions and the key plane's D2H copy runs under them
-        staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink)
+        staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink, plan)
         run_plan(net, frames, plan, pool)
         if frames_ready is not None:   # the non-key frames were still in flight (upload_frames); the residual needs them
             torch.cuda.current_stream(dev).wait_event(frames_ready)
@@ -380,15 +407,30 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
     return enc
 
 
-def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None):
-    """Device copies of the schedule (pred_slot int32 [nt], apply u8 [nt]) and the key plane (compress.py:183-263)."""
+def stage_plan(frames, keys, pred_slot_np, apply_np, sink=None, plan=None):
+    """Device copies of the schedule (pred_slot int32 [nt], apply u8 [nt]) and the key plane (compress.py:183-263).
+    plan: the cached Plan these tables belong to -- its device copies are then uploaded once, not per call."""
     dev = frames.device
     nt = frames.shape[0]
-    pred_slot = torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)).to(dev)
-    apply = torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev)
-    is_key = np.zeros(nt, np.uint8)
-    is_key[list(keys)] = 1
-    return stage_device(frames, torch.from_numpy(is_key).to(dev), pred_slot, apply, sink, keys_host=sorted(keys))
+
+    def is_key_host():
+        is_key = np.zeros(nt, np.uint8)
+        is_key[list(keys)] = 1
+        return torch.from_numpy(is_key)
+
+    if plan is not None:
+        pred_slot = _plan_dev(plan, dev, "pred_slot", lambda: torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)))
+        apply = _plan_dev(plan, dev, "apply", lambda: torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)))
+        is_key = _plan_dev(plan, dev, "is_key", is_key_host)
+        keys_sorted = plan.dev.get("keys_sorted")
+        if keys_sorted is None:
+            keys_sorted = plan.dev["keys_sorted"] = sorted(keys)
+    else:
+        pred_slot = torch.from_numpy(np.ascontiguousarray(pred_slot_np, np.int32)).to(dev)
+        apply = torch.from_numpy(np.ascontiguousarray(apply_np, np.uint8)).to(dev)
+        is_key = is_key_host().to(dev)
+        keys_sorted = sorted(keys)
+    return stage_device(frames, is_key, pred_slot, apply, sink, keys_host=keys_sorted)
 
 
 def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
@@ -600,9 +642,9 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
     key_plane = key_plane.view(nt, H, W, C)
     nz = ops.frames_nonzero(key_plane).cpu().numpy()                                     # decompress.py:123-127
     keys = [int(i) for i in np.nonzero(nz)[0]]
-    plan = plan_from_keys(nt, p, keys)
+    plan = cached_plan(nt, p, keys)
     pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
-    pred_slot = torch.from_numpy(plan.pred_slot).to(dev)
+    pred_slot = _plan_dev(plan, dev, "pred_slot", lambda: torch.from_numpy(np.ascontiguousarray(plan.pred_slot, np.int32)))
     if ops.is_wide(body) != ops.is_wide(key_plane):
         raise TezipError("key plane and stream disagree about the sample width")
     if table is not None:

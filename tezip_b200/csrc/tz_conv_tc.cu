@@ -196,6 +196,8 @@ struct ConvArgs {
   int tiles_w, tiles_h, n_tiles_n;
   uint32_t m_tiles_w, m_tiles_h, m_tiles_n;   // fast_div magic numbers of the three
   int kchunks, ksteps;           // K blocks per tap, MMAs (K=16) per K block
+  int ksteps_last;               // pair mode: K=16 steps of the LAST block that hold a real input channel (the rest
+                                 // multiply zero weights and are not issued; a1 of the (3,48,96,192) net: 96 = 64 + 32)
   int KC, cin_pad;               // channels per K block, kchunks*KC
   int n_tile;                    // MMA N (multiple of 16)
   int stages;
@@ -226,6 +228,14 @@ struct ConvArgs {
   __half *xr_out;                // X_{l-1}: [B, 2H, 2W, xr_cstride], r written up-sampled at channel xr_coff
   int xr_cstride, xr_coff;
   float *r0_out;                 // layer 0: r as fp32 [B, H, W, R] (xr_out == nullptr)
+  int xr_up;                     // 1: r is written 2x up-sampled (four stores); 0: once, at its own resolution
+  // --- layer 0 with the up(r_1) half of K moved to r_1's resolution (see tc_create): the gate pre-activations of
+  // that half arrive as G [B, H/2, W/2, 4 parities, R, 4 gates] fp32 and are added like the bias map
+  const float *gr;
+  int gr_cols;                   // 16 R
+  // --- raw epilogue (EPI 2): the accumulator row as fp32 [B, H, W, g_cols]
+  float *g_out;
+  int g_cols;
   long long *dbg;                // optional [gridDim][8]: MMA-thread cycle breakdown (TZ_CONV_DEBUG), else nullptr
 };
 
@@ -538,14 +548,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_fence_after();
               const uint32_t b_base = (((pair_bbase + s * P.stage_stride) >> 4) & 0x3FFFu) | (1u << 16);
               if (elect_one()) {
+                if (ch + 1 == P.kchunks && P.ksteps_last == 2) {   // half-empty last block: two K steps per tap
 #pragma unroll
-                for (int j = 0; j < 3; j++) {   // 64-channel chunks: 128-byte pixels
-                  const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
-                  const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+                  for (int j = 0; j < 3; j++) {
+                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
 #pragma unroll
-                  for (int k = 0; k < 4; k++)
-                    tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
-                                acc | (uint32_t)(tg | j | k));
+                    for (int k = 0; k < 2; k++)
+                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                                  acc | (uint32_t)(tg | j | k));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 3; j++) {   // 64-channel chunks: 128-byte pixels
+                    const uint32_t a_lo = a_base + (uint32_t)(tg * 10 + j) * 8u;
+                    const uint32_t b_lo = b_base + (uint32_t)j * (P.b_block >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                      tc2_mma_f16(d_tmem, make_desc(a_lo + 2 * k, ahi_pair), make_desc(b_lo + 2 * k, hi), idesc,
+                                  acc | (uint32_t)(tg | j | k));
+                  }
                 }
                 tc2_commit(empty0 + 8 * s);
               }
@@ -789,11 +811,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int j0 = 8 * (part + PF * nparts); j0 < n_real; j0 += 8 * nparts) chunk(j0, nullptr);
         }
+      } else if (EPI == 2) {
+        // raw accumulator rows (the r_1-resolution half of the layer-0 gate convolution): fp32, 32-byte stores.
+        // tcgen05.ld is warp-collective: every lane walks the loop, only the stores are predicated.
+        {
+          float *dst = P.g_out + (((long long)b * P.H + h) * P.W + w) * P.g_cols + nt * P.n_tile;
+          const int n_real = P.g_cols - nt * P.n_tile < P.n_tile ? P.g_cols - nt * P.n_tile : P.n_tile;
+          for (int j0 = 8 * part; j0 < n_real; j0 += 16 * nparts) {
+            float va[8], vb[8];
+            const int j1 = j0 + 8 * nparts;
+            const bool has_b = j1 < n_real;   // warp-uniform
+            tc_ld8(trow + j0, va);
+            tc_ld8(trow + (has_b ? j1 : j0), vb);
+            tc_ld_wait();
+            if (valid) {
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + j0), "f"(va[0]),
+                           "f"(va[1]), "f"(va[2]), "f"(va[3]), "f"(va[4]), "f"(va[5]), "f"(va[6]), "f"(va[7])
+                           : "memory");
+              if (has_b)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + j1), "f"(vb[0]),
+                             "f"(vb[1]), "f"(vb[2]), "f"(vb[3]), "f"(vb[4]), "f"(vb[5]), "f"(vb[6]), "f"(vb[7])
+                             : "memory");
+            }
+          }
+        }
       } else {
         // LSTM cell: columns [g*NCp + j], g = i,f,c,o.  c = f*C0 + i*tanh(.), r = o*tanh(c)
         const long long pix = (long long)h * P.W + w;
         const float *bm = P.bm + pix * 4 * P.R + nt * P.NC;
         const float *c0 = P.c0 + pix * P.R + nt * P.NC;
+        // layer 0: this pixel's block of G (its parity): [R channels][4 gates] -> one 16-byte load per channel
+        const float4 *grp = nullptr;
+        if (P.gr)
+          grp = reinterpret_cast<const float4 *>(
+                    P.gr + ((((long long)b * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) *
+                               (long long)(4 * P.R)) + nt * P.NC;
         // r for channels j0..j0+7 of this N tile -> fp16 into hv (or straight to the fp32 r_0 buffer at layer 0)
         auto lstm_chunk = [&](int j0, __half *hv) {
           float vi[8], vf[8], vc[8], vo[8];
@@ -819,6 +871,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ldg256(bp + 16, bq + 16);
             ldg256(bp + 24, bq + 24);
             ldg256(c0 + j0, cq);
+            if (grp) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float4 g4 = __ldg(grp + j0 + j);
+                bq[j] = __fadd_rn(bq[j], g4.x);
+                bq[8 + j] = __fadd_rn(bq[8 + j], g4.y);
+                bq[16 + j] = __fadd_rn(bq[16 + j], g4.z);
+                bq[24 + j] = __fadd_rn(bq[24 + j], g4.w);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const float gi = hsig(__fadd_rn(vi[j], bq[j]));
@@ -832,10 +894,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               if (j0 + j < P.NC) {
-                const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
-                const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
-                const float gc = fast_tanh(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
-                const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
+                float4 g4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (grp) g4 = __ldg(grp + j0 + j);
+                const float gi = hsig(__fadd_rn(vi[j], __fadd_rn(bm[0 * P.R + j0 + j], g4.x)));
+                const float gf = hsig(__fadd_rn(vf[j], __fadd_rn(bm[1 * P.R + j0 + j], g4.y)));
+                const float gc = fast_tanh(__fadd_rn(vc[j], __fadd_rn(bm[2 * P.R + j0 + j], g4.z)));
+                const float go = hsig(__fadd_rn(vo[j], __fadd_rn(bm[3 * P.R + j0 + j], g4.w)));
                 const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
                 r[j] = __fmul_rn(go, fast_tanh(c));
               } else {
@@ -858,7 +922,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool second = jp + 8 < P.NC;
           lstm_chunk(jp, hv);
           if (second) lstm_chunk(jp + 8, hv + 8);
-          if (valid && P.xr_out) {
+          if (valid && P.xr_out && !P.xr_up) {
+            // r at its own resolution (read by the r-resolution half of the layer-0 gate convolution)
+            const int ch0 = nt * P.NC + jp;
+            __half *dst = P.xr_out + ((long long)b * P.H * P.W + pix) * P.xr_cstride + P.xr_coff + ch0;
+            if ((jp + 16 <= P.NC) && (((P.xr_coff + ch0) | P.xr_cstride) & 15) == 0) {
+              const uint4 lo = *reinterpret_cast<const uint4 *>(hv), hi4 = *reinterpret_cast<const uint4 *>(hv + 8);
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y),
+                           "r"(lo.z), "r"(lo.w), "r"(hi4.x), "r"(hi4.y), "r"(hi4.z), "r"(hi4.w)
+                           : "memory");
+            } else {
+              for (int j = 0; j < 16 && jp + j < P.NC; j++) dst[j] = hv[j];
+            }
+          } else if (valid && P.xr_out) {
             // nearest 2x up-sampling folded into the store: 4 destinations per source pixel
             const int H2 = P.H * 2, W2 = P.W * 2;
             const int ch0 = nt * P.NC + jp;
@@ -1046,6 +1122,12 @@ struct TcState {
   int cx[TZ_MAX_LAYERS];
   int epad[TZ_MAX_LAYERS];    // channel offset of the up(r_{l+1}) block: 2*S_l rounded up to 16 (32-byte stores)
   float *r0;                  // [maxB, H_0, W_0, R_0] fp32
+  // layer 0 with the up(r_1) half of its gate convolution evaluated at r_1's resolution (use_gr):
+  bool use_gr;
+  __half *rlow;               // r_1 at its own resolution: [maxB, H_1, W_1, cxr] fp16 (channels >= R_1 stay zero)
+  int cxr;
+  float *gr;                  // G: [maxB, H_1, W_1, 4 parities, R_0, 4 gates] fp32
+  tz::ConvTc rconv0;          // r_1 -> G (raw epilogue)
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
   int sm_count;
@@ -1168,7 +1250,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         if (n_real % split) continue;
         const int unit = n_real / split;
         if (epi == 1 && unit > 64) continue;
-        if (epi == 0 && split > 1 && (unit % 16) != 0) continue;
+        if (epi != 1 && split > 1 && (unit % 16) != 0) continue;
         const int ntile = (epi == 1) ? round_up(4 * round_up(unit, 8), 16) : round_up(unit, 16);
         const uint32_t wbytes = 9u * (uint32_t)(cin64 / A.KC) * (((uint32_t)ntile * 2u * (uint32_t)A.KC + 1023u) & ~1023u);
         if (wbytes > (split == 1 ? budget : 112u * 1024u) || ntile > 256) continue;
@@ -1189,7 +1271,7 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   if (!A.halo) {
     const bool want2 = !halo_env;
     const int ntile_c = (epi == 1) ? round_up(4 * round_up(n_unit, 8), 16) : round_up(n_unit, 16);
-    if (want2 && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
+    if (want2 && epi != 2 && (A.cin_pad % 64) == 0 && A.cin_pad <= cx && (A.W % 8) == 0 && (A.H % 16) == 0 && ntile_c <= 256 &&
         (ntile_c % 16) == 0) {
       A.halo = 4;
       A.KC = 64;
@@ -1203,6 +1285,11 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
     }
   }
   A.tile_h = 1 << A.th_log;
+  A.ksteps_last = A.ksteps;
+  if (A.halo == 4) {
+    const int last = round_up(cin_real, 16) - (A.kchunks - 1) * 64;   // channels of the last block that carry weights
+    if (last > 0 && last <= 32) A.ksteps_last = 2;
+  }
   if (epi == 1) {
     A.NC = n_unit;
     A.NCp = round_up(A.NC, 8);
@@ -1369,10 +1456,19 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   T->L = L;
   T->sm_count = sm_count();
   const int mb = h->cfg.max_batch;
+  // Layer 0 is the widest image and the narrowest convolution (N = 4 R_0 = 12 columns for RGB): an M128 x K16 MMA
+  // costs 44 cycles however narrow N is (it reads 4 KB of A from shared memory), so its gate convolution is bound by
+  // the NUMBER of K16 slabs, and 27 of the 36 slabs per tile come from up(r_1).  A 3x3 convolution over a
+  // nearest-neighbour up-sampled image is, for each of the four output parities, a convolution over the
+  // low-resolution image with pre-summed taps (prednet.py:250-258 with UpSampling2D): those 27 slabs per 128 pixels
+  // become one convolution at r_1's resolution with 4 x 4R_0 output columns (36 slabs per 512 pixels), whose raw
+  // accumulators G are added in the layer-0 LSTM epilogue like the bias map.  r_1 is then never written up-sampled
+  // and X_0 holds only the 32-byte e_0 block.
+  T->use_gr = L >= 2 && 16 * h->R[0] <= 256 && !getenv("TZ_NO_GR");
   for (int l = 0; l < L; l++) {
     TZ_REQUIRE(h->H[l] % 2 == 0 || l == L - 1, "tensor-core path: odd layer height");
     T->epad[l] = round_up(2 * h->S[l], 16);   // 32-byte aligned r_up block
-    T->cx[l] = round_up(T->epad[l] + (l < L - 1 ? h->R[l + 1] : 0), 16);
+    T->cx[l] = round_up(T->epad[l] + ((l < L - 1 && !(l == 0 && T->use_gr)) ? h->R[l + 1] : 0), 16);
     size_t bytes = (size_t)mb * h->H[l] * h->W[l] * T->cx[l] * sizeof(__half);
     T->X[l] = (__half *)dev_alloc(h, bytes);
     if (!T->X[l]) return TZ_ENOMEM;
@@ -1380,6 +1476,14 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   }
   T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
   if (!T->r0) return TZ_ENOMEM;
+  if (T->use_gr) {
+    T->cxr = round_up(h->R[1], 64);
+    const size_t px1 = (size_t)mb * h->H[1] * h->W[1];
+    T->rlow = (__half *)dev_alloc(h, px1 * T->cxr * sizeof(__half));
+    T->gr = (float *)dev_alloc(h, px1 * 16 * h->R[0] * sizeof(float));
+    if (!T->rlow || !T->gr) return TZ_ENOMEM;
+    TZ_CHECK_CUDA(cudaMemset(T->rlow, 0, px1 * T->cxr * sizeof(__half)));
+  }
   if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1)) {
     const int C = h->S[0];
     TZ_CHECK_CUDA(cudaMemcpy(T->ahat0_w, h->w_ahat[0], sizeof(float) * 9 * C * C, cudaMemcpyDeviceToHost));
@@ -1387,14 +1491,16 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   }
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
   for (int l = 0; l < L; l++) {
     // gate conv: reads all of X_l = [e_l | up(r_{l+1})]; the r_{t-1} slice of the kernel is hoisted into BM_l
-    std::vector<int> gmap(T->epad[l] + (l < L - 1 ? h->R[l + 1] : 0), -1);
+    const bool r_in_x = l < L - 1 && !(l == 0 && T->use_gr);   // X_l carries the up-sampled r_{l+1} block
+    std::vector<int> gmap(T->epad[l] + (r_in_x ? h->R[l + 1] : 0), -1);
     for (int i = 0; i < 2 * h->S[l]; i++) gmap[i] = h->R[l] + i;                                  // e_l
-    if (l < L - 1)
+    if (r_in_x)
       for (int i = 0; i < h->R[l + 1]; i++) gmap[T->epad[l] + i] = h->R[l] + 2 * h->S[l] + i;    // up(r_{l+1})
     int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
     if (rc) return rc;
@@ -1412,13 +1518,48 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       G.bm = bp;
       G.bm_packed = 1;
     }
-    if (l > 0) {
+    G.xr_up = 1;
+    if (l == 1 && T->use_gr) {
+      G.xr_out = T->rlow;
+      G.xr_cstride = T->cxr;
+      G.xr_coff = 0;
+      G.xr_up = 0;
+    } else if (l > 0) {
       G.xr_out = T->X[l - 1];
       G.xr_cstride = T->cx[l - 1];
       G.xr_coff = T->epad[l - 1];
     } else {
       G.xr_out = nullptr;
       G.r0_out = T->r0;
+    }
+    if (l == 0 && T->use_gr) {
+      // the up(r_1) half of the layer-0 gates at r_1's resolution.  Output parity (py, px), low-resolution offset
+      // (oy, ox): W_eff = sum of the taps (dy, dx) with floor((py + dy) / 2) == oy and floor((px + dx) / 2) == ox
+      // (py = 0: dy = -1 -> oy = -1, dy = 0, 1 -> oy = 0;  py = 1: dy = -1, 0 -> oy = 0, dy = 1 -> oy = 1).  Keras'
+      // zero padding acts on the up-sampled image; its rows -1 and 2H_1 are the low-resolution rows -1 and H_1, so
+      // TMA's out-of-bounds zero fill reproduces it exactly.  Columns: [parity][channel][gate i,f,c,o].
+      const int R0 = h->R[0], R1 = h->R[1], cols = 16 * R0, cin = h->cin_g[0], coff = R0 + 2 * h->S[0];
+      std::vector<float> weff((size_t)9 * R1 * cols, 0.0f);
+      for (int py = 0; py < 2; py++)
+        for (int px = 0; px < 2; px++)
+          for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+              const int oy = (py + dy + 2) / 2 - 1, ox = (px + dx + 2) / 2 - 1;   // floor((p + d) / 2)
+              const int tsrc = (dy + 1) * 3 + (dx + 1), tdst = (oy + 1) * 3 + (ox + 1);
+              for (int ci = 0; ci < R1; ci++)
+                for (int g = 0; g < 4; g++)
+                  for (int ch = 0; ch < R0; ch++)
+                    weff[((size_t)tdst * R1 + ci) * cols + ((py * 2 + px) * R0 + ch) * 4 + g] +=
+                        wg_host[0][((size_t)tsrc * cin + coff + ci) * 4 * R0 + g * R0 + ch];
+            }
+      std::vector<int> rmap(T->cxr, -1);
+      for (int i = 0; i < R1; i++) rmap[i] = i;
+      rc = make_conv(h, &T->rconv0, 2, 1, T->rlow, T->cxr, rmap, weff, R1, cols, cols);
+      if (rc) return rc;
+      T->rconv0.args.g_out = T->gr;
+      T->rconv0.args.g_cols = cols;
+      G.gr = T->gr;
+      G.gr_cols = cols;
     }
     if (l < L - 1) {
       // a conv: reads channels [0, 2S_l) of X_l
@@ -1483,6 +1624,8 @@ static int launch_conv(TcState *T, ConvTc *c, int B, cudaStream_t st) {
     }
   } else if (c->epi == 0) {
     conv_tc_kernel<0, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
+  } else if (c->epi == 2) {
+    conv_tc_kernel<2, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   } else {
     conv_tc_kernel<1, false><<<grid, 128 + 32 * A.epi_warps, c->smem_bytes, st>>>(c->tmA, c->tmB, A);
   }
@@ -1527,6 +1670,10 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
     if (ev) cudaEventRecord(ev[ne++], st);
   }
   for (int l = L - 1; l >= 0; l--) {
+    if (l == 0 && T->use_gr) {   // r_1 -> G first (timed together with the layer-0 gates)
+      int rc = launch_conv(T, &T->rconv0, B, st);
+      if (rc) return rc;
+    }
     int rc = launch_conv(T, &T->gconv[l], B, st);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[ne++], st);
