@@ -229,11 +229,7 @@ struct ConvArgs {
   int xr_cstride, xr_coff;
   float *r0_out;                 // layer 0: r as fp32 [B, H, W, R] (xr_out == nullptr)
   int xr_up;                     // 1: r is written 2x up-sampled (four stores); 0: once, at its own resolution
-  // --- layer 0 with the up(r_1) half of K moved to r_1's resolution (see tc_create): the gate pre-activations of
-  // that half arrive as G [B, H/2, W/2, 4 parities, R, 4 gates] fp32 and are added like the bias map
-  const float *gr;
-  int gr_cols;                   // 16 R
-  // --- raw epilogue (EPI 2): the accumulator row as fp32 [B, H, W, g_cols]
+  // --- raw epilogue (EPI 2): the accumulator row as fp32 [B, H, W, g_cols] (G of the layer-0 split, tc_create)
   float *g_out;
   int g_cols;
   long long *dbg;                // optional [gridDim][8]: MMA-thread cycle breakdown (TZ_CONV_DEBUG), else nullptr
@@ -840,12 +836,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long pix = (long long)h * P.W + w;
         const float *bm = P.bm + pix * 4 * P.R + nt * P.NC;
         const float *c0 = P.c0 + pix * P.R + nt * P.NC;
-        // layer 0: this pixel's block of G (its parity): [R channels][4 gates] -> one 16-byte load per channel
-        const float4 *grp = nullptr;
-        if (P.gr)
-          grp = reinterpret_cast<const float4 *>(
-                    P.gr + ((((long long)b * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) *
-                               (long long)(4 * P.R)) + nt * P.NC;
         // r for channels j0..j0+7 of this N tile -> fp16 into hv (or straight to the fp32 r_0 buffer at layer 0)
         auto lstm_chunk = [&](int j0, __half *hv) {
           float vi[8], vf[8], vc[8], vo[8];
@@ -871,16 +861,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ldg256(bp + 16, bq + 16);
             ldg256(bp + 24, bq + 24);
             ldg256(c0 + j0, cq);
-            if (grp) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const float4 g4 = __ldg(grp + j0 + j);
-                bq[j] = __fadd_rn(bq[j], g4.x);
-                bq[8 + j] = __fadd_rn(bq[8 + j], g4.y);
-                bq[16 + j] = __fadd_rn(bq[16 + j], g4.z);
-                bq[24 + j] = __fadd_rn(bq[24 + j], g4.w);
-              }
-            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const float gi = hsig(__fadd_rn(vi[j], bq[j]));
@@ -894,12 +874,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               if (j0 + j < P.NC) {
-                float4 g4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (grp) g4 = __ldg(grp + j0 + j);
-                const float gi = hsig(__fadd_rn(vi[j], __fadd_rn(bm[0 * P.R + j0 + j], g4.x)));
-                const float gf = hsig(__fadd_rn(vf[j], __fadd_rn(bm[1 * P.R + j0 + j], g4.y)));
-                const float gc = fast_tanh(__fadd_rn(vc[j], __fadd_rn(bm[2 * P.R + j0 + j], g4.z)));
-                const float go = hsig(__fadd_rn(vo[j], __fadd_rn(bm[3 * P.R + j0 + j], g4.w)));
+                const float gi = hsig(__fadd_rn(vi[j], bm[0 * P.R + j0 + j]));
+                const float gf = hsig(__fadd_rn(vf[j], bm[1 * P.R + j0 + j]));
+                const float gc = fast_tanh(__fadd_rn(vc[j], bm[2 * P.R + j0 + j]));
+                const float go = hsig(__fadd_rn(vo[j], bm[3 * P.R + j0 + j]));
                 const float c = __fadd_rn(__fmul_rn(gf, c0[j0 + j]), __fmul_rn(gi, gc));
                 r[j] = __fmul_rn(go, fast_tanh(c));
               } else {
@@ -1100,6 +1078,217 @@ __global__ void __launch_bounds__(256) ahat0_kernel(const float *__restrict__ r0
   }
 }
 
+// ------------------------------------------------------------------------------------------------ layer-0 tail
+// prednet.py:255-259 at layer 0 (gates + LSTM), :268-271 (A-hat_0 = prediction) and :274-277 of the NEXT step, in one
+// kernel.  What is left of the layer-0 gate convolution once its up(r_1) half has moved to r_1's resolution (G,
+// tc_create) is K = 9 taps x 2C error channels for 4C outputs.  As a tcgen05 implicit GEMM that is nine K16 slabs of
+// which 10/16 are padding, one 44-cycle MMA each, behind an LSTM epilogue that waits for three global operands per
+// pixel (measured 0.107 ms per 100 frames with the tensor pipe 8 % active); as plain FMAs it is 648 per pixel and
+// issue-bound (0.122 ms).  Here a warp runs it as m16n8k16 register-level MMAs (fp16 x fp16 -> fp32, the numerics
+// of the other convolutions): K = tap * 2C + channel is dense (54 of 64 for RGB, four K steps), the N = 16 columns
+// are ordered so that lane t of a quad ends with the four gates of channel t for its two pixels, the bias map and
+// G seed the accumulators, and the LSTM follows in registers.
+// One block = 32 x 16 output pixels: e_0 on the 36 x 20 region (fp16 as stored, 16 bytes per pixel in shared
+// memory), r_0 on the 34 x 18 region (the A-hat convolution needs a one-pixel halo of r_0, recomputed instead of
+// exchanged; fp32), then the prediction (fp32 FMAs, weights in the constant bank), clipped, and the next step's
+// error units.  X_0 is double-buffered: neighbouring blocks still read this step's error units while this block
+// writes the next step's.
+template <int C>
+struct L0TailW {
+  float wa[9 * C * C];           // A-hat kernel [tap][ci][co]
+  float ba[C];
+};
+constexpr int L0_KSTEPS_MAX = 4;   // ceil(9 * 2C / 16) for C <= 3
+
+__device__ __forceinline__ void mma_16816(float d[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// bfrag: [lane 32][K step][n tile 2][2] packed half2 B fragments of the e_0 slice of the gate kernel (tc_create);
+// bm: the layer-0 bias map re-ordered to [pixel][channel][gate i, f, c, o] (one 16-byte load per pixel and channel)
+#ifndef L0_MINB
+#define L0_MINB 3
+#endif
+template <int C>
+struct L0TailSmem {
+  static constexpr int TW = 32, TH = 16, EW = TW + 4, EH = TH + 4, RW = TW + 2, RH = TH + 2;
+  __half eh[EH][EW][8];          // e_0: 2C <= 8 channels per pixel (fp16 as stored)
+  float4 a0[RW * RH * C];        // bias map + G per (pixel, channel): the accumulators' initial values [i, f, c, o]
+  float c0[RW * RH * C];
+  float rt[C][RH][RW];           // r_0
+};
+
+template <int C>
+__global__ void __launch_bounds__(320, L0_MINB) l0_tail_kernel(const __half *__restrict__ xe_in, int cstride,
+                                                         const float *__restrict__ bm, const float *__restrict__ c0,
+                                                         const float *__restrict__ gr, const uint32_t *__restrict__ bfrag,
+                                                         const __grid_constant__ L0TailW<C> wb, float *__restrict__ out,
+                                                         int H, int W, float clip, const float *__restrict__ p0,
+                                                         __half *__restrict__ xe_out) {
+  using SM = L0TailSmem<C>;
+  constexpr int TW = SM::TW, TH = SM::TH, EW = SM::EW, EH = SM::EH, RW = SM::RW, RH = SM::RH, NT = 320;
+  constexpr int KS = (9 * 2 * C + 15) / 16;          // K steps
+  constexpr int MT = (RW * RH + 15) / 16;            // 16-pixel M tiles of the r_0 region
+  extern __shared__ __align__(16) uint8_t l0_smem[];
+  SM &sm = *reinterpret_cast<SM *>(l0_smem);
+  auto &rt = sm.rt;
+  const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- everything this block reads from global memory is requested up front (independent loads, many in flight
+  // per thread); the MMA / LSTM loop below then runs out of shared memory.
+  // (1) e_0 of the 36 x 20 region: one 16-byte load per pixel (the first 8 halves of its row; channels >= 2C are
+  // zero in X_0 and multiply zero weights)
+  for (int i = tid; i < EW * EH; i += NT) {
+    const int ey = i / EW, ex = i - ey * EW;
+    const int gy = y0 - 2 + ey, gx = x0 - 2 + ex;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      q = __ldg(reinterpret_cast<const uint4 *>(xe_in + (((long long)b * H + gy) * W + gx) * cstride));
+    *reinterpret_cast<uint4 *>(&sm.eh[ey][ex][0]) = q;
+  }
+  // (2) per (pixel, channel) of the 34 x 18 region: bias map + G (this pixel's parity block of the r_1-resolution
+  // convolution) and c(t=0).  (Measured: requesting all iterations' operands before the first store, or prefetching
+  // them a pass ahead in registers, does not shorten the kernel -- it runs at ~70 % of the L1 data pipe's wavefront
+  // rate, shared-memory operand reads of the MMAs and the sector-granular global accesses together.)
+  for (int i = tid; i < RW * RH * C; i += NT) {
+    const int p = i / C, ch = i - p * C;
+    const int ry = p / RW, rx = p - ry * RW;
+    const int gy = y0 - 1 + ry, gx = x0 - 1 + rx;
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float cv = 0.0f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const long long pix = (long long)gy * W + gx;
+      const float4 gq = __ldg(reinterpret_cast<const float4 *>(
+                                  gr + ((((long long)b * (H >> 1) + (gy >> 1)) * (W >> 1) + (gx >> 1)) * 4 +
+                                        ((gy & 1) * 2 + (gx & 1))) * (4 * C)) + ch);
+      const float4 bq = __ldg(reinterpret_cast<const float4 *>(bm) + pix * C + ch);   // [pixel][channel][i, f, c, o]
+      cv = __ldg(c0 + pix * C + ch);
+      v = make_float4(__fadd_rn(bq.x, gq.x), __fadd_rn(bq.y, gq.y), __fadd_rn(bq.z, gq.z), __fadd_rn(bq.w, gq.w));
+    }
+    sm.a0[i] = v;
+    sm.c0[i] = cv;
+  }
+  // this lane's B fragments and the shared-memory offsets of its A columns (k = 16 s + 2 t + 8 j, k = tap * 2C + ci)
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bf[KS][2][2];
+  int aoff[KS][2];
+#pragma unroll
+  for (int s_ = 0; s_ < KS; s_++) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(bfrag + ((lane * L0_KSTEPS_MAX + s_) * 2 + q) * 2));
+      bf[s_][q][0] = v.x;
+      bf[s_][q][1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int k = 16 * s_ + 2 * t + 8 * j;
+      const int tap = k / (2 * C), ci = k - tap * 2 * C;
+      aoff[s_][j] = (k < 9 * 2 * C) ? (((tap / 3) * EW + (tap % 3)) * 16 + ci * 2) : -1;
+    }
+  }
+  __syncthreads();
+  // ---- r_0 on the 34 x 18 region, 16 pixels per warp pass
+  const char *ebase = reinterpret_cast<const char *>(&sm.eh[0][0][0]);
+  for (int mt = warp; mt < MT; mt += NT / 32) {   // warp-uniform: mma.sync is warp-collective
+    int pr[2], pp[2];
+    bool ok[2];
+    float acc[2][4], cprev[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      int p = mt * 16 + g + 8 * r;
+      const bool inreg = p < RW * RH;
+      if (!inreg) p = RW * RH - 1;
+      pp[r] = p;
+      const int ry = p / RW, rx = p - ry * RW;
+      pr[r] = (ry * EW + rx) * 16;
+      const int py = y0 - 1 + ry, px = x0 - 1 + rx;
+      ok[r] = inreg && py >= 0 && py < H && px >= 0 && px < W;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      cprev[r] = 0.0f;
+      if (t < C) {
+        v = sm.a0[p * C + t];
+        cprev[r] = sm.c0[p * C + t];
+      }
+      acc[0][2 * r + 0] = v.x;   // n tile 0: columns (2t, 2t+1) = gates i, f of channel t
+      acc[0][2 * r + 1] = v.y;
+      acc[1][2 * r + 0] = v.z;   // n tile 1: gates c, o
+      acc[1][2 * r + 1] = v.w;
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < KS; s_++) {
+      uint32_t a[4];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          a[2 * j + r] = aoff[s_][j] >= 0 ? *reinterpret_cast<const uint32_t *>(ebase + pr[r] + aoff[s_][j]) : 0u;
+      mma_16816(acc[0], a[0], a[1], a[2], a[3], bf[s_][0][0], bf[s_][0][1]);
+      mma_16816(acc[1], a[0], a[1], a[2], a[3], bf[s_][1][0], bf[s_][1][1]);
+    }
+    if (t < C) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (mt * 16 + g + 8 * r < RW * RH) {
+          float rv = 0.0f;   // outside the image: Keras' zero padding of the A-hat convolution
+          if (ok[r]) {
+            const float gi = hsig(acc[0][2 * r]), gf = hsig(acc[0][2 * r + 1]);
+            const float gc = fast_tanh(acc[1][2 * r]), go = hsig(acc[1][2 * r + 1]);
+            const float c = __fadd_rn(__fmul_rn(gf, cprev[r]), __fmul_rn(gi, gc));
+            rv = __fmul_rn(go, fast_tanh(c));
+          }
+          const int ry = pp[r] / RW, rx = pp[r] - ry * RW;
+          rt[t][ry][rx] = rv;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- prediction = min(relu(conv3x3(r_0) + b), pixel_max) and the next step's error units
+  for (int i = tid; i < TW * TH; i += NT) {
+    const int ty = i / TW, tx = i - ty * TW;
+    const int y = y0 + ty, x = x0 + tx;
+    if (x >= W || y >= H) continue;
+    float acc[C];
+#pragma unroll
+    for (int co = 0; co < C; co++) acc[co] = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+        for (int ci = 0; ci < C; ci++) {
+          const float v = rt[ci][ty + ky][tx + kx];
+#pragma unroll
+          for (int co = 0; co < C; co++) acc[co] = fmaf(v, wb.wa[((ky * 3 + kx) * C + ci) * C + co], acc[co]);
+        }
+    const long long pix = ((long long)b * H + y) * W + x;
+    float *dst = out + pix * C;
+    __align__(16) __half ev[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) ev[j] = __float2half_rn(0.0f);
+#pragma unroll
+    for (int co = 0; co < C; co++) {
+      const float a = fminf(fmaxf(acc[co] + wb.ba[co], 0.0f), clip);
+      dst[co] = a;
+      const float ah = __ldg(p0 + ((long long)y * W + x) * C + co);
+      ev[co] = __float2half_rn(fmaxf(__fsub_rn(ah, a), 0.0f));
+      ev[C + co] = __float2half_rn(fmaxf(__fsub_rn(a, ah), 0.0f));
+    }
+    const uint4 lo = *reinterpret_cast<const uint4 *>(ev);
+    if (cstride >= 16)   // the whole 32-byte sector of the e_0 block (its upper half is padding and stays zero)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %5, %5, %5};" ::"l"(xe_out + pix * cstride), "r"(lo.x),
+                   "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(0u)
+                   : "memory");
+    else
+      *reinterpret_cast<uint4 *>(xe_out + pix * cstride) = lo;
+  }
+}
+
 __global__ void f32_to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(src[i]);
@@ -1128,6 +1317,11 @@ struct TcState {
   int cxr;
   float *gr;                  // G: [maxB, H_1, W_1, 4 parities, R_0, 4 gates] fp32
   tz::ConvTc rconv0;          // r_1 -> G (raw epilogue)
+  __half *X0b;                // second X_0 buffer: the layer-0 tail kernel reads one and writes the other
+  tz::ConvTc aconv0_alt;      // a_0 reading X0b
+  int x0_cur;                 // which of X[0] / X0b holds the current step's error units
+  uint32_t *l0_bfrag;         // layer-0 tail kernel: B fragments of the e_0 slice of the gate kernel (per lane)
+  float *l0_bm;               // BM_0 as [pixel][channel][gate]
   tz::ConvTc aconv[TZ_MAX_LAYERS];   // l = 0..L-2
   tz::ConvTc gconv[TZ_MAX_LAYERS];   // l = 0..L-1
   int sm_count;
@@ -1461,10 +1655,12 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   // the NUMBER of K16 slabs, and 27 of the 36 slabs per tile come from up(r_1).  A 3x3 convolution over a
   // nearest-neighbour up-sampled image is, for each of the four output parities, a convolution over the
   // low-resolution image with pre-summed taps (prednet.py:250-258 with UpSampling2D): those 27 slabs per 128 pixels
-  // become one convolution at r_1's resolution with 4 x 4R_0 output columns (36 slabs per 512 pixels), whose raw
-  // accumulators G are added in the layer-0 LSTM epilogue like the bias map.  r_1 is then never written up-sampled
-  // and X_0 holds only the 32-byte e_0 block.
-  T->use_gr = L >= 2 && 16 * h->R[0] <= 256 && !getenv("TZ_NO_GR");
+  // become one tcgen05 convolution at r_1's resolution with 4 x 4R_0 output columns (36 slabs per 512 pixels,
+  // `rconv0`, raw fp32 accumulators G).  What remains of layer 0 -- the e_0 half of the gates (K = 54), + bias map
+  // + G, the LSTM, the A-hat_0 convolution and the next step's error units -- is one kernel (l0_tail_kernel).  r_1
+  // is never written up-sampled and X_0 holds only the 32-byte e_0 block (double-buffered).  Used when S_0 = R_0 is 1
+  // or 3 (every net the reference builds); other nets keep the generic kernels.
+  T->use_gr = L >= 2 && h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && !getenv("TZ_NO_GR");
   for (int l = 0; l < L; l++) {
     TZ_REQUIRE(h->H[l] % 2 == 0 || l == L - 1, "tensor-core path: odd layer height");
     T->epad[l] = round_up(2 * h->S[l], 16);   // 32-byte aligned r_up block
@@ -1483,6 +1679,10 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     T->gr = (float *)dev_alloc(h, px1 * 16 * h->R[0] * sizeof(float));
     if (!T->rlow || !T->gr) return TZ_ENOMEM;
     TZ_CHECK_CUDA(cudaMemset(T->rlow, 0, px1 * T->cxr * sizeof(__half)));
+    const size_t xb = (size_t)mb * h->H[0] * h->W[0] * T->cx[0] * sizeof(__half);
+    T->X0b = (__half *)dev_alloc(h, xb);
+    if (!T->X0b) return TZ_ENOMEM;
+    TZ_CHECK_CUDA(cudaMemset(T->X0b, 0, xb));
   }
   if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1)) {
     const int C = h->S[0];
@@ -1492,6 +1692,10 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(l0_tail_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(L0TailSmem<3>)));
+  TZ_CHECK_CUDA(cudaFuncSetAttribute(l0_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(L0TailSmem<1>)));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   TZ_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
 
@@ -1502,13 +1706,17 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     for (int i = 0; i < 2 * h->S[l]; i++) gmap[i] = h->R[l] + i;                                  // e_l
     if (r_in_x)
       for (int i = 0; i < h->R[l + 1]; i++) gmap[T->epad[l] + i] = h->R[l] + 2 * h->S[l] + i;    // up(r_{l+1})
-    int rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
-    if (rc) return rc;
+    int rc = TZ_OK;
+    const bool tail0 = l == 0 && T->use_gr;   // layer-0 gates: r_1 half on the tensor core (rconv0), the rest in l0_tail_kernel
+    if (!tail0) {
+      rc = make_conv(h, &T->gconv[l], 1, l, T->X[l], T->cx[l], gmap, wg_host[l], h->cin_g[l], 4 * h->R[l], h->R[l]);
+      if (rc) return rc;
+    }
     ConvArgs &G = T->gconv[l].args;
     G.bm = h->BM[l];
     G.bm_packed = 0;
     G.c0 = h->C0[l];
-    if (G.NC % 8 == 0 && h->R[l] % 8 == 0) {
+    if (!tail0 && G.NC % 8 == 0 && h->R[l] % 8 == 0) {
       const long long npix = (long long)h->H[l] * h->W[l];
       float *bp = (float *)dev_alloc(h, (size_t)npix * 4 * h->R[l] * sizeof(float));
       if (!bp) return TZ_ENOMEM;
@@ -1558,8 +1766,48 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       if (rc) return rc;
       T->rconv0.args.g_out = T->gr;
       T->rconv0.args.g_cols = cols;
-      G.gr = T->gr;
-      G.gr_cols = cols;
+      // e_0 slice of the gate kernel as m16n8k16 B fragments (l0_tail_kernel): k = tap * 2 S_0 + ci; column
+      // 8 q + 2 t' + u = gate (2 q + u) of channel t'.  Lane (g, t) holds b0 = (k, k + 1) and b1 = (k + 8, k + 9)
+      // with k = 16 s + 2 t, for column n = 8 q + g.
+      {
+        const int KC2 = 2 * h->S[0];
+        std::vector<uint32_t> bf((size_t)32 * L0_KSTEPS_MAX * 2 * 2, 0u);
+        auto wval = [&](int k, int col) -> float {
+          if (k >= 9 * KC2) return 0.0f;
+          const int tap = k / KC2, ci = k - tap * KC2;
+          const int q = col >> 3, tp = (col & 7) >> 1, u = col & 1;
+          if (tp >= R0) return 0.0f;
+          const int gate = 2 * q + u;
+          return wg_host[0][((size_t)tap * cin + R0 + ci) * 4 * R0 + gate * R0 + tp];
+        };
+        auto pack = [&](float lo, float hi) -> uint32_t {
+          const __half2 v = __floats2half2_rn(lo, hi);
+          uint32_t u;
+          memcpy(&u, &v, 4);
+          return u;
+        };
+        for (int lane = 0; lane < 32; lane++)
+          for (int s_ = 0; s_ < L0_KSTEPS_MAX; s_++)
+            for (int q = 0; q < 2; q++) {
+              const int gq = lane >> 2, tq = lane & 3, k = 16 * s_ + 2 * tq, col = 8 * q + gq;
+              uint32_t *dst = &bf[((size_t)(lane * L0_KSTEPS_MAX + s_) * 2 + q) * 2];
+              dst[0] = pack(wval(k, col), wval(k + 1, col));
+              dst[1] = pack(wval(k + 8, col), wval(k + 9, col));
+            }
+        T->l0_bfrag = (uint32_t *)dev_alloc(h, bf.size() * sizeof(uint32_t));
+        if (!T->l0_bfrag) return TZ_ENOMEM;
+        TZ_CHECK_CUDA(cudaMemcpy(T->l0_bfrag, bf.data(), bf.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // BM_0 [pixel][gate][channel] -> [pixel][channel][gate]
+        const size_t npix = (size_t)h->H[0] * h->W[0];
+        std::vector<float> bsrc(npix * 4 * R0), bdst(npix * 4 * R0);
+        TZ_CHECK_CUDA(cudaMemcpy(bsrc.data(), h->BM[0], bsrc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t px = 0; px < npix; px++)
+          for (int g = 0; g < 4; g++)
+            for (int ch = 0; ch < R0; ch++) bdst[(px * R0 + ch) * 4 + g] = bsrc[(px * 4 + g) * R0 + ch];
+        T->l0_bm = (float *)dev_alloc(h, bdst.size() * sizeof(float));
+        if (!T->l0_bm) return TZ_ENOMEM;
+        TZ_CHECK_CUDA(cudaMemcpy(T->l0_bm, bdst.data(), bdst.size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
     }
     if (l < L - 1) {
       // a conv: reads channels [0, 2S_l) of X_l
@@ -1575,10 +1823,22 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
       Aa.xe_out = T->X[l + 1];
       Aa.xe_cstride = T->cx[l + 1];
       Aa.S_next = h->S[l + 1];
+      if (tail0) {   // the same convolution reading the other X_0 buffer
+        rc = make_conv(h, &T->aconv0_alt, 0, l, T->X0b, T->cx[l], amap, wa, 2 * h->S[l], h->S[l + 1], h->S[l + 1]);
+        if (rc) return rc;
+        ConvArgs &Ab = T->aconv0_alt.args;
+        Ab.bias = Aa.bias;
+        Ab.ahat_next = Aa.ahat_next;
+        Ab.xe_out = Aa.xe_out;
+        Ab.xe_cstride = Aa.xe_cstride;
+        Ab.S_next = Aa.S_next;
+      }
     }
   }
   return TZ_OK;
 }
+
+bool tc_layer0_split(tz_prednet *h) { return h->tc && h->tc->use_gr; }
 
 void tc_destroy(tz_prednet *h) {
   delete h->tc;
@@ -1653,33 +1913,51 @@ int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, 
   const int L = h->L;
   int ne = 0;
   h->x0_staged = false;
+  __half *x0_now = (T->use_gr && T->x0_cur) ? T->X0b : T->X[0];
   if (ev) cudaEventRecord(ev[ne++], st);
   if (skip_e0) {
     if (ev) cudaEventRecord(ev[ne++], st);
   } else {
     const int C = h->S[0];
     long long total = (long long)B * h->H[0] * h->W[0] * C;
-    e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], T->X[0], total,
+    e0_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, h->Ahat0[0], x0_now, total,
                                                                  (long long)h->H[0] * h->W[0] * C, C, T->cx[0]);
     TZ_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[ne++], st);
   }
   for (int l = 0; l < L - 1; l++) {
-    int rc = launch_conv(T, &T->aconv[l], B, st);
+    int rc = launch_conv(T, (l == 0 && T->use_gr && T->x0_cur) ? &T->aconv0_alt : &T->aconv[l], B, st);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[ne++], st);
   }
   for (int l = L - 1; l >= 0; l--) {
-    if (l == 0 && T->use_gr) {   // r_1 -> G first (timed together with the layer-0 gates)
-      int rc = launch_conv(T, &T->rconv0, B, st);
-      if (rc) return rc;
-    }
-    int rc = launch_conv(T, &T->gconv[l], B, st);
+    int rc = launch_conv(T, (l == 0 && T->use_gr) ? &T->rconv0 : &T->gconv[l], B, st);   // layer 0: r_1 -> G
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[ne++], st);
   }
   int rc = TZ_OK;
-  if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
+  if (T->use_gr) {
+    // the rest of layer 0 in one CUDA-core kernel: e_0 half of the gates + G + LSTM + A-hat_0 + next e_0
+    TZ_REQUIRE(B <= 65535, "tensor-core path: at most 65535 frames per step");
+    __half *x0_next = T->x0_cur ? T->X[0] : T->X0b;
+    dim3 grid((h->W[0] + 31) / 32, (h->H[0] + 15) / 16, B);
+    if (h->S[0] == 3) {
+      L0TailW<3> wb;
+      memcpy(wb.wa, T->ahat0_w, sizeof(wb.wa));
+      memcpy(wb.ba, T->ahat0_b, sizeof(wb.ba));
+      l0_tail_kernel<3><<<grid, 320, sizeof(L0TailSmem<3>), st>>>(x0_now, T->cx[0], T->l0_bm, h->C0[0], T->gr, T->l0_bfrag, wb, out, h->H[0],
+                                              h->W[0], h->cfg.pixel_max, h->Ahat0[0], x0_next);
+    } else {
+      L0TailW<1> wb;
+      memcpy(wb.wa, T->ahat0_w, sizeof(wb.wa));
+      memcpy(wb.ba, T->ahat0_b, sizeof(wb.ba));
+      l0_tail_kernel<1><<<grid, 320, sizeof(L0TailSmem<1>), st>>>(x0_now, T->cx[0], T->l0_bm, h->C0[0], T->gr, T->l0_bfrag, wb, out, h->H[0],
+                                              h->W[0], h->cfg.pixel_max, h->Ahat0[0], x0_next);
+    }
+    TZ_CHECK_LAUNCH();
+    T->x0_cur ^= 1;
+    h->x0_staged = true;
+  } else if (h->R[0] == h->S[0] && (h->S[0] == 3 || h->S[0] == 1) && B <= 65535) {
     dim3 grid((h->W[0] + 31) / 32, (h->H[0] + 15) / 16, B);
     if (h->S[0] == 3) {
       Ahat0W<3> wb;

@@ -477,11 +477,23 @@ int tz_prednet_kernel_info(tz_prednet *h, int i, char *name, int name_len, doubl
     fl = 2.0 * h->H[l] * h->W[l] * 9.0 * 2 * h->S[l] * h->S[l + 1];
   } else if (i <= 2 * L - 1) {
     int l = L - 1 - (i - L);
-    snprintf(name, name_len, "conv_tc_gates%d", l);
     fl = 2.0 * h->H[l] * h->W[l] * 9.0 * h->cin_g[l] * 4 * h->R[l];
+    if (l == 0 && tc_layer0_split(h)) {
+      // layer 0 is split: its up(r_1) half runs on the tensor core at r_1's resolution (this launch); the e_0 half,
+      // the LSTM, A-hat_0 and the next step's error units are the "l0_tail" launch
+      snprintf(name, name_len, "conv_tc_gates0_r1half");
+      fl = 2.0 * h->H[0] * h->W[0] * 9.0 * h->R[1] * 4 * h->R[0];
+    } else {
+      snprintf(name, name_len, "conv_tc_gates%d", l);
+    }
   } else {
-    snprintf(name, name_len, "ahat0");
     fl = 2.0 * h->H[0] * h->W[0] * 9.0 * h->R[0] * h->S[0];
+    if (tc_layer0_split(h)) {
+      snprintf(name, name_len, "l0_tail");
+      fl += 2.0 * h->H[0] * h->W[0] * 9.0 * (h->cin_g[0] - h->R[1]) * 4 * h->R[0];
+    } else {
+      snprintf(name, name_len, "ahat0");
+    }
   }
   *flops_per_frame = fl;
   return TZ_OK;

@@ -64,6 +64,7 @@ int lstm_direct(const float *pre, const float *c_prev, float *r_out, float *c_ou
 // tensor-core path (tz_conv_tc.cu)
 int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &w_host);
 void tc_destroy(tz_prednet *h);
+bool tc_layer0_split(tz_prednet *h);   // layer 0 runs as conv(r_1) at r_1's resolution + the fused tail kernel
 // skip_e0: X_0 already holds the error units of `in` (staged by the previous step's ahat0 kernel)
 int tc_next(tz_prednet *h, const float *in, float *out, int B, cudaStream_t st, cudaEvent_t *ev = nullptr,
             bool skip_e0 = false);
