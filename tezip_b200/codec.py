@@ -386,7 +386,10 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
         keys, pred_slot_np, apply_np = plan.keys, plan.pred_slot, plan.apply_eb
         # the schedule is static: upload it and emit the key plane before the first PredNet step is queued, so that
-        # nothing on the host waits behind the predictions and the key plane's D2H copy runs under them
+        # nothing on the host waits behind the predictions and the key plane's D2H copy runs under them.  (Queuing
+        # this behind the first PredNet step instead -- the GPU then never waits for these small launches -- was
+        # measured: +0.4 % with device-resident frames, but -8 % through the host-buffer API, where the flag copies
+        # then sit in the copy queue behind the frames still being uploaded.)
         staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink, plan)
         run_plan(net, frames, plan, pool)
         if frames_ready is not None:   # the non-key frames were still in flight (upload_frames); the residual needs them
@@ -446,9 +449,18 @@ def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
     # the key plane and two tiny asynchronous copies; encode_with_pool looks at the answer once everything is queued.
     nz = ops.frames_nonzero(key_plane)
     nz_host, ik_host = _flag_scratch(dev, nt)     # cached pinned buffers: consumed by check_key_frames() in this call
-    nz_host.copy_(nz, non_blocking=True)
-    ik_host.copy_(is_key, non_blocking=True)
-    return pred_slot, apply, key_plane, (nz_host, ik_host, torch.cuda.current_stream(dev).record_event())
+    # The two flag copies run on the device->host side stream, never on the compute stream: in streaming use
+    # (encode_frames_host(wait_copies=False)) the previous sequence's 123 MB stream may still be draining through the
+    # same copy engine, and a copy queued on the compute stream would hold back every PredNet kernel behind it.
+    main, out = torch.cuda.current_stream(dev), side_stream(dev)
+    out.wait_event(main.record_event())
+    with torch.cuda.stream(out):
+        nz_host.copy_(nz, non_blocking=True)
+        ik_host.copy_(is_key, non_blocking=True)
+        done = out.record_event()
+    nz.record_stream(out)
+    is_key.record_stream(out)
+    return pred_slot, apply, key_plane, (nz_host, ik_host, done)
 
 
 def check_key_frames(staged):
