@@ -667,7 +667,7 @@ def run_native(args):
     achieved = kern[dom]["tflops"]
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same B, same shape)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
         if Bk == 100 and nt == 1000:
             traffic = tj["per_launch_dram_bytes"].get(kern[dom]["kernel"])
@@ -684,7 +684,7 @@ def run_native(args):
                 "frac_algorithmic_vs_sustained": achieved / pk["tf_sustained"], "peak_sustained": pk["tf_sustained"],
                 "traffic": traffic,
                 "traffic_source": "static: DRAM bytes per launch from the committed ncu --set full capture of this "
-                                  "command (profiles/r1_traffic.json, same B and shape); not re-measured in this run",
+                                  "command (profiles/r2_traffic.json, same B and shape); not re-measured in this run",
                 "flops_convention": "achieved = algorithmic FLOPs of SURVEY.md 8(d); frac = executed FLOPs / burst peak",
                 "peak_source": "%s cuBLAS bf16 dense burst (fp16 operands run at the same rate)" % pk["src"],
                 "launch_ms": kern[dom]["ms"], "share_of_next": kern[dom]["ms"] / total_ms,

@@ -178,3 +178,42 @@ def test_config4_frame_shape_roundtrip(cuda_lib):
     out, _ = codec.decode_arrays(enc.key_plane, enc.body, enc.table, enc.shape, 0, net)
     assert torch.equal(out.view(torch.int16), fr.view(torch.int16))
     net.close()
+
+
+def test_fused_stream_and_decoder_across_2_31_elements(cuda_lib):
+    """BASELINE config 4 is 5.2e9 samples: stream offsets pass 2^31 (frame 2048 of a 1024x1024x1 sequence) and 2^32.
+    The fused lossless kernels (frames + predictions -> delta stream, no materialised residual) and the decoder are
+    checked against plain torch arithmetic around the 2^31 mark, where a narrowed 32-bit remainder once produced one
+    wrong delta (and with it a constant offset in every later frame)."""
+    import torch
+    from tezip_b200 import ops
+    dev = torch.device("cuda", 0)
+    free, _total = torch.cuda.mem_get_info(dev)
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs 40 GB of free device memory")
+    nt, H, W = 2051, 1024, 1024
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    frames = torch.randint(0, 65536, (nt, H, W, 1), generator=g, device=dev, dtype=torch.int32).to(torch.uint16)
+    pool = torch.rand((8, H, W, 1), generator=g, device=dev, dtype=torch.float32)
+    slot = (torch.arange(nt, device=dev, dtype=torch.int32) % 9) - 1          # -1 = window start, else pool slot
+    y = torch.empty(nt * H * W, dtype=torch.int32, device=dev)
+    ops.encode16(frames, pool, slot, None, 1, lut=None, out=y)                # fused path, raw delta stream
+
+    def x_of(f):                                                              # compress.py:293-314, 16-bit constants
+        s = int(slot[f])
+        if s < 0:
+            return torch.zeros(H * W, dtype=torch.int32, device=dev)
+        return (pool[s].view(-1) * 65535.0).trunc().to(torch.int32) - frames[f].view(-1).to(torch.int32)
+
+    for f in (2047, 2048, 2049):                                              # element 2^31 is the first of frame 2048
+        xp, xc = x_of(f - 1), x_of(f)
+        want = torch.cat([xp[-1:], xc[:-1]]) - xc                             # y[i] = x[i-1] - x[i] (compress.py:75)
+        got = y[f * H * W:(f + 1) * H * W]
+        assert torch.equal(got, want), "delta stream differs in frame %d" % f
+    # and back: the decoder's prefix scan + reconstruction over the same offsets
+    key_plane = frames.clone()
+    key_plane.view(torch.int16)[slot >= 0] = 0                                # compress.py:183: key frames only
+    out = ops.reconstruct(y, (nt, H, W, 1), H, W, -1, None, pool, slot, key_plane)
+    for f in (0, 1, 2046, 2047, 2048, 2049, 2050):
+        assert torch.equal(out[f].view(torch.int16), frames[f].view(torch.int16)), "decoded frame %d differs" % f

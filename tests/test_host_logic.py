@@ -236,3 +236,35 @@ def test_zstd_decoder_refuses_absurd_declared_sizes(monkeypatch):
     monkeypatch.setenv("TEZIP_MAX_DECODED_BYTES", "1000")
     with pytest.raises(RuntimeError):
         container.zstd_decompress(blob)
+
+
+def test_run_plan_arrival_ranges_cover_the_sequence_in_order():
+    """Streaming loader (compress.run): before each group of windows run_plan asks for the frames that group needs;
+    the requests are contiguous, in order, and cover [0, nt) -- checked with a stand-in predictor (no GPU)."""
+    import torch
+
+    class FakeNet:
+        max_batch, Hp, Wp = 3, 8, 8
+
+        def p0(self, out):
+            pass
+
+        def next(self, x, out):
+            pass
+
+        def next_chained(self, out):
+            pass
+
+    real = codec.ops.pad_normalize
+    codec.ops.pad_normalize = lambda frames, idx, Hp, Wp: torch.zeros((len(idx), 8, 8, 3))
+    try:
+        for nt, p, w, want in ((25, 0, 5, [(0, 15), (15, 25)]), (23, 2, 5, [(0, 17), (17, 23)]), (7, 0, 10, [(0, 7)]),
+                               (30, 0, 3, [(0, 9), (9, 18), (18, 27), (27, 30)])):
+            calls = []
+            plan = codec.plan_from_keys(nt, p, codec.swp_keys(nt, p, w))
+            pool = torch.zeros((plan.n_slots, 8, 8, 3))
+            codec.run_plan(FakeNet(), torch.zeros((nt, 8, 8, 3), dtype=torch.uint8), plan, pool,
+                           lambda a, b: calls.append((a, b)))
+            assert calls == want
+    finally:
+        codec.ops.pad_normalize = real

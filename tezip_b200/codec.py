@@ -110,19 +110,32 @@ def _plan_dev(plan, device, name, make):
     return t
 
 
-def run_plan(net, frames, plan, pool):
+def run_plan(net, frames, plan, pool, arrive=None):
     """Fills pool[1:] with the predictions of every non-key frame; pool[0] = P0.
+    arrive(a, b): optional, called before a group of windows is started with the frame range [a, b) that must be on
+    the device by then (streaming loader, compress.run): ranges are contiguous and cover [0, nt) in order.
 
     Windows are independent, so they are taken in groups of at most net.max_batch (in the plan's length-sorted
     order): a group runs all of its lock-steps back to back, the first from the key frames, every later one as a
     chained step on the previous prediction (its live windows are a prefix of the previous step's)."""
     net.p0(out=pool[0])
     if not plan.steps:
+        if arrive is not None:
+            arrive(0, plan.nt)
         return
     mb = net.max_batch
     key_idx_all, _slot0, B1 = plan.steps[0]
+    done = 0
     for g0 in range(0, B1, mb):
         g1 = min(g0 + mb, B1)
+        if arrive is not None:
+            # the group's windows in stream order end at the largest (first + length); everything before that is
+            # requested now (windows are sorted by length, so for equal windows this is simply the next range)
+            mine = set(int(v) for v in key_idx_all[g0:g1])
+            end = plan.nt if g1 == B1 else max(f + n for f, n in plan.windows if f in mine)
+            if end > done:
+                arrive(done, end)
+                done = end
         idx = _plan_dev(plan, frames.device, ("key_idx", g0, g1),
                         lambda: torch.from_numpy(np.ascontiguousarray(key_idx_all[g0:g1])))
         x = ops.pad_normalize(frames, idx, net.Hp, net.Wp)                  # compress.py:219 / decompress.py:161
@@ -135,6 +148,8 @@ def run_plan(net, frames, plan, pool):
                 net.next(x[:nb], out=out)                                   # compress.py:222-229
             else:
                 net.next_chained(out)
+    if arrive is not None and done < plan.nt:
+        arrive(done, plan.nt)
 
 
 def run_dwp(net, frames, p, threshold, pool, n_chains=1, window=None, shard=False):
@@ -362,7 +377,7 @@ def pool_slots_upper_bound(nt):
 
 
 def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
-                  keep_x=False, comm=None, sink=None, frames_ready=None):
+                  keep_x=False, comm=None, sink=None, frames_ready=None, arrive=None):
     """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
 
     comm: optional shard communicator (tezip_b200/dist.py) when `frames` is one rank's window-aligned shard of a
@@ -390,8 +405,14 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         # this behind the first PredNet step instead -- the GPU then never waits for these small launches -- was
         # measured: +0.4 % with device-resident frames, but -8 % through the host-buffer API, where the flag copies
         # then sit in the copy queue behind the frames still being uploaded.)
-        staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink, plan)
-        run_plan(net, frames, plan, pool)
+        if arrive is None:
+            staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink, plan)
+            run_plan(net, frames, plan, pool)
+        else:
+            # streaming loader: `frames` fills up group by group (arrive(a, b) uploads [a, b)); the key plane needs
+            # every key frame, so the schedule is staged after the last group has been queued
+            run_plan(net, frames, plan, pool, arrive)
+            staged = stage_plan(frames, keys, pred_slot_np, apply_np, sink, plan)
         if frames_ready is not None:   # the non-key frames were still in flight (upload_frames); the residual needs them
             torch.cuda.current_stream(dev).wait_event(frames_ready)
     else:

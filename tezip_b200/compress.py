@@ -28,29 +28,38 @@ def io_workers():
     return max(1, int(env)) if env else max(1, min(32, os.cpu_count() or 1))
 
 
-def load_images(DATA_DIR, workers=None, paths=None):
-    """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB.
-    16-bit grayscale images (PIL mode I;16 -- the reference stops at compress.py:106-110) -> u16 [nt,H,W,1], written
-    as a version-2 container.  One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
-    pool, so the array goes to the GPU with one asynchronous copy (SURVEY.md 8(f) rank 2)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from PIL import Image, UnidentifiedImageError
-    file_paths = list(paths) if paths is not None else sorted(glob.glob(os.path.join(DATA_DIR, '*')))
-    if len(file_paths) == 0:
-        _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
-    try:
-        first = Image.open(file_paths[0])
-        image_mode = first.mode
-        wide = image_mode in ('I;16', 'I;16L')
-        if image_mode not in ('RGB', 'L') and not wide:
-            _die("ERROR: input image is {0}. Only RGB and grayscale are supported.".format(image_mode))
-        isRGB = image_mode == 'RGB'
-        w, h = first.size
+class SequenceLoader:
+    """compress.py:97-131 as a stream: the images are decoded IN ORDER by a thread pool into one pinned buffer while
+    the caller already works on the frames that have arrived (`wait(a, b)` blocks until frames [a, b) are decoded).
+    The reference decodes the whole sequence before its first prediction; here the GPU starts on the first group of
+    windows as soon as its frames are there."""
+
+    def __init__(self, DATA_DIR, workers=None, paths=None):
+        from concurrent.futures import ThreadPoolExecutor
+        from PIL import Image, UnidentifiedImageError
+        self.dir = DATA_DIR
+        self.errors = (PermissionError, IndexError, UnidentifiedImageError, IsADirectoryError, ValueError)
+        file_paths = list(paths) if paths is not None else sorted(glob.glob(os.path.join(DATA_DIR, '*')))
+        if len(file_paths) == 0:
+            _die("ERROR:", DATA_DIR, "is an empty or non-existent directory")
+        self.paths = file_paths
+        self.files = [os.path.basename(path) for path in file_paths]
+        try:
+            first = Image.open(file_paths[0])
+            image_mode = first.mode
+            wide = image_mode in ('I;16', 'I;16L')
+            if image_mode not in ('RGB', 'L') and not wide:
+                _die("ERROR: input image is {0}. Only RGB and grayscale are supported.".format(image_mode))
+            self.isRGB = isRGB = image_mode == 'RGB'
+            w, h = first.size
+        except self.errors:
+            _die(DATA_DIR, "contains files or folders that are not images.")
         buf = torch.empty((len(file_paths), h, w, 1), dtype=torch.uint16) if wide else \
             torch.empty((len(file_paths), h, w, 3), dtype=torch.uint8)
         if torch.cuda.is_available():
             buf = buf.pin_memory()
-        frames = buf.numpy()
+        self.tensor = buf
+        self.frames = frames = buf.numpy()
 
         def decode(i):
             img = Image.open(file_paths[i])
@@ -61,12 +70,30 @@ def load_images(DATA_DIR, workers=None, paths=None):
             else:
                 frames[i] = np.asarray(img if isRGB else img.convert('RGB'))    # shape mismatch -> ValueError
 
-        with ThreadPoolExecutor(workers or io_workers()) as pool:
-            list(pool.map(decode, range(len(file_paths))))
-        files = [os.path.basename(path) for path in file_paths]
-    except (PermissionError, IndexError, UnidentifiedImageError, IsADirectoryError, ValueError):
-        _die(DATA_DIR, "contains files or folders that are not images.")
-    return frames, files, isRGB
+        self.pool = ThreadPoolExecutor(workers or io_workers())
+        self.futures = [self.pool.submit(decode, i) for i in range(len(file_paths))]   # FIFO: decoded in order
+
+    def wait(self, a=0, b=None):
+        try:
+            for f in self.futures[a:b]:
+                f.result()
+        except self.errors:
+            self.close()
+            _die(self.dir, "contains files or folders that are not images.")
+
+    def close(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)
+
+
+def load_images(DATA_DIR, workers=None, paths=None):
+    """compress.py:97-131: sorted glob, RGB or L (converted to RGB) -> u8 [nt,H,W,3], basenames, isRGB.
+    16-bit grayscale images (PIL mode I;16 -- the reference stops at compress.py:106-110) -> u16 [nt,H,W,1], written
+    as a version-2 container.  One pinned allocation for the whole sequence (the reference hstacks frame by frame, O(nt^2)) filled by a thread
+    pool, so the array goes to the GPU with one asynchronous copy (SURVEY.md 8(f) rank 2)."""
+    loader = SequenceLoader(DATA_DIR, workers, paths)
+    loader.wait()
+    loader.close()
+    return loader.frames, loader.files, loader.isRGB
 
 
 def save_images(frames, file_names, isRGB, OUTPUT_DIR, workers=None):
@@ -167,16 +194,32 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, M
                            ENTROPY_RUN, zstd_workers, THRESHOLD, dwp_chains)
     if not os.path.exists(OUTPUT_DIR):
         os.mkdir(OUTPUT_DIR)
-    frames, files, isRGB = load_images(DATA_DIR)
+    loader = SequenceLoader(DATA_DIR)          # decoding starts now, in order, on the I/O threads
+    frames, files, isRGB = loader.frames, loader.files, loader.isRGB
     nt = frames.shape[0]
     n_win = max(1, (nt - PREPROCESS + (WINDOW_SIZE or nt) - 1) // (WINDOW_SIZE or nt)) if THRESHOLD is None \
         else max(1, dwp_chains)
-    net = load_predictor(WEIGHTS_DIR, max_batch=min(max(n_win, 1), 256))
+    # static windows: groups of STREAM_WINDOWS windows are predicted as their frames arrive (the weights load and the
+    # first groups' kernels overlap the decoding of the rest); dynamic windows scan the whole sequence
+    stream = THRESHOLD is None and nt > 0
+    group = int(os.environ.get("TEZIP_STREAM_WINDOWS", "32"))
+    net = load_predictor(WEIGHTS_DIR, max_batch=min(max(n_win, 1), group if stream else 256))
     try:
         t0 = time.time()
         dev = net.device
-        enc = codec.encode_frames(torch.from_numpy(frames).to(dev, non_blocking=True), net, PREPROCESS, WINDOW_SIZE,
-                                  THRESHOLD, MODE, list(BOUND_VALUE), ENTROPY_RUN, dwp_chains=dwp_chains)
+        if stream:
+            frames_dev = torch.empty(loader.tensor.shape, dtype=loader.tensor.dtype, device=dev)
+
+            def arrive(a, b):          # frames [a, b) are needed on the device now
+                loader.wait(a, b)
+                frames_dev[a:b].copy_(loader.tensor[a:b], non_blocking=True)
+            enc = codec.encode_frames(frames_dev, net, PREPROCESS, WINDOW_SIZE, None, MODE, list(BOUND_VALUE),
+                                      ENTROPY_RUN, arrive=arrive)
+        else:
+            loader.wait()
+            enc = codec.encode_frames(loader.tensor.to(dev, non_blocking=True), net, PREPROCESS, WINDOW_SIZE,
+                                      THRESHOLD, MODE, list(BOUND_VALUE), ENTROPY_RUN, dwp_chains=dwp_chains)
+        loader.close()
         payload = enc.payload()
         key_plane = enc.key_plane.cpu().numpy()
         torch.cuda.synchronize(dev)

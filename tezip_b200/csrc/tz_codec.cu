@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_reconstruct_kernel(
       P[0] = a.x & 0xff; P[1] = (a.x >> 8) & 0xff; P[2] = (a.x >> 16) & 0xff; P[3] = a.x >> 24;
       P[4] = a.y & 0xff; P[5] = (a.y >> 8) & 0xff; P[6] = (a.y >> 16) & 0xff; P[7] = a.y >> 24;
     } else {
-      int r = (int)(i0 - f * g.frame_elems);
+      int r = rem_in_frame(i0, f, g.frame_elems);
       int row = r / g.rowlen;
       int col = r - row * g.rowlen;
       const float4 *pp =
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_reconstruct_kernel(
         if (s < 0) {
           P = key_plane[i];
         } else {
-          int r = (int)(i - f * g.frame_elems);
+          int r = rem_in_frame(i, f, g.frame_elems);
           int row = r / g.rowlen;
           int col = r - row * g.rowlen;
           P = q255(pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col]);
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(256) pad_normalize_kernel(const uint8_t *__res
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long b = i / g.pframe_elems;
-    int r = (int)(i - b * g.pframe_elems);
+    int r = rem_in_frame(i, b, g.pframe_elems);
     int row = r / g.prow;
     int col = r - row * g.prow;
     float v = 0.0f;

@@ -26,13 +26,24 @@ static Geo make_geo(int H, int W, int C, int Hp, int Wp) {
 // compress.py:307,310-311: float32 product, then truncation toward zero.
 __device__ __forceinline__ int q255(float p) { return __float2int_rz(__fmul_rn(p, 255.0f)); }
 
+// i - f * d where 0 <= i - f * d < 2^31 (the offset of stream element i inside its frame), in UNSIGNED 32-bit
+// arithmetic.  Written as `(int)(i - f * d)` nvcc narrows the expression to 32-bit operations on the low words and
+// then widens the PARTS as if they were non-overflowing signed ints; when the low words of i and f * d lie on
+// different sides of 2^31 the pool address is off by 2^32 elements.  Seen at stream element 2^31 - 1 of a
+// 1024x1024x1 sequence (frame 2048): one wrong delta, and every later frame decoded with a constant offset.
+__device__ __forceinline__ int rem_in_frame(long long i, long long f, long long d) {
+  const unsigned int lo = (unsigned int)(unsigned long long)i;
+  const unsigned int fd = (unsigned int)((unsigned long long)f * (unsigned long long)d);
+  return (int)(lo - fd);
+}
+
 // compress.py:293-314 for one sample (generic addressing).
 __device__ __forceinline__ int resid_at(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
                                         const int32_t *__restrict__ slot, const Geo &g, long long i) {
   long long f = i / g.frame_elems;
   int s = slot[f];
   if (s < 0) return 0;
-  int r = (int)(i - f * g.frame_elems);
+  int r = rem_in_frame(i, f, g.frame_elems);
   int row = r / g.rowlen;
   int col = r - row * g.rowlen;
   float p = pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col];
@@ -53,7 +64,7 @@ __device__ __forceinline__ void resid8(const uint8_t *__restrict__ frames, const
       for (int k = 0; k < 8; k++) v[k] = 0;
       return;
     }
-    int r = (int)(i0 - f * g.frame_elems);
+    int r = rem_in_frame(i0, f, g.frame_elems);
     int row = r / g.rowlen;
     int col = r - row * g.rowlen;
     uint2 a = *reinterpret_cast<const uint2 *>(frames + i0);

@@ -27,7 +27,7 @@ __device__ __forceinline__ int resid16_at(const uint16_t *__restrict__ frames, c
   long long f = i / g.frame_elems;
   int s = slot[f];
   if (s < 0) return 0;
-  int r = (int)(i - f * g.frame_elems);
+  int r = rem_in_frame(i, f, g.frame_elems);
   int row = r / g.rowlen;
   int col = r - row * g.rowlen;
   float p = pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col];
@@ -46,7 +46,7 @@ __device__ __forceinline__ void resid16x8(const uint16_t *__restrict__ frames, c
       for (int k = 0; k < 8; k++) v[k] = 0;
       return;
     }
-    int r = (int)(i0 - f * g.frame_elems);
+    int r = rem_in_frame(i0, f, g.frame_elems);
     int row = r / g.rowlen;
     int col = r - row * g.rowlen;
     uint4 a = *reinterpret_cast<const uint4 *>(frames + i0);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode16_reconstruct_kernel(
       P[0] = a.x & 0xffff; P[1] = a.x >> 16; P[2] = a.y & 0xffff; P[3] = a.y >> 16;
       P[4] = a.z & 0xffff; P[5] = a.z >> 16; P[6] = a.w & 0xffff; P[7] = a.w >> 16;
     } else {
-      int r = (int)(i0 - f * g.frame_elems);
+      int r = rem_in_frame(i0, f, g.frame_elems);
       int row = r / g.rowlen;
       int col = r - row * g.rowlen;
       const float4 *pp =
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode16_reconstruct_kernel(
         if (s < 0) {
           P = key_plane[i];
         } else {
-          int r = (int)(i - f * g.frame_elems);
+          int r = rem_in_frame(i, f, g.frame_elems);
           int row = r / g.rowlen;
           int col = r - row * g.rowlen;
           P = q65535(pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col]);
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256) pad_normalize16_kernel(const uint16_t *__
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long b = i / g.pframe_elems;
-    int r = (int)(i - b * g.pframe_elems);
+    int r = rem_in_frame(i, b, g.pframe_elems);
     int row = r / g.prow;
     int col = r - row * g.prow;
     float v = 0.0f;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(1024) window_sse16_kernel(const uint16_t *__re
   double acc = 0.0;
   for (long long i = threadIdx.x; i < g.pframe_elems; i += 1024) {
     int row = (int)(i / g.prow);
-    int col = (int)(i - (long long)row * g.prow);
+    int col = rem_in_frame(i, row, g.prow);
     double a = 0.0;
     if (row < g.H && col < g.rowlen)
       a = (double)__fdiv_rn((float)frames[f * g.frame_elems + (long long)row * g.rowlen + col], 65535.0f);
