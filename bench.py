@@ -84,15 +84,35 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML from a thread every
+    5 ms (nvidia-smi -lms needs > 100 ms for its first line on an 8-GPU box -- longer than a short timed region), with
+    the nvidia-smi loop as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.samples, self.stop_flag = None, [], False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])          # CUDA ordinal -> NVML index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -102,11 +122,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(self.reasons_fn(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            nv = self.nvml
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [c for c, _r in self.samples]
+            reasons = sorted(nm for nm, bit in bits.items() if any(r & bit for _c, r in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -128,7 +170,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ================================================================================================ reference arm
