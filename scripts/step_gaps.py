@@ -25,10 +25,10 @@ def ev():
 def one():
     t = [time.perf_counter()]
     e = [ev()]
-    plan = codec.plan_from_keys(nt, 0, codec.swp_keys(nt, 0, W))
+    plan = codec.cached_plan(nt, 0, codec.swp_keys(nt, 0, W))
     pool = torch.empty((plan.n_slots, 128, 160, 3), dtype=torch.float32, device=dev)
     t.append(time.perf_counter()); e.append(ev())
-    staged = codec.stage_plan(frames, plan.keys, plan.pred_slot, plan.apply_eb, None)
+    staged = codec.stage_plan(frames, plan.keys, plan.pred_slot, plan.apply_eb, None, plan)
     t.append(time.perf_counter()); e.append(ev())
     codec.run_plan(net, frames, plan, pool)
     t.append(time.perf_counter()); e.append(ev())
