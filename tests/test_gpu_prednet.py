@@ -117,7 +117,10 @@ def test_chained_steps_bitwise(cuda_lib, direct):
                                          (FULL, 512, 512, 2),            # 16x the bench frame
                                          ((1, 16, 32, 64), 64, 96, 5),   # one channel (SURVEY 8(d) config 4 family)
                                          ((3, 24, 40), 48, 72, 7),       # three layers, widths not multiples of 16
-                                         ((3, 48, 96, 192), 128, 160, 37)])   # odd batch: ragged last CTA pair
+                                         ((3, 48, 96, 192), 128, 160, 37),    # odd batch: ragged last CTA pair
+                                         ((3, 32), 40, 56, 3),            # two layers: layer 1 is the top of the split
+                                         ((1, 48, 96, 192), 128, 128, 2),     # the config-4 net on a small frame
+                                         ((2, 16, 32), 32, 48, 3)])       # S_0 = 2: generic layer-0 kernels (no split)
 def test_tc_matches_oracle_more_shapes(cuda_lib, stack, H, W, B):
     import torch
     onet, ws = oracle_net(stack)
