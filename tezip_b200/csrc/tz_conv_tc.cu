@@ -219,6 +219,8 @@ struct ConvArgs {
   const float *ahat_next;        // [H/2, W/2, S_next]
   __half *xe_out;                // X_{l+1}: [B, H/2, W/2, xe_cstride], e written at channels [0, 2*S_next)
   int xe_cstride, S_next;
+  int perm16;                    // accumulator columns are permuted inside every group of 16 output channels so that a
+                                 // lane of the pooling epilogue ends with FOUR consecutive channels (8-byte stores)
   // --- R epilogue (LSTM)
   const float *bm;               // [H, W, 4R];  when bm_packed: [H, W, R/8, 4 gates, 8] (one 128-byte line per
                                  // thread and 8-channel chunk -> eight 16-byte loads of one cache line)
@@ -683,6 +685,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_real = P.S_next - nt * P.n_tile < P.n_tile ? P.S_next - nt * P.n_tile : P.n_tile;
         constexpr int PF = 6;
         const bool vec_ok = ((P.S_next | P.xe_cstride) & 7) == 0;
+        if (P.perm16) {
+          // Lane-balanced pooling over PAIRS of 8-channel chunks (columns [16k, 16k + 16)).  As below, the four lanes
+          // of a 2x2 window swap halves (xor 1 keeps 4 of a chunk's 8 columns, xor tile-width keeps 2), so a lane ends
+          // with the pooled maximum of columns (co, co + 1) of both chunks -- and the weight rows were packed so that
+          // these four columns are the four CONSECUTIVE channels 16k + 2co .. + 3 (make_conv): bias and A-hat arrive
+          // as one 16-byte load each, E+ and E- leave as one 8-byte store each.  The epilogue of the narrow layer-0
+          // convolution is bound by the L1 data pipe (shuffles + sector-granular stores), not by warps or issue
+          // slots; this halves its store wavefronts.
+          const int hm = 1 << P.tw_log;
+          const bool wbit = (lane & 1) != 0, hbit = (lane & hm) != 0;
+          const int co = (wbit ? 4 : 0) + (hbit ? 2 : 0);
+          const int npairs = n_real >> 4;
+          constexpr int PP = PF / 2;
+          float4 ahq[PP];
+#pragma unroll
+          for (int c = 0; c < PP; c++) {
+            const int k = part + c * nparts;
+            if (valid && k < npairs) ahq[c] = __ldg(reinterpret_cast<const float4 *>(ah + nt * P.n_tile + 16 * k + 2 * co));
+          }
+          auto finish_pair = [&](int k, const float *va, const float *vb, float4 aa) {
+            const int ch4 = nt * P.n_tile + 16 * k + 2 * co;
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias + ch4));
+            float ua[4], ub[4], z[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float sa = wbit ? va[q] : va[q + 4], ka = wbit ? va[q + 4] : va[q];
+              const float sb = wbit ? vb[q] : vb[q + 4], kb = wbit ? vb[q + 4] : vb[q];
+              ua[q] = fmaxf(ka, __shfl_xor_sync(0xffffffffu, sa, 1));
+              ub[q] = fmaxf(kb, __shfl_xor_sync(0xffffffffu, sb, 1));
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              const float sa = hbit ? ua[q] : ua[q + 2], ka = hbit ? ua[q + 2] : ua[q];
+              const float sb = hbit ? ub[q] : ub[q + 2], kb = hbit ? ub[q + 2] : ub[q];
+              z[q] = fmaxf(ka, __shfl_xor_sync(0xffffffffu, sa, hm));
+              z[2 + q] = fmaxf(kb, __shfl_xor_sync(0xffffffffu, sb, hm));
+            }
+            if (valid) {
+              const float a0 = fmaxf(__fadd_rn(z[0], bb.x), 0.0f), a1 = fmaxf(__fadd_rn(z[1], bb.y), 0.0f);
+              const float a2 = fmaxf(__fadd_rn(z[2], bb.z), 0.0f), a3 = fmaxf(__fadd_rn(z[3], bb.w), 0.0f);
+              const __half2 p0 = __floats2half2_rn(fmaxf(__fsub_rn(aa.x, a0), 0.0f), fmaxf(__fsub_rn(aa.y, a1), 0.0f));
+              const __half2 p1 = __floats2half2_rn(fmaxf(__fsub_rn(aa.z, a2), 0.0f), fmaxf(__fsub_rn(aa.w, a3), 0.0f));
+              const __half2 m0 = __floats2half2_rn(fmaxf(__fsub_rn(a0, aa.x), 0.0f), fmaxf(__fsub_rn(a1, aa.y), 0.0f));
+              const __half2 m1 = __floats2half2_rn(fmaxf(__fsub_rn(a2, aa.z), 0.0f), fmaxf(__fsub_rn(a3, aa.w), 0.0f));
+              uint2 up, dn;
+              up.x = *reinterpret_cast<const uint32_t *>(&p0);
+              up.y = *reinterpret_cast<const uint32_t *>(&p1);
+              dn.x = *reinterpret_cast<const uint32_t *>(&m0);
+              dn.y = *reinterpret_cast<const uint32_t *>(&m1);
+              *reinterpret_cast<uint2 *>(dst + ch4) = up;
+              *reinterpret_cast<uint2 *>(dst + P.S_next + ch4) = dn;
+            }
+          };
+#pragma unroll
+          for (int c = 0; c < PP; c++) {
+            const int k = part + c * nparts;
+            if (k < npairs) {   // warp-uniform
+              float va[8], vb[8];
+              tc_ld8(trow + 16 * k, va);
+              tc_ld8(trow + 16 * k + 8, vb);
+              tc_ld_wait();
+              finish_pair(k, va, vb, ahq[c]);
+            }
+          }
+          for (int k = part + PP * nparts; k < npairs; k += nparts) {   // more than PP pairs per warp
+            float4 a4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (valid) a4 = __ldg(reinterpret_cast<const float4 *>(ah + nt * P.n_tile + 16 * k + 2 * co));
+            float va[8], vb[8];
+            tc_ld8(trow + 16 * k, va);
+            tc_ld8(trow + 16 * k + 8, vb);
+            tc_ld_wait();
+            finish_pair(k, va, vb, a4);
+          }
+        } else
         if (vec_ok && ((P.H | P.W) & 1) == 0 && P.tw_log >= 1 && P.th_log >= 1) {
           // Lane-balanced pooling.  The four lanes of a 2x2 window swap halves instead of all computing everything
           // (transpose-reduce: xor 1 keeps 4 of the 8 channels, xor tile-width keeps 2), so each lane ends with the
@@ -1519,6 +1595,10 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
       set_error("unsupported channel count %d for the tensor-core path", n_real);
       return TZ_EINVAL;
     }
+    // pooling epilogue with 8-byte stores (conv_tc_kernel, EPI 0): whole groups of 16 channels per tile, even image
+    // and 8 x 16 or larger power-of-two tiles, a 32-byte aligned e block in X_{l+1}
+    A.perm16 = epi == 0 && (n_unit % 16) == 0 && (A.H % 2) == 0 && (A.W % 2) == 0 && A.tw_log >= 1 && A.th_log >= 1 &&
+               !getenv("TZ_NO_PERM16");
   }
   rows_total = A.n_tiles_n * A.n_tile;
   const int Ktot = 9 * A.cin_pad;
@@ -1532,7 +1612,14 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
         if (g < 4 && j < A.NC) src_col = g * n_real + nt * A.NC + j;
       } else {
         int per = n_real / A.n_tiles_n;
-        if (r < per) src_col = nt * per + r;
+        if (r < per) {
+          int ch = r;
+          if (A.perm16) {   // column r of the tile holds channel: chunk A (r % 16 < 8) -> 2 of every 4, chunk B the others
+            const int k16 = r >> 4, c16 = r & 15, c = c16 & 7;
+            ch = 16 * k16 + 2 * (c & ~1) + (c & 1) + (c16 >= 8 ? 2 : 0);
+          }
+          src_col = nt * per + ch;
+        }
       }
       if (src_col < 0) continue;
       float *dst = wp.data() + (size_t)(nt * A.n_tile + r) * Ktot;
@@ -1693,8 +1780,10 @@ int tc_create(tz_prednet *h, const std::vector<std::vector<float>> &wg_host) {
     if (!T->X[l]) return TZ_ENOMEM;
     TZ_CHECK_CUDA(cudaMemset(T->X[l], 0, bytes));   // pad channels multiply zero weights: they must stay finite
   }
-  T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
-  if (!T->r0) return TZ_ENOMEM;
+  if (!T->use_gr) {   // (with the layer-0 split r_0 never leaves the chip)
+    T->r0 = (float *)dev_alloc(h, (size_t)mb * h->H[0] * h->W[0] * h->R[0] * sizeof(float));
+    if (!T->r0) return TZ_ENOMEM;
+  }
   if (T->use_gr) {
     T->cxr = round_up(h->R[1], 64);
     const size_t px1 = (size_t)mb * h->H[1] * h->W[1];
