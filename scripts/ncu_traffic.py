@@ -17,8 +17,8 @@ def main(raw, out, note):
     def num(r, k):
         v, u = float(r[ix[k]].replace(",", "")), units[ix[k]]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
-    seq = [r for r in rows[2:] if any(s in r[ix["Kernel Name"]] for s in ("e0_tc_kernel", "conv_tc_kernel", "l0_tail"))]
-    start = next(i for i, r in enumerate(seq) if "e0_tc_kernel" in r[ix["Kernel Name"]])
+    seq = [r for r in rows[2:] if any(s in r[ix["Kernel Name"]] for s in ("e0_tc_kernel", "e0_px_kernel", "conv_tc_kernel", "l0_tail"))]
+    start = next(i for i, r in enumerate(seq) if ("e0_tc_kernel" in r[ix["Kernel Name"]] or "e0_px_kernel" in r[ix["Kernel Name"]]))
     seq = seq[start:start + len(ORDER)]
     per = {}
     for name, r in zip(ORDER, seq):
