@@ -32,3 +32,23 @@ def fused():
 
 
 print(os.environ.get("TAG", ""), "fused_lossy %.4f ms" % ev(fused), "| residual+eb %.4f" % ev(lambda: (ops.residual(fr, pool, slot, out=x), ops.error_bound(fr, x, apply_t, "abs", [2.0]))))
+
+# the stream kernels (delta + histogram, delta + rank map, fused lossless passes, decoder)
+N = nt * H * W * C
+ops.residual(fr, pool, slot, out=x)
+ops.error_bound(fr, x, apply_t, "abs", [2.0])
+hist = torch.zeros(_lib.TZ_HIST_BINS, dtype=torch.int64, device=dev)
+ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+lut = torch.from_numpy(ops.encode_lut(enc.table)).to(dev)
+obuf = torch.empty(N, dtype=torch.int16, device=dev)
+lut_d = torch.from_numpy(ops.decode_lut(enc.table)).to(dev)
+t = {
+    "delta_hist": ev(lambda: ops.finding_difference_hist(x, hist, ovf)),
+    "delta_rank": ev(lambda: ops.finding_difference_rank(x, lut, out=obuf)),
+    "lossless_hist": ev(lambda: ops.encode_lossless(fr, pool, slot, 0, hist=hist, overflow=ovf)),
+    "lossless_rank": ev(lambda: ops.encode_lossless(fr, pool, slot, 1, lut=lut, out=obuf)),
+    "reconstruct": ev(lambda: ops.reconstruct(enc.body, (nt, H, W, C), H, W, len(enc.table), lut_d, pool, slot,
+                                              enc.key_plane)),
+}
+bps = {"delta_hist": 2, "delta_rank": 4, "lossless_hist": 5, "lossless_rank": 7, "reconstruct": 7}
+print(os.environ.get("TAG", ""), " ".join("%s %.4f ms (%.0f GB/s)" % (k, v, bps[k] * N / v / 1e6) for k, v in t.items()))

@@ -661,10 +661,13 @@ def parse_payload(data):
     return data[:table_start], data[table_start:-1].copy(), shape, p
 
 
-def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0, body_event=None):
+def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0, body_event=None,
+                  nonzero=None):
     """decompress.py:115-256,269 on device tensors: key_plane u8 [nt,H,W,C], body int16 [N] -> u8 frames.
     body_event: optional CUDA event after which `body` is valid (its host->device copy may still be in flight on
-    another stream while the predictions are replayed; only the final reconstruct needs it)."""
+    another stream while the predictions are replayed; only the final reconstruct needs it).
+    nonzero: optional host u8[nt], the key-frame flags of decompress.py:123-127 when the caller has already computed
+    them (decode_arrays_host does, on its upload stream)."""
     _one, nt, H, W, C = shape
     dev = key_plane.device
     Hp, Wp = padding_size(H), padding_size(W)
@@ -673,7 +676,7 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
     if body.numel() != nt * H * W * C:
         raise TezipError("entropy.dat holds %d residuals, shape needs %d" % (body.numel(), nt * H * W * C))
     key_plane = key_plane.view(nt, H, W, C)
-    nz = ops.frames_nonzero(key_plane).cpu().numpy()                                     # decompress.py:123-127
+    nz = ops.frames_nonzero(key_plane).cpu().numpy() if nonzero is None else np.asarray(nonzero)   # decompress.py:123-127
     keys = [int(i) for i in np.nonzero(nz)[0]]
     plan = cached_plan(nt, p, keys)
     pool = torch.empty((plan.n_slots, Hp, Wp, C), dtype=torch.float32, device=dev)
@@ -738,19 +741,41 @@ def upload_frames(frames_host, dev, p, window, threshold):
     return frames, side.record_event()
 
 
-def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, first_mode=0, first_x=0):
+def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, first_mode=0, first_x=0,
+                       wait_copies=True):
     """Host-buffer API of the decoder: the key plane goes first (the prediction replay needs it), the int16 stream
-    follows on a side stream while PredNet runs, the frames come back at the end."""
+    follows while PredNet runs, the frames come back at the end.  Both uploads and the key-frame scan
+    (decompress.py:123-127) run on the upload stream and the download on the download stream, so in streaming use
+    (wait_copies=False, consecutive sequences, alternating out_host buffers) the next sequence's key plane is already
+    on the device -- and its schedule known to the host -- while the current sequence is still being predicted, and
+    its kernels never queue behind the current sequence's download.  wait_copies=False returns (out, plan, event):
+    synchronise the event before reading out_host."""
     dev = net.device
     main = torch.cuda.current_stream(dev)
-    key_plane = key_host.to(dev, non_blocking=True)
-    body = torch.empty(body_host.numel(), dtype=body_host.dtype, device=dev)   # allocated on the main stream's pool
-    side = side_stream(dev, "in")
-    side.wait_event(main.record_event())      # after the key plane copy (same copy engine) and any earlier use of `body`
-    with torch.cuda.stream(side):
-        body.copy_(body_host, non_blocking=True)
-        ev = side.record_event()
+    _one, nt, H, W, C = shape
+    s_in = side_stream(dev, "in")
+    with torch.cuda.stream(s_in):      # allocations below belong to the upload stream's pool: safe to fill right away
+        key_plane = key_host.to(dev, non_blocking=True)
+        nz_dev = ops.frames_nonzero(key_plane.view(nt, H, W, C))
+        nz_host = _flag_scratch(dev, nt)[0]
+        nz_host.copy_(nz_dev, non_blocking=True)
+        ev_key = s_in.record_event()
+        body = body_host.to(dev, non_blocking=True)
+        ev_body = s_in.record_event()
+    key_plane.record_stream(main)      # used by the kernels of the main stream from here on
+    body.record_stream(main)
+    ev_key.synchronize()               # the host needs the key positions to build the schedule
+    nz = nz_host.numpy().copy()
+    main.wait_event(ev_key)
     out, plan = decode_arrays(key_plane, body, table, shape, p, net, first_mode=first_mode, first_x=first_x,
-                              body_event=ev)
-    out_host.copy_(out, non_blocking=True)
-    return out, plan
+                              body_event=ev_body, nonzero=nz)
+    if wait_copies:
+        out_host.copy_(out, non_blocking=True)
+        return out, plan
+    s_out = side_stream(dev, "out")
+    s_out.wait_event(main.record_event())
+    out.record_stream(s_out)
+    with torch.cuda.stream(s_out):
+        out_host.copy_(out, non_blocking=True)
+        done = s_out.record_event()
+    return out, plan, done

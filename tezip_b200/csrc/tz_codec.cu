@@ -439,62 +439,204 @@ __global__ void __launch_bounds__(1024) build_table_kernel(const unsigned long l
   }
 }
 
-// ------------------------------------------------------------------------------------------------ delta + histogram
-// compress.py:73-77 + :348-355.  Shared-memory histogram (16 KB), run-length aggregated atomics, one
-// 64-bit global atomic per non-empty bin per block.  SRC 0: x is materialised (int16); SRC 1/2: the
-// residual is recomputed from frames + predictions (fused lossless path), FAST = SRC 2.
-template <int SRC>
-__device__ __forceinline__ void fetch8(const int16_t *__restrict__ x, const uint8_t *__restrict__ frames,
-                                       const float *__restrict__ pool, const int32_t *__restrict__ slot,
-                                       const Geo &g, long long i0, long long n, int v[8], int &prev, int has_prev) {
-  if (SRC == 0) {
-    load8_i16(x, i0, n, v);
-    prev = (i0 > 0 || has_prev == 2) ? (int)x[i0 - 1] : 0;   // has_prev == 2: x points into a longer stream
-  } else {
-    resid8<SRC == 2>(frames, pool, slot, g, i0, n, v);
-    prev = (i0 > 0) ? resid_at(frames, pool, slot, g, i0 - 1) : 0;
+// ------------------------------------------------------------------------------------------------ stream kernels
+// Work decomposition shared by the two encoder passes and the decoder: one WARP owns a chunk of WCH = 1024
+// consecutive stream elements and walks it in four coalesced rounds of 256 (lane k: 8 consecutive elements = one
+// 16-byte access of the int16 stream).  All loads of the four rounds are issued before the first use (the
+// previous one-group-per-thread loops kept 16 bytes per thread in flight, half of what the HBM latency needs);
+// the element before a lane's group comes from the neighbouring lane by shuffle -- only the first element of a
+// chunk is fetched again -- and the (frame, offset) pair of a group is derived from ONE 64-bit division per chunk
+// (it used to be two per group: 64-bit integer division is ~100 instructions and made these passes issue-bound).
+// No block-level synchronisation inside the loop.
+constexpr int WCH_ROUNDS = 4;
+constexpr int WCH = 32 * 8 * WCH_ROUNDS;
+
+struct StreamPos {   // stream element i = f * frame_elems + r
+  long long f;
+  unsigned int r;
+};
+__device__ __forceinline__ StreamPos stream_locate(long long i, const Geo &g) {
+  StreamPos p;
+  p.f = i / g.frame_elems;
+  p.r = (unsigned int)rem_in_frame(i, p.f, g.frame_elems);
+  return p;
+}
+__device__ __forceinline__ StreamPos stream_advance(StreamPos p, unsigned int d, unsigned int FE) {   // r + d < 2^32
+  p.r += d;
+  if (p.r >= FE) {
+    const unsigned int q = p.r / FE;
+    p.f += q;
+    p.r -= q * FE;
   }
+  return p;
+}
+// offset of in-frame element r inside the (padded) prediction frame
+__device__ __forceinline__ unsigned int pool_ofs(unsigned int r, const Geo &g) {
+  if (g.prow == g.rowlen) return r;
+  const unsigned int row = r / (unsigned int)g.rowlen;
+  return row * (unsigned int)g.prow + (r - row * (unsigned int)g.rowlen);
+}
+// compress.py:293-314 for one sample at a known position.
+__device__ __forceinline__ int resid_pos(const uint8_t *__restrict__ frames, const float *__restrict__ pool,
+                                         const int32_t *__restrict__ slot, const Geo &g, StreamPos p) {
+  const int s = slot[p.f];
+  if (s < 0) return 0;
+  const float pv = pool[(long long)s * g.pframe_elems + pool_ofs(p.r, g)];
+  return q255(pv) - (int)frames[p.f * g.frame_elems + p.r];
+}
+__device__ __forceinline__ void unpack8_i16(const uint4 a, int v[8]) {
+  v[0] = (int16_t)(a.x & 0xffff); v[1] = (int16_t)(a.x >> 16);
+  v[2] = (int16_t)(a.y & 0xffff); v[3] = (int16_t)(a.y >> 16);
+  v[4] = (int16_t)(a.z & 0xffff); v[5] = (int16_t)(a.z >> 16);
+  v[6] = (int16_t)(a.w & 0xffff); v[7] = (int16_t)(a.w >> 16);
+}
+__device__ __forceinline__ uint4 pack8_i16(const int v[8]) {
+  uint4 a;
+  a.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+  a.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+  a.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+  a.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+  return a;
+}
+__device__ __forceinline__ void unpack8_u8(const uint2 a, int v[8]) {
+  v[0] = a.x & 0xff; v[1] = (a.x >> 8) & 0xff; v[2] = (a.x >> 16) & 0xff; v[3] = a.x >> 24;
+  v[4] = a.y & 0xff; v[5] = (a.y >> 8) & 0xff; v[6] = (a.y >> 16) & 0xff; v[7] = a.y >> 24;
 }
 
+// The quantised residuals of one chunk: v[round][k] = x[cbase + round * 256 + lane * 8 + k] (0 beyond n), and, in
+// lane 0, prev0 = the element before the chunk (compress.py:75; on a shard *prev_x; 0 at the start of the stream).
+// SRC 0: x is materialised (int16).  SRC 1 / 2: the residual is recomputed from frames + predictions (fused
+// lossless path); 2 = rowlen % 8 == 0, so a group of 8 lies inside one row of one frame.
 template <int SRC>
-__global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restrict__ x,
-                                                         const uint8_t *__restrict__ frames,
-                                                         const float *__restrict__ pool,
-                                                         const int32_t *__restrict__ slot, Geo g, long long n,
-                                                         int has_prev, const int32_t *__restrict__ prev_x,
-                                                         unsigned long long *__restrict__ hist,
-                                                         unsigned long long *__restrict__ overflow) {
+__device__ __forceinline__ void enc_chunk_load(const int16_t *__restrict__ x, const uint8_t *__restrict__ frames,
+                                               const float *__restrict__ pool, const int32_t *__restrict__ slot,
+                                               const Geo &g, long long n, long long cbase, int lane, int has_prev,
+                                               const int32_t *__restrict__ prev_x, int v[WCH_ROUNDS][8], int &prev0) {
+  prev0 = 0;
+  if (SRC == 0) {
+    if (cbase + WCH <= n) {
+      uint4 q[WCH_ROUNDS];
+#pragma unroll
+      for (int it = 0; it < WCH_ROUNDS; it++) q[it] = *reinterpret_cast<const uint4 *>(x + cbase + it * 256 + lane * 8);
+      if (lane == 0) prev0 = (cbase > 0 || has_prev == 2) ? (int)x[cbase - 1] : 0;   // has_prev == 2: x points into a longer stream
+#pragma unroll
+      for (int it = 0; it < WCH_ROUNDS; it++) unpack8_i16(q[it], v[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < WCH_ROUNDS; it++) load8_i16(x, cbase + it * 256 + lane * 8, n, v[it]);
+      if (lane == 0) prev0 = (cbase > 0 || has_prev == 2) ? (int)x[cbase - 1] : 0;
+    }
+  } else if (SRC == 2) {
+    const unsigned int FE = (unsigned int)g.frame_elems;
+    const StreamPos p0 = stream_locate(cbase, g);
+    uint2 a[WCH_ROUNDS];
+    float4 pa[WCH_ROUNDS], pb[WCH_ROUNDS];
+    bool on[WCH_ROUNDS];
+#pragma unroll
+    for (int it = 0; it < WCH_ROUNDS; it++) {
+      const unsigned int off = it * 256 + lane * 8;
+      const long long i0 = cbase + off;
+      on[it] = false;
+      if (i0 < n) {   // n is a multiple of 8 here: a group is entirely inside or outside the stream
+        const StreamPos p = stream_advance(p0, off, FE);
+        const int s = slot[p.f];
+        if (s >= 0) {   // s < 0: first frame of a window, x = 0 (compress.py:314)
+          on[it] = true;
+          a[it] = *reinterpret_cast<const uint2 *>(frames + i0);
+          const float4 *pp = reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + pool_ofs(p.r, g));
+          pa[it] = pp[0];
+          pb[it] = pp[1];
+        }
+      }
+    }
+    if (lane == 0 && cbase > 0) {
+      StreamPos pm = p0;
+      if (pm.r > 0) {
+        pm.r--;
+      } else {
+        pm.f--;
+        pm.r = FE - 1;
+      }
+      prev0 = resid_pos(frames, pool, slot, g, pm);
+    }
+#pragma unroll
+    for (int it = 0; it < WCH_ROUNDS; it++) {
+      if (on[it]) {
+        int o[8];
+        unpack8_u8(a[it], o);
+        v[it][0] = q255(pa[it].x) - o[0]; v[it][1] = q255(pa[it].y) - o[1];
+        v[it][2] = q255(pa[it].z) - o[2]; v[it][3] = q255(pa[it].w) - o[3];
+        v[it][4] = q255(pb[it].x) - o[4]; v[it][5] = q255(pb[it].y) - o[5];
+        v[it][6] = q255(pb[it].z) - o[6]; v[it][7] = q255(pb[it].w) - o[7];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[it][k] = 0;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < WCH_ROUNDS; it++) resid8<false>(frames, pool, slot, g, cbase + it * 256 + lane * 8, n, v[it]);
+    if (lane == 0 && cbase > 0) prev0 = resid_at(frames, pool, slot, g, cbase - 1);
+  }
+  if (lane == 0 && cbase == 0 && has_prev == 1) prev0 = *prev_x;
+}
+
+// y of round `it` (compress.py:75): the element before a lane's group is the neighbouring lane's last element, the
+// previous round's last element (lane 0), or prev0 (lane 0, round 0).
+__device__ __forceinline__ void enc_round_delta(const int v[WCH_ROUNDS][8], int it, int lane, int prev0,
+                                                bool first_global, int y[8]) {
+  const int up = __shfl_up_sync(0xffffffffu, v[it][7], 1);
+  const int wrap = __shfl_sync(0xffffffffu, it > 0 ? v[it - 1][7] : 0, 31);
+  const int prev = lane > 0 ? up : (it > 0 ? wrap : prev0);
+  delta8(v[it], prev, first_global && it == 0 && lane == 0, y);
+}
+
+// ------------------------------------------------------------------------------------------------ delta + histogram
+// compress.py:73-77 + :348-355.  Shared-memory histogram (16 KB), run-length aggregated atomics, one 64-bit global
+// atomic per non-empty bin per block.
+template <int SRC>
+__global__ void __launch_bounds__(256, SRC == 0 ? 3 : 2) delta_hist_kernel(const int16_t *__restrict__ x,
+                                                            const uint8_t *__restrict__ frames,
+                                                            const float *__restrict__ pool,
+                                                            const int32_t *__restrict__ slot, Geo g, long long n,
+                                                            int has_prev, const int32_t *__restrict__ prev_x,
+                                                            unsigned long long *__restrict__ hist,
+                                                            unsigned long long *__restrict__ overflow) {
   __shared__ unsigned int sh[TZ_HIST_BINS];
   __shared__ unsigned int sh_ovf;
   for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sh[i] = 0;
   if (threadIdx.x == 0) sh_ovf = 0;
   __syncthreads();
-  long long ngroups = (n + 7) / 8;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
-       gi += (long long)gridDim.x * blockDim.x) {
-    long long i0 = gi * 8;
-    int v[8], y[8], prev;
-    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
-    if (i0 == 0 && has_prev == 1) prev = *prev_x;
-    delta8(v, prev, i0 == 0 && !has_prev, y);
-    int cur = -1, cnt = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nchunks = (n + WCH - 1) / WCH;
+  for (long long wid = (long long)blockIdx.x * 8 + warp; wid < nchunks; wid += (long long)gridDim.x * 8) {
+    const long long cbase = wid * WCH;
+    int v[WCH_ROUNDS][8], prev0;
+    enc_chunk_load<SRC>(x, frames, pool, slot, g, n, cbase, lane, has_prev, prev_x, v, prev0);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (i0 + k < n) {
-        int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);                 // :348 int16 arithmetic
-        if (s == cur) {
-          cnt++;
-        } else {
-          if (cnt) {
-            if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+    for (int it = 0; it < WCH_ROUNDS; it++) {
+      const long long i0 = cbase + it * 256 + lane * 8;
+      int y[8];
+      enc_round_delta(v, it, lane, prev0, cbase == 0 && !has_prev, y);
+      int cur = -1, cnt = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (i0 + k < n) {
+          int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);                 // :348 int16 arithmetic
+          if (s == cur) {
+            cnt++;
+          } else {
+            if (cnt) {
+              if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+            }
+            cur = s;
+            cnt = 1;
           }
-          cur = s;
-          cnt = 1;
         }
       }
-    }
-    if (cnt) {
-      if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+      if (cnt) {
+        if ((unsigned)cur < TZ_HIST_BINS) atomicAdd(&sh[cur], cnt); else atomicAdd(&sh_ovf, cnt);
+      }
     }
   }
   __syncthreads();
@@ -507,35 +649,41 @@ __global__ void __launch_bounds__(256) delta_hist_kernel(const int16_t *__restri
 
 // ------------------------------------------------------------------------------------------------ delta + rank map
 // compress.py:84-90 with the symbol -> rank table held in shared memory (pure LUT: SURVEY.md A13).
+__device__ __forceinline__ void load_lut_smem(int16_t *sl, const int16_t *__restrict__ lut) {   // 8 KB, 16-byte accesses
+  for (int i = threadIdx.x; i < TZ_HIST_BINS / 8; i += blockDim.x)
+    reinterpret_cast<uint4 *>(sl)[i] = reinterpret_cast<const uint4 *>(lut)[i];
+  __syncthreads();
+}
+
 template <int SRC>
-__global__ void __launch_bounds__(256) delta_rank_kernel(const int16_t *__restrict__ x,
-                                                         const uint8_t *__restrict__ frames,
-                                                         const float *__restrict__ pool,
-                                                         const int32_t *__restrict__ slot, Geo g, long long n,
-                                                         int has_prev, const int32_t *__restrict__ prev_x,
-                                                         const int16_t *__restrict__ lut,
-                                                         int16_t *__restrict__ out) {
-  __shared__ int16_t sl[TZ_HIST_BINS];
-  if (lut) {
-    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
-    __syncthreads();
-  }
-  long long ngroups = (n + 7) / 8;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups;
-       gi += (long long)gridDim.x * blockDim.x) {
-    long long i0 = gi * 8;
-    int v[8], y[8], prev;
-    fetch8<SRC>(x, frames, pool, slot, g, i0, n, v, prev, has_prev);
-    if (i0 == 0 && has_prev == 1) prev = *prev_x;
-    delta8(v, prev, i0 == 0 && !has_prev, y);
-    if (lut) {
+__global__ void __launch_bounds__(256, SRC == 0 ? 3 : 2) delta_rank_kernel(const int16_t *__restrict__ x,
+                                                            const uint8_t *__restrict__ frames,
+                                                            const float *__restrict__ pool,
+                                                            const int32_t *__restrict__ slot, Geo g, long long n,
+                                                            int has_prev, const int32_t *__restrict__ prev_x,
+                                                            const int16_t *__restrict__ lut,
+                                                            int16_t *__restrict__ out) {
+  __shared__ __align__(16) int16_t sl[TZ_HIST_BINS];
+  if (lut) load_lut_smem(sl, lut);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nchunks = (n + WCH - 1) / WCH;
+  for (long long wid = (long long)blockIdx.x * 8 + warp; wid < nchunks; wid += (long long)gridDim.x * 8) {
+    const long long cbase = wid * WCH;
+    int v[WCH_ROUNDS][8], prev0;
+    enc_chunk_load<SRC>(x, frames, pool, slot, g, n, cbase, lane, has_prev, prev_x, v, prev0);
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);
-        y[k] = ((unsigned)s < TZ_HIST_BINS) ? (int)sl[s] : s;            // where() leaves other values alone
+    for (int it = 0; it < WCH_ROUNDS; it++) {
+      int y[8];
+      enc_round_delta(v, it, lane, prev0, cbase == 0 && !has_prev, y);
+      if (lut) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          int s = (int)(int16_t)(TZ_SYMBOL_OFFSET - y[k]);
+          y[k] = ((unsigned)s < TZ_HIST_BINS) ? (int)sl[s] : s;            // where() leaves other values alone
+        }
       }
+      store8_i16(out, cbase + it * 256 + lane * 8, n, y);
     }
-    store8_i16(out, i0, n, y);
   }
 }
 
@@ -553,49 +701,100 @@ __device__ __forceinline__ void map8(const int16_t *sl, bool use_lut, int v[8]) 
   }
 }
 
-__global__ void __launch_bounds__(DEC_THREADS) decode_chunksum_kernel(const int16_t *__restrict__ body, long long n,
-                                                                      int use_lut,
-                                                                      const int16_t *__restrict__ lut,
-                                                                      unsigned int *__restrict__ sums) {
-  __shared__ int16_t sl[TZ_HIST_BINS];
-  __shared__ unsigned int wsum[DEC_THREADS / 32];
-  if (use_lut) {
-    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
-    __syncthreads();
-  }
-  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
-  int v[8];
-  load8_i16(body, i0, n, v);   // zeros beyond n
-  map8(sl, use_lut != 0, v);
-  unsigned int s = 0;
+// pass 1: sums[c] = sum of y over chunk c (uint32 wrap-around), zero for the padding chunks c in [nchunks, npad)
+__global__ void __launch_bounds__(256) decode_wsum_kernel(const int16_t *__restrict__ body, long long n, long long npad,
+                                                          int use_lut, const int16_t *__restrict__ lut,
+                                                          unsigned int *__restrict__ sums) {
+  __shared__ __align__(16) int16_t sl[TZ_HIST_BINS];
+  if (use_lut) load_lut_smem(sl, lut);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long wid = (long long)blockIdx.x * 8 + warp; wid < npad; wid += (long long)gridDim.x * 8) {
+    const long long cbase = wid * WCH;
+    unsigned int s = 0;
+    if (cbase + WCH <= n) {
+      uint4 q[WCH_ROUNDS];
 #pragma unroll
-  for (int k = 0; k < 8; k++)
-    if (i0 + k < n) s += (unsigned int)v[k];
+      for (int it = 0; it < WCH_ROUNDS; it++) q[it] = *reinterpret_cast<const uint4 *>(body + cbase + it * 256 + lane * 8);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int t = 0;
-    for (int w = 0; w < DEC_THREADS / 32; w++) t += wsum[w];
-    sums[blockIdx.x] = t;
+      for (int it = 0; it < WCH_ROUNDS; it++) {
+        int v[8];
+        unpack8_i16(q[it], v);
+        map8(sl, use_lut != 0, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += (unsigned int)v[k];
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < WCH_ROUNDS; it++) {
+        const long long i0 = cbase + it * 256 + lane * 8;
+        int v[8];
+        load8_i16(body, i0, n, v);   // zeros beyond n
+        map8(sl, use_lut != 0, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (i0 + k < n) s += (unsigned int)v[k];
+      }
+    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) sums[wid] = s;
   }
 }
 
-// decompress.py:22-29 (as a prefix sum), :252-256, :269.
+// pass 2: exclusive scan of the chunk sums in place, one block; 8 entries per thread (two 16-byte accesses), two
+// barriers per 8192 entries.  npad is a multiple of 8.
+__global__ void __launch_bounds__(1024) decode_scan8_kernel(unsigned int *__restrict__ sums, long long npad) {
+  __shared__ unsigned int wtot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int carry = 0;   // the same value in every thread
+  for (long long base = 0; base < npad; base += 8192) {
+    const long long i = base + (long long)threadIdx.x * 8;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (i < npad) {
+      a = *reinterpret_cast<const uint4 *>(sums + i);
+      b = *reinterpret_cast<const uint4 *>(sums + i + 4);
+    }
+    const unsigned int tot = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    unsigned int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    const unsigned int w = wtot[lane];   // every warp scans the 32 warp totals for itself
+    unsigned int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    const unsigned int woff = __shfl_sync(0xffffffffu, winc - w, warp);
+    const unsigned int total = __shfl_sync(0xffffffffu, winc, 31);
+    unsigned int e = carry + woff + inc - tot;
+    if (i < npad) {
+      uint4 oa, ob;
+      oa.x = e; e += a.x; oa.y = e; e += a.y; oa.z = e; e += a.z; oa.w = e; e += a.w;
+      ob.x = e; e += b.x; ob.y = e; e += b.y; ob.z = e; e += b.z; ob.w = e;
+      *reinterpret_cast<uint4 *>(sums + i) = oa;
+      *reinterpret_cast<uint4 *>(sums + i + 4) = ob;
+    }
+    carry += total;
+    __syncthreads();   // wtot is rewritten in the next round
+  }
+}
+
+// pass 3: decompress.py:22-29 (as a prefix sum), :252-256, :269.  x[i] = x0 + y0 - S[i], S inclusive from element 0.
 template <bool FAST>
-__global__ void __launch_bounds__(DEC_THREADS) decode_reconstruct_kernel(
-    const int16_t *__restrict__ body, long long n, int use_lut, const int16_t *__restrict__ lut,
+__global__ void __launch_bounds__(256, 2) decode_wrecon_kernel(
+    const int16_t *__restrict__ body, long long n, long long nchunks, int use_lut, const int16_t *__restrict__ lut,
     const unsigned int *__restrict__ chunk_prefix, int first_mode, int first_x, const float *__restrict__ pool,
     const int32_t *__restrict__ slot, const uint8_t *__restrict__ key_plane, uint8_t *__restrict__ out,
     int16_t *__restrict__ x_out, Geo g) {
-  __shared__ int16_t sl[TZ_HIST_BINS];
-  __shared__ unsigned int wtot[DEC_THREADS / 32];
-  if (use_lut) {
-    for (int i = threadIdx.x; i < TZ_HIST_BINS; i += blockDim.x) sl[i] = lut[i];
-    __syncthreads();
-  }
-  // y[0] of the whole stream (needed because x[i] = x0 + y0 - S[i], S inclusive from element 0)
+  __shared__ __align__(16) int16_t sl[TZ_HIST_BINS];
+  if (use_lut) load_lut_smem(sl, lut);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // y[0] of the whole stream (needed because x[i] = x0 + y0 - S[i])
   int y0;
   {
     int r = body[0];
@@ -607,78 +806,130 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_reconstruct_kernel(
     }
   }
   const int x0 = (first_mode == 0) ? y0 : first_x;
-  long long i0 = (long long)blockIdx.x * DEC_CHUNK + threadIdx.x * 8;
-  int v[8];
-  load8_i16(body, i0, n, v);
-  map8(sl, use_lut != 0, v);
-  unsigned int loc[8];
-  unsigned int run = 0;
+  const unsigned int xy = (unsigned int)(x0 + y0);
+  const unsigned int FE = (unsigned int)g.frame_elems;
+  for (long long wid = (long long)blockIdx.x * 8 + warp; wid < nchunks; wid += (long long)gridDim.x * 8) {
+    const long long cbase = wid * WCH;
+    unsigned int before = chunk_prefix[wid];   // sum of all y before the current round
+    if (FAST && cbase + WCH <= n) {
+      const StreamPos p0 = stream_locate(cbase, g);
+      uint4 q[WCH_ROUNDS];
+      uint2 kp[WCH_ROUNDS];
+      float4 pa[WCH_ROUNDS], pb[WCH_ROUNDS];
+      bool key[WCH_ROUNDS];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    run += (i0 + k < n) ? (unsigned int)v[k] : 0u;
-    loc[k] = run;
-  }
-  unsigned int inc = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((threadIdx.x & 31) >= o) inc += t;
-  }
-  if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
-  __syncthreads();
-  unsigned int woff = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wtot[w];
-  unsigned int base = chunk_prefix[blockIdx.x] + woff + inc - run;   // sum of all y before i0
-  if (i0 >= n) return;
-  int xs[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) xs[k] = (int)(int16_t)((unsigned int)(x0 + y0) - (base + loc[k]));
-  if (x_out) store8_i16(x_out, i0, n, xs);
-  if (FAST && i0 + 8 <= n) {
-    long long f = i0 / g.frame_elems;
-    int s = slot[f];
-    int P[8];
-    if (s < 0) {
-      uint2 a = *reinterpret_cast<const uint2 *>(key_plane + i0);
-      P[0] = a.x & 0xff; P[1] = (a.x >> 8) & 0xff; P[2] = (a.x >> 16) & 0xff; P[3] = a.x >> 24;
-      P[4] = a.y & 0xff; P[5] = (a.y >> 8) & 0xff; P[6] = (a.y >> 16) & 0xff; P[7] = a.y >> 24;
-    } else {
-      int r = rem_in_frame(i0, f, g.frame_elems);
-      int row = r / g.rowlen;
-      int col = r - row * g.rowlen;
-      const float4 *pp =
-          reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + (long long)row * g.prow + col);
-      float4 p0 = pp[0], p1 = pp[1];
-      P[0] = q255(p0.x); P[1] = q255(p0.y); P[2] = q255(p0.z); P[3] = q255(p0.w);
-      P[4] = q255(p1.x); P[5] = q255(p1.y); P[6] = q255(p1.z); P[7] = q255(p1.w);
-    }
-    unsigned int o[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) o[k] = (unsigned int)min(max(P[k] - xs[k], 0), 255);   // :252-256,269
-    uint2 w;
-    w.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-    w.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
-    *reinterpret_cast<uint2 *>(out + i0) = w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      long long i = i0 + k;
-      if (i < n) {
-        long long f = i / g.frame_elems;
-        int s = slot[f];
-        int P;
+      for (int it = 0; it < WCH_ROUNDS; it++) {
+        const unsigned int off = it * 256 + lane * 8;
+        const long long i0 = cbase + off;
+        q[it] = *reinterpret_cast<const uint4 *>(body + i0);
+        const StreamPos p = stream_advance(p0, off, FE);
+        const int s = slot[p.f];
+        key[it] = s < 0;
         if (s < 0) {
-          P = key_plane[i];
+          kp[it] = *reinterpret_cast<const uint2 *>(key_plane + i0);
         } else {
-          int r = rem_in_frame(i, f, g.frame_elems);
-          int row = r / g.rowlen;
-          int col = r - row * g.rowlen;
-          P = q255(pool[(long long)s * g.pframe_elems + (long long)row * g.prow + col]);
+          const float4 *pp = reinterpret_cast<const float4 *>(pool + (long long)s * g.pframe_elems + pool_ofs(p.r, g));
+          pa[it] = pp[0];
+          pb[it] = pp[1];
         }
-        out[i] = (uint8_t)min(max(P - xs[k], 0), 255);
+      }
+#pragma unroll
+      for (int it = 0; it < WCH_ROUNDS; it++) {
+        const long long i0 = cbase + it * 256 + lane * 8;
+        int v[8];
+        unpack8_i16(q[it], v);
+        map8(sl, use_lut != 0, v);
+        unsigned int loc[8], run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          run += (unsigned int)v[k];
+          loc[k] = run;
+        }
+        unsigned int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const unsigned int base = before + inc - run;
+        before += __shfl_sync(0xffffffffu, inc, 31);
+        int xs[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) xs[k] = (int)(int16_t)(xy - (base + loc[k]));
+        if (x_out) *reinterpret_cast<uint4 *>(x_out + i0) = pack8_i16(xs);
+        int P[8];
+        if (key[it]) {
+          unpack8_u8(kp[it], P);
+        } else {
+          P[0] = q255(pa[it].x); P[1] = q255(pa[it].y); P[2] = q255(pa[it].z); P[3] = q255(pa[it].w);
+          P[4] = q255(pb[it].x); P[5] = q255(pb[it].y); P[6] = q255(pb[it].z); P[7] = q255(pb[it].w);
+        }
+        unsigned int o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = (unsigned int)min(max(P[k] - xs[k], 0), 255);   // :252-256,269
+        uint2 w;
+        w.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        w.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+        *reinterpret_cast<uint2 *>(out + i0) = w;
+      }
+    } else {
+      // the last, partial chunk of a stream, and geometries whose rows are not multiples of 8 samples
+#pragma unroll 1
+      for (int it = 0; it < WCH_ROUNDS; it++) {
+        const long long i0 = cbase + it * 256 + lane * 8;
+        int v[8];
+        load8_i16(body, i0, n, v);
+        map8(sl, use_lut != 0, v);
+        unsigned int loc[8], run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          run += (i0 + k < n) ? (unsigned int)v[k] : 0u;
+          loc[k] = run;
+        }
+        unsigned int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const unsigned int base = before + inc - run;
+        before += __shfl_sync(0xffffffffu, inc, 31);
+        int xs[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) xs[k] = (int)(int16_t)(xy - (base + loc[k]));
+        if (x_out) store8_i16(x_out, i0, n, xs);
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+          const long long i = i0 + k;
+          if (i < n) {
+            const long long f = i / g.frame_elems;
+            const int s = slot[f];
+            int P;
+            if (s < 0) {
+              P = key_plane[i];
+            } else {
+              const unsigned int r = (unsigned int)rem_in_frame(i, f, g.frame_elems);
+              P = q255(pool[(long long)s * g.pframe_elems + pool_ofs(r, g)]);
+            }
+            out[i] = (uint8_t)min(max(P - xs[k], 0), 255);
+          }
+        }
       }
     }
   }
+}
+
+// persistent grid for the warp-chunk kernels: 8 warps per block, at most per_sm resident blocks per SM
+template <typename K>
+static int resident_blocks(K kernel) {   // 256-thread blocks of `kernel` that fit on one SM (registers / shared memory)
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+  return nb;
+}
+static int chunk_grid(long long n, int per_sm) {
+  const long long blocks = ((n + WCH - 1) / WCH + 7) / 8;
+  const long long cap = (long long)tz::sm_count() * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
 // ------------------------------------------------------------------------------------------------ misc
@@ -924,7 +1175,8 @@ int tz_delta_hist(const int16_t *x, long long n, int has_prev, const int32_t *pr
   TZ_REQUIRE(has_prev >= 0 && has_prev <= 2 && (has_prev != 1 || prev_x), "tz_delta_hist: bad has_prev / prev_x");
   if (n == 0) return TZ_OK;
   Geo g = make_geo(1, 1, 1, 1, 1);
-  int grid = stream_grid((n + 7) / 8, 256, 4);
+  static const int per_sm = resident_blocks(delta_hist_kernel<0>);
+  int grid = chunk_grid(n, per_sm);
   delta_hist_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x,
                                                               hist, overflow);
   TZ_CHECK_LAUNCH();
@@ -944,7 +1196,8 @@ int tz_delta_rank(const int16_t *x, long long n, int has_prev, const int32_t *pr
   TZ_REQUIRE(has_prev >= 0 && has_prev <= 2 && (has_prev != 1 || prev_x), "tz_delta_rank: bad has_prev / prev_x");
   if (n == 0) return TZ_OK;
   Geo g = make_geo(1, 1, 1, 1, 1);
-  int grid = stream_grid((n + 7) / 8, 256, 4);
+  static const int per_sm = resident_blocks(delta_rank_kernel<0>);
+  int grid = chunk_grid(n, per_sm);
   delta_rank_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, nullptr, g, n, has_prev, prev_x,
                                                               lut, out);
   TZ_CHECK_LAUNCH();
@@ -962,7 +1215,7 @@ int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int3
   if (nt == 0) return TZ_OK;
   Geo g = make_geo(H, W, C, Hp, Wp);
   long long n = nt * g.frame_elems;
-  int grid = stream_grid((n + 7) / 8, 256, 4);
+  int grid = chunk_grid(n, 2);
   cudaStream_t st = (cudaStream_t)stream;
   if (pass == 0) {
     TZ_REQUIRE(hist && overflow, "tz_encode_lossless: pass 0 needs hist and overflow");
@@ -982,8 +1235,8 @@ int tz_encode_lossless(const uint8_t *frames, const float *pred_pool, const int3
 }
 
 long long tz_reconstruct_workspace_bytes(long long n) {
-  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
-  return (nchunks + 1) * (long long)sizeof(unsigned int);
+  long long nchunks = (n + WCH - 1) / WCH;
+  return ((nchunks + 7) / 8 * 8 + 8) * (long long)sizeof(unsigned int);
 }
 
 int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int Hp, int Wp, int table_len,
@@ -996,22 +1249,24 @@ int tz_reconstruct(const int16_t *body, long long nt, int H, int W, int C, int H
   TZ_REQUIRE(table_len < 0 || rank_lut, "tz_reconstruct: rank_lut required when table_len >= 0");
   if (nt == 0) return TZ_OK;
   Geo g = make_geo(H, W, C, Hp, Wp);
+  TZ_REQUIRE(g.frame_elems < (1LL << 31), "tz_reconstruct: frame too large");
   long long n = nt * g.frame_elems;
-  long long nchunks = (n + DEC_CHUNK - 1) / DEC_CHUNK;
-  TZ_REQUIRE(nchunks < 2147483647LL, "tz_reconstruct: stream too long for one call");
+  long long nchunks = (n + WCH - 1) / WCH;
+  long long npad = (nchunks + 7) / 8 * 8;
   unsigned int *sums = (unsigned int *)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   int use_lut = table_len >= 0;
-  decode_chunksum_kernel<<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(body, n, use_lut, rank_lut, sums);
+  static const int sum_per_sm = resident_blocks(decode_wsum_kernel);
+  decode_wsum_kernel<<<chunk_grid(n, sum_per_sm), 256, 0, st>>>(body, n, npad, use_lut, rank_lut, sums);
   TZ_CHECK_LAUNCH();
-  decode_scan_kernel<<<1, 1024, 0, st>>>(sums, nchunks);
+  decode_scan8_kernel<<<1, 1024, 0, st>>>(sums, npad);
   TZ_CHECK_LAUNCH();
   if (fast_ok(g))
-    decode_reconstruct_kernel<true><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
-        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+    decode_wrecon_kernel<true><<<chunk_grid(n, 2), 256, 0, st>>>(
+        body, n, nchunks, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
   else
-    decode_reconstruct_kernel<false><<<(unsigned)nchunks, DEC_THREADS, 0, st>>>(
-        body, n, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
+    decode_wrecon_kernel<false><<<chunk_grid(n, 2), 256, 0, st>>>(
+        body, n, nchunks, use_lut, rank_lut, sums, first_mode, first_x, pred_pool, pred_slot, key_plane, out, x_out, g);
   TZ_CHECK_LAUNCH();
   return TZ_OK;
 }
