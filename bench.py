@@ -319,9 +319,21 @@ def config4_record(args, dev, rank, world, comm, nt_total, with_e2e, cpu_frames)
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warm):
+    out_sets = [out_host, torch.empty_like(out_host).pin_memory()]
+    dseq = [0]
+    d_in_flight = [None, None]
+
+    def decompress_e2e_pipelined():
+        oh = out_sets[dseq[0] & 1]
+        dseq[0] += 1
+        d_in_flight[dseq[0] & 1] = codec.decode_arrays_host(keyp_host, body_host, enc0.table, enc0.shape, 0, net, oh,
+                                                            first_mode=first_mode, first_x=first_x, wait_copies=False)
+
+    def timed(fn, steps, warm, flush=None):
         for _ in range(warm):
             fn()
+        if flush is not None:
+            flush()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.tz_launch_count()
@@ -329,6 +341,8 @@ def config4_record(args, dev, rank, world, comm, nt_total, with_e2e, cpu_frames)
         e0.record()
         for _ in range(steps):
             fn()
+        if flush is not None:
+            flush()
         e1.record()
         torch.cuda.synchronize(dev)
         barrier()
@@ -570,6 +584,25 @@ def run_native(args):
     def compress_dev():
         return codec.encode_frames(frames_dev, net, 0, win, thr, mode, bound, True, dwp_chains=chains, comm=comm)
 
+    # Back-to-back steps: a step returns as soon as its kernels are queued (defer=True) and the host-side end of the
+    # PREVIOUS step's entropy stage (reading its table and flags) runs after the next step has been queued, so the
+    # GPU does not idle between steps while the host reads one table and launches the next step's first kernels.
+    # Every step's table is still read and checked inside the timed region (flush()).
+    prev_enc = [None]
+
+    def settle(enc):
+        if prev_enc[0] is not None:
+            prev_enc[0].finalize()
+        prev_enc[0] = enc
+        return enc
+
+    def flush():
+        settle(None)
+
+    def compress_dev_stream():
+        return settle(codec.encode_frames(frames_dev, net, 0, win, thr, mode, bound, True, dwp_chains=chains, comm=comm,
+                                          defer=True))
+
     def compress_e2e():
         enc = codec.encode_frames_host(frames_host, net, 0, win, thr, mode, bound, keyp_host, body_host, True,
                                        dwp_chains=chains, comm=comm)
@@ -589,11 +622,11 @@ def run_native(args):
         kh, bh = host_sets[seq[0] & 1]
         seq[0] += 1
         enc = codec.encode_frames_host(frames_host, net, 0, win, thr, mode, bound, kh, bh, True, dwp_chains=chains,
-                                       comm=comm, wait_copies=False)
+                                       comm=comm, wait_copies=False, defer=True)
         if comm is not None:
             offsets[0] = comm.stream_offsets_async(enc.body.numel())
         in_flight[seq[0] & 1] = enc   # the record owns the device tensors its copies read: keep it until the next but one
-        return enc
+        return settle(enc)
 
     in_flight = [None, None]
     enc0 = compress_dev()
@@ -609,9 +642,21 @@ def run_native(args):
         torch.cuda.synchronize(dev)
         return out
 
-    def timed(fn, steps, warm):
+    out_sets = [out_host, torch.empty_like(out_host).pin_memory()]
+    dseq = [0]
+    d_in_flight = [None, None]
+
+    def decompress_e2e_pipelined():
+        oh = out_sets[dseq[0] & 1]
+        dseq[0] += 1
+        d_in_flight[dseq[0] & 1] = codec.decode_arrays_host(keyp_host, body_host, enc0.table, enc0.shape, 0, net, oh,
+                                                            first_mode=first_mode, first_x=first_x, wait_copies=False)
+
+    def timed(fn, steps, warm, flush=None):
         for _ in range(warm):
             fn()
+        if flush is not None:
+            flush()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.tz_launch_count()
@@ -619,6 +664,8 @@ def run_native(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if flush is not None:
+            flush()
         e1.record()
         torch.cuda.synchronize(dev)
         barrier()
@@ -632,14 +679,22 @@ def run_native(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_c, wall_c, launches = timed(compress_dev, args.steps, args.warmup)
+    ms_c, wall_c, launches = timed(compress_dev_stream, args.steps, args.warmup, flush)
     ms_d, wall_d, launches_d = timed(decompress_dev, args.steps, args.warmup)
     clocks = sampler.stop()
+    ms_c_sync, _w, _l = timed(compress_dev, args.steps, 1)
     _ms, wall_ce, _ = timed(compress_e2e, args.steps, max(1, args.warmup - 1))
     _ms, wall_de, _ = timed(decompress_e2e, args.steps, max(1, args.warmup - 1))
-    _ms, wall_cp, _ = timed(compress_e2e_pipelined, args.steps, max(1, args.warmup - 1))
+    _ms, wall_cp, _ = timed(compress_e2e_pipelined, args.steps, max(1, args.warmup - 1), flush)
     torch.cuda.synchronize(dev)
     pipelined_ok = bool(torch.equal(host_sets[0][1], host_sets[1][1]) and torch.equal(host_sets[0][0], host_sets[1][0]))
+    # the streaming decoder reads the container the synchronised compress_e2e left in keyp_host / body_host
+    compress_e2e()
+    _ms, wall_dp, _ = timed(decompress_e2e_pipelined, args.steps, 2)
+    torch.cuda.synchronize(dev)
+    dec_ref = decompress_dev()
+    pipelined_dec_ok = bool(torch.equal(out_sets[0], out_sets[1]) and torch.equal(out_sets[0], dec_ref.cpu()))
+    d_in_flight[:] = [None, None]
 
     # ---- the platform's ceiling for the e2e number: the same bytes over the same pinned buffers, NO kernels (frames
     # in on one stream, stream + key frames out on another, all ranks at once).  e2e / this = what the path costs on
@@ -909,13 +964,18 @@ def run_native(args):
         payload = enc0.payload()
         kp_np = enc0.key_plane.cpu().numpy()
         nw = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        zb = tzc.zstd_compress(payload, 9, workers=nw)
-        zk = tzc.zstd_compress(kp_np, 9, workers=nw)
-        tz_s = time.perf_counter() - t0
-        cont = {"zstd_level": 9, "workers": nw, "seconds": tz_s, "raw_MB_per_s": raw_bytes / 1e6 / tz_s,
-                "ratio": raw_bytes / float(len(zb) + len(zk)),
-                "note": "single zstd frame with content size (what the reference decoder needs); not part of value/e2e"}
+        cont = {"workers": nw, "note": "single zstd frames with content size (what the reference decoder needs), all "
+                                       "host threads (ZSTD_c_nbWorkers); not part of value/e2e.  Level 9 is the "
+                                       "reference's; TEZIP_ZSTD_LEVEL selects another"}
+        for lvl in (9, 3, 1):
+            t0 = time.perf_counter()
+            zb = tzc.zstd_compress(payload, lvl, workers=nw)
+            zk = tzc.zstd_compress(kp_np, lvl, workers=max(1, nw // 4))
+            tz_s = time.perf_counter() - t0
+            cont["level%d" % lvl] = {"seconds": tz_s, "raw_MB_per_s": raw_bytes / 1e6 / tz_s,
+                                     "ratio": raw_bytes / float(len(zb) + len(zk))}
+        cont["zstd_level"], cont["seconds"] = 9, cont["level9"]["seconds"]
+        cont["raw_MB_per_s"], cont["ratio"] = cont["level9"]["raw_MB_per_s"], cont["level9"]["ratio"]
 
     if rank == 0:
         total_mb = world * raw_bytes / 1e6
@@ -933,8 +993,15 @@ def run_native(args):
                              % ((enc_keep.pool.numel() * 4 + net.device_bytes()) / 1e9),
                        "sharding": "by window, %d ranks" % world},
             "decompress": {"value": total_mb / (ms_d * 1e-3), "unit": "MB/s", "ms_per_step": ms_d,
-                           "e2e": {"value": total_mb / (wall_de * 1e-3), "unit": "MB/s",
-                                   "h2d_bytes_per_step": int(N * 3), "d2h_bytes_per_step": int(N)}},
+                           "e2e": {"value": total_mb / (wall_dp * 1e-3), "unit": "MB/s",
+                                   "h2d_bytes_per_step": int(N * 3), "d2h_bytes_per_step": int(N),
+                                   "mode": "streaming decoder (codec.decode_arrays_host, wait_copies=False, two "
+                                           "alternating pinned output buffers): the next sequence's key plane is "
+                                           "uploaded and scanned on the upload stream while the current one is "
+                                           "predicted, downloads run on their own stream; one synchronize around the "
+                                           "K steps",
+                                   "outputs_identical_to_device_path": pipelined_dec_ok,
+                                   "synchronised_each_step": {"value": total_mb / (wall_de * 1e-3), "unit": "MB/s"}}},
             "e2e": {"value": total_mb / (wall_cp * 1e-3), "unit": "MB/s", "h2d_bytes_per_step": int(N),
                     "d2h_bytes_per_step": int(N * 2 + key_bytes),
                     "mode": "streaming compressor through the host-buffer API (codec.encode_frames_host, "
@@ -956,7 +1023,10 @@ def run_native(args):
                                      "synchronised_over_ceiling": wall_copy / wall_ce}},
             "stream_check": stream_check,
             "gpu_launches": int(launches), "gpu_launches_decompress": int(launches_d),
-            "wall_ms_per_step": wall_c, "clocks": clocks, "max_abs_error_levels": maxerr,
+            "wall_ms_per_step": wall_c,
+            "ms_per_step_host_synchronised": ms_c_sync,   # encode_frames(defer=False): the host reads every step's
+                                                          # table before it queues the next step (GPU idles meanwhile)
+            "clocks": clocks, "max_abs_error_levels": maxerr,
             "roofline": roofline, "roofline_codec": roofline_codec, "cpu_baseline": cpu, "ratio": ratio,
             "decompress_sweep": sweep, "container": cont, "dwp": dwp_rec, "config4": c4_rec,
             "prednet_gflop_per_frame": net.flops_per_frame() / 1e9,

@@ -186,3 +186,56 @@ def test_more_windows_than_max_batch_is_bitwise_equal(cuda_lib):
             assert all(np.array_equal(a, b) for a, b in zip(cur, ref)), mb
         net.close()
     assert np.abs(ref[2].astype(int) - frames.cpu().numpy().astype(int)).max() <= 2
+
+
+def test_deferred_streaming_encode_and_decode(cuda_lib):
+    """Streaming use of both APIs: encode with defer=True (the host-side end of a sequence's entropy stage runs after
+    the NEXT sequence has been queued; more sequences in flight than landing slots included) and wait_copies=False,
+    decode with wait_copies=False -- streams, tables, key planes and frames equal the synchronous calls'."""
+    import torch
+    from tezip_b200 import codec
+    stack, H, W, nt = TINY, 24, 40, 17
+    _o, ws = oracle_net(stack)
+    net = gpu_net(stack, ws, 24, 40, max_batch=8)
+    seqs = [torch.from_numpy(synth.make_frames(nt, H, W, 3, seed=60 + i)).pin_memory() for i in range(7)]
+    refs = [codec.encode_frames(s.cuda(), net, 0, 4, None, "abs", [2.0], True) for s in seqs]
+    # device-resident, deferred: finalize each record after the next call has been queued
+    recs, prev = [], None
+    for s in seqs:
+        enc = codec.encode_frames(s.cuda(), net, 0, 4, None, "abs", [2.0], True, defer=True)
+        if prev is not None:
+            prev.finalize()
+        prev = enc
+        recs.append(enc)
+    prev.finalize()
+    for enc, ref in zip(recs, refs):
+        assert np.array_equal(enc.table, ref.table)
+        assert torch.equal(enc.body, ref.body) and torch.equal(enc.key_plane, ref.key_plane)
+    # never finalised explicitly: the landing ring (4 slots) finalises a record when its slot comes round again, and
+    # reading `table` finalises the rest
+    recs = [codec.encode_frames(s.cuda(), net, 0, 4, None, "abs", [2.0], True, defer=True) for s in seqs]
+    for enc, ref in zip(recs, refs):
+        assert np.array_equal(enc.table, ref.table) and torch.equal(enc.body, ref.body)
+    # host buffers, streaming both ways
+    outs = [(torch.empty_like(seqs[0]).pin_memory(), torch.empty(seqs[0].numel(), dtype=torch.int16).pin_memory())
+            for _ in range(2)]
+    dec_out = [torch.empty_like(seqs[0]).pin_memory() for _ in range(2)]
+    prev, keep = None, []
+    for i, s in enumerate(seqs):
+        kh, bh = outs[i & 1]
+        enc = codec.encode_frames_host(s, net, 0, 4, None, "abs", [2.0], kh, bh, True, chunks=3, wait_copies=False,
+                                       defer=True)
+        if prev is not None:
+            prev.finalize()
+        prev = enc
+        enc.finalize().copies_done.synchronize()     # (this test reads every result, so it cannot run further ahead)
+        assert np.array_equal(bh.numpy(), refs[i].body.cpu().numpy()), i
+        assert np.array_equal(kh.numpy(), refs[i].key_plane.cpu().numpy()), i
+        out, _plan, done = codec.decode_arrays_host(kh, bh, enc.table, enc.shape, 0, net, dec_out[i & 1],
+                                                    wait_copies=False)
+        keep.append(out)
+        ref_out, _p = codec.decode_arrays(refs[i].key_plane, refs[i].body, refs[i].table, refs[i].shape, 0, net)
+        done.synchronize()
+        assert np.array_equal(dec_out[i & 1].numpy(), ref_out.cpu().numpy()), i
+        assert np.abs(dec_out[i & 1].numpy().astype(int) - s.numpy().astype(int)).max() <= 2
+    net.close()

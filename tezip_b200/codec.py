@@ -215,11 +215,29 @@ class Encoded:
     keys: list
     key_plane: torch.Tensor      # u8 [nt,H,W,C] (device)
     body: torch.Tensor           # int16 [N] (device): ranks, or the delta stream with entropy=False
-    table: np.ndarray            # int16 [T] or None
+    _table: np.ndarray           # int16 [T] or None (see `table`)
     pred_slot: np.ndarray
     pool: torch.Tensor = None    # kept only when keep_pool=True
     x: torch.Tensor = None
     copies_done: object = None   # encode_frames_host(wait_copies=False): CUDA event after the device->host copies
+    _pending: object = None      # defer=True: the host-side end of the entropy stage, not run yet (finalize())
+    _sink: object = None
+
+    def finalize(self):
+        """defer=True records: waits for the table and the flags of THIS sequence (queued long before its last
+        kernel), raises what a synchronous call would have raised, and -- only when the table needs the reference's
+        chained replacement -- queues the rank map again.  Idempotent; `table` and `payload()` call it."""
+        fn, self._pending = self._pending, None
+        if fn is not None:
+            self._table = fn()
+            if self._sink is not None:
+                self.copies_done = self._sink.done
+        return self
+
+    @property
+    def table(self):
+        self.finalize()
+        return self._table
 
     def payload(self):
         """entropy.dat before zstd (compress.py:375-395), host int16 (int32 for 16-bit samples: container v2)."""
@@ -342,18 +360,6 @@ class HostSink:
             self.done = self.stream.record_event()
 
 
-_HOST_SCRATCH = {}
-
-
-def _host_scratch(device, wide=False):
-    """Pinned landing buffers for the table / flags of one encode (cached: pinning memory per call is slow)."""
-    key = (str(device), wide)
-    if key not in _HOST_SCRATCH:
-        tm = torch.empty(TZ_WIDE_BINS + 2, dtype=torch.int32) if wide else torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16)
-        _HOST_SCRATCH[key] = (tm.pin_memory(), torch.empty(1, dtype=torch.int64).pin_memory())
-    return _HOST_SCRATCH[key]
-
-
 _FLAG_SCRATCH = {}
 
 
@@ -367,6 +373,45 @@ def _flag_scratch(device, nt):
     return cur[0, :nt], cur[1, :nt]
 
 
+class _Landing:
+    """Pinned landing buffers for the small results of ONE encode (table + meta, overflow count, key-frame flags).
+    Cached in a ring per device -- pinning memory per call is slow -- and handed out round-robin, so that a deferred
+    record (defer=True) can still read its own table while the next sequences are being queued.  A slot whose
+    previous owner has not been finalised yet finalises it first."""
+    RING = 4
+
+    def __init__(self):
+        self.tm = {}          # wide -> pinned table|meta buffer
+        self.ovf = torch.empty(1, dtype=torch.int64).pin_memory()
+        self.flags = None     # pinned u8 [2, cap]
+        self.owner = None     # Encoded whose finalize() has not run yet
+
+    def table_meta(self, wide):
+        if wide not in self.tm:
+            t = torch.empty(TZ_WIDE_BINS + 2, dtype=torch.int32) if wide else torch.empty(TZ_HIST_BINS + 4, dtype=torch.int16)
+            self.tm[wide] = t.pin_memory()
+        return self.tm[wide]
+
+    def flag_pair(self, nt):
+        if self.flags is None or self.flags.shape[1] < nt:
+            self.flags = torch.empty((2, max(nt, 1024)), dtype=torch.uint8).pin_memory()
+        return self.flags[0, :nt], self.flags[1, :nt]
+
+
+_LANDING = {}
+
+
+def _landing(device):
+    key = str(device)
+    ring = _LANDING.setdefault(key, [[_Landing() for _ in range(_Landing.RING)], 0])
+    ring[1] += 1
+    slot = ring[0][ring[1] % _Landing.RING]
+    if slot.owner is not None:
+        owner, slot.owner = slot.owner, None
+        owner.finalize()
+    return slot
+
+
 def is_lossless(mode, bound):
     """compress.py:24,35: BOUND_VALUE[0] == 0 (or absrel with BOUND_VALUE[1] == 0) leaves diff untouched."""
     return float(bound[0]) == 0.0 or (mode == "absrel" and float(bound[1]) == 0.0)
@@ -377,7 +422,7 @@ def pool_slots_upper_bound(nt):
 
 
 def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, dwp_chains=1, keep_pool=False,
-                  keep_x=False, comm=None, sink=None, frames_ready=None, arrive=None):
+                  keep_x=False, comm=None, sink=None, frames_ready=None, arrive=None, defer=False):
     """compress.py:176-395 on a device tensor `frames` u8 [nt,H,W,C].
 
     comm: optional shard communicator (tezip_b200/dist.py) when `frames` is one rank's window-aligned shard of a
@@ -424,7 +469,7 @@ def encode_frames(frames, net, p, window, threshold, mode, bound, entropy=True, 
         staged = stage_device(frames, is_key, pred_slot, apply_dev, sink)
         keys = pred_slot_np = apply_np = None          # read back once, after everything has been queued
     enc = encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy, keep_pool, keep_x,
-                           comm, sink, staged)
+                           comm, sink, staged, defer=defer and keys is not None)
     if keys is None:
         enc.keys = [int(k) for k in np.nonzero(staged[3][1].numpy())[0]]
         enc.pred_slot = staged[1].cpu().numpy()
@@ -469,7 +514,8 @@ def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
     # (decompress.py:123-127): the reference then silently decodes the wrong window.  The check costs one pass over
     # the key plane and two tiny asynchronous copies; encode_with_pool looks at the answer once everything is queued.
     nz = ops.frames_nonzero(key_plane)
-    nz_host, ik_host = _flag_scratch(dev, nt)     # cached pinned buffers: consumed by check_key_frames() in this call
+    landing = _landing(dev)                       # cached pinned buffers: consumed by check_key_frames() / finalize()
+    nz_host, ik_host = landing.flag_pair(nt)
     # The two flag copies run on the device->host side stream, never on the compute stream: in streaming use
     # (encode_frames_host(wait_copies=False)) the previous sequence's 123 MB stream may still be draining through the
     # same copy engine, and a copy queued on the compute stream would hold back every PredNet kernel behind it.
@@ -481,12 +527,12 @@ def stage_device(frames, is_key, pred_slot, apply, sink=None, keys_host=None):
         done = out.record_event()
     nz.record_stream(out)
     is_key.record_stream(out)
-    return pred_slot, apply, key_plane, (nz_host, ik_host, done)
+    return pred_slot, apply, key_plane, (nz_host, ik_host, done, landing)
 
 
 def check_key_frames(staged):
     """Raises if a scheduled key frame is all zero (see stage_plan)."""
-    nz_host, ik_host, ev = staged[3]
+    nz_host, ik_host, ev = staged[3][:3]
     ev.synchronize()
     bad = np.nonzero((nz_host.numpy() == 0) & (ik_host.numpy() != 0))[0]
     if bad.size:
@@ -495,9 +541,12 @@ def check_key_frames(staged):
 
 
 def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound, entropy=True, keep_pool=False,
-                     keep_x=False, comm=None, sink=None, staged=None):
+                     keep_x=False, comm=None, sink=None, staged=None, defer=False):
     """compress.py:271-395 given the predictions: key plane, residual, error bound, delta, table, rank map.
     staged: the result of stage_plan() when the caller already ran it (before the predictions).
+    defer: return as soon as everything is queued; the host-side end of the entropy stage (reading the table, the
+    overflow / collision / key-frame flags) runs in Encoded.finalize() -- a streaming caller queues the next sequence
+    first, so the GPU never waits for the host between sequences.
     frames u8 -> the reference's int16 stream; frames u16 -> the container-v2 int32 stream (same steps, wider codes)."""
     nt, H, W, C = frames.shape
     dev = frames.device
@@ -564,7 +613,8 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
             ops.build_table_device(hist, table_dev, lut, meta)                            # :352-361, :84-90
         # their (small) copies to the host are queued NOW, ahead of the stream's large device->host copies in the
         # copy engine's queue; they are waited for at the end
-        tm_host, ovf_host = _host_scratch(dev, wide)
+        landing = staged[3][3]
+        tm_host, ovf_host = landing.table_meta(wide), landing.ovf
         tm_host.copy_(tm, non_blocking=True)
         ovf_host.copy_(ovf, non_blocking=True)
         small_ready = torch.cuda.current_stream(dev).record_event()
@@ -602,24 +652,43 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
                 sink.body_chunk(body, 0, N)
 
     rank_pass(lut)
-    if entropy:
-        small_ready.synchronize()
-        if int(ovf_host[0]) != 0:
-            raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
-                             "cannot represent this bound" % nbins)
-        if wide:
-            table = tm_host[:int(tm_host[nbins])].numpy().copy()
-        else:
-            meta_np = tm_host[TZ_HIST_BINS:].view(torch.int32).numpy()
-            table = tm_host[:int(meta_np[0])].numpy().copy()
-            if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
-                rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
-    check_key_frames(staged)
-    if sink is not None:
-        sink.finish()
-    return Encoded((1, nt, H, W, C), p, None if keys is None else list(keys), key_plane, body, table,
-                   None if pred_slot_np is None else np.asarray(pred_slot_np), pool if keep_pool else None,
-                   x if keep_x else None)
+
+    def host_end():
+        """The host-side end of the entropy stage: -> table.  (The small copies it waits for were queued ahead of the
+        stream's large device->host copies.)"""
+        table = None
+        staged[3][3].owner = None
+        if entropy:
+            small_ready.synchronize()
+            if int(ovf_host[0]) != 0:
+                raise TezipError("residual symbols fall outside [0, %d): the reference's bincount/int16 stream "
+                                 "cannot represent this bound" % nbins)
+            if wide:
+                table = tm_host[:int(tm_host[nbins])].numpy().copy()
+            else:
+                meta_np = tm_host[TZ_HIST_BINS:].view(torch.int32).numpy()
+                table = tm_host[:int(meta_np[0])].numpy().copy()
+                if int(meta_np[1]) != 0:   # a symbol inside the rank range: the reference's sequential replacement chains
+                    rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
+                    if sink is not None:
+                        sink.finish()
+        check_key_frames(staged)
+        return table
+
+    enc = Encoded((1, nt, H, W, C), p, None if keys is None else list(keys), key_plane, body, None,
+                  None if pred_slot_np is None else np.asarray(pred_slot_np), pool if keep_pool else None,
+                  x if keep_x else None)
+    enc._sink = sink
+    if defer:
+        if sink is not None:
+            sink.finish()
+        enc._pending = host_end
+        staged[3][3].owner = enc
+    else:
+        enc._table = host_end()
+        if sink is not None:
+            sink.finish()
+    return enc
 
 
 # ------------------------------------------------------------------------------------------------ decompress
@@ -696,19 +765,21 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
 
 
 def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_host, body_host, entropy=True,
-                       dwp_chains=1, comm=None, chunks=4, wait_copies=True):
+                       dwp_chains=1, comm=None, chunks=4, wait_copies=True, defer=False):
     """Host-buffer API: frames_host u8 [nt,H,W,C] (pinned) -> key_host u8 (pinned, same shape), body_host int16 [N]
     (pinned).  The H2D copy, the kernels and the D2H copies are pipelined; returns the Encoded record (table, keys)
     after the copies have been ordered on the current stream (synchronise before reading the host buffers).
     wait_copies=False (streaming use: the next sequence's kernels should not queue behind this one's device->host
     copies): the copies are only ordered on the side stream and the record carries `copies_done`, the event to
     synchronise before reading key_host / body_host.  Keep the returned record alive until then (it owns the device
-    tensors the copies read) and give consecutive calls different host buffers."""
+    tensors the copies read) and give consecutive calls different host buffers.
+    defer=True (static windows): return without waiting for this sequence's table; call `finalize()` on the record
+    (or read its `table`) after the NEXT sequence has been queued -- the GPU then never idles between sequences."""
     dev = net.device
     sink = HostSink(key_host, body_host, dev, chunks, wait_copies)
     frames, ready = upload_frames(frames_host, dev, p, window, threshold)
     enc = encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
-                        frames_ready=ready)
+                        frames_ready=ready, defer=defer)
     enc.copies_done = sink.done
     return enc
 

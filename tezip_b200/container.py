@@ -83,9 +83,17 @@ def zstd_decompress(data):
     return dst[:r]
 
 
+def container_level():
+    """zstd level of the container files: 9 like the reference (compress.py:276,398) unless TEZIP_ZSTD_LEVEL says
+    otherwise -- any level gives a frame the reference's decoder reads; lower levels trade a few per cent of ratio for
+    a several times faster container stage (bench.py's `container` record quotes both)."""
+    return int(os.environ.get("TEZIP_ZSTD_LEVEL", str(ZSTD_LEVEL)))
+
+
 def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
     """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd).
-    Container v2 (16-bit samples): key_plane u16 and payload int32, both little-endian, same three files."""
+    Container v2 (16-bit samples): key_plane u16 and payload int32, both little-endian, same three files.
+    The two zstd frames are produced concurrently (libzstd releases the GIL under ctypes)."""
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, NAMES_FILE), "w", encoding="UTF-8") as f:     # compress.py:133-136
         f.write("%d\n" % int(is_rgb))
@@ -94,10 +102,15 @@ def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
     wide = np.asarray(payload).dtype == np.int32
     if wide != (np.asarray(key_plane).dtype == np.uint16):
         raise ValueError("key plane and stream disagree about the sample width")
-    kb = zstd_compress(np.ascontiguousarray(key_plane, "<u2" if wide else np.uint8), ZSTD_LEVEL, workers)   # compress.py:271-278
+    level = container_level()
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:
+        fk = pool.submit(zstd_compress, np.ascontiguousarray(key_plane, "<u2" if wide else np.uint8), level,
+                         max(0, workers // 4))                                                          # compress.py:271-278
+        fe = pool.submit(zstd_compress, np.ascontiguousarray(payload, "<i4" if wide else "<i2"), level, workers)  # :394-400
+        kb, eb = fk.result(), fe.result()
     with open(os.path.join(out_dir, KEY_FILE), "wb") as f:
         f.write(kb)
-    eb = zstd_compress(np.ascontiguousarray(payload, "<i4" if wide else "<i2"), ZSTD_LEVEL, workers)       # compress.py:394-400
     with open(os.path.join(out_dir, ENTROPY_FILE), "wb") as f:
         f.write(eb)
     return len(kb), len(eb)
