@@ -777,7 +777,18 @@ def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_
     (or read its `table`) after the NEXT sequence has been queued -- the GPU then never idles between sequences."""
     dev = net.device
     sink = HostSink(key_host, body_host, dev, chunks, wait_copies)
-    frames, ready = upload_frames(frames_host, dev, p, window, threshold)
+    if defer and threshold is None and frames_host.is_pinned():
+        # streaming: the host runs a sequence ahead of the GPU, so the whole upload goes to the upload stream NOW (it
+        # lands while the previous sequence is still being predicted) instead of key-frames-first on the compute stream
+        main, side = torch.cuda.current_stream(dev), side_stream(dev, "in")
+        with torch.cuda.stream(side):          # allocated from the upload stream's pool: free to be written at once
+            frames = frames_host.to(dev, non_blocking=True)
+            landed = side.record_event()
+        frames.record_stream(main)
+        main.wait_event(landed)
+        ready = None
+    else:
+        frames, ready = upload_frames(frames_host, dev, p, window, threshold)
     enc = encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
                         frames_ready=ready, defer=defer)
     enc.copies_done = sink.done
