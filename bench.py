@@ -319,16 +319,6 @@ def config4_record(args, dev, rank, world, comm, nt_total, with_e2e, cpu_frames)
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    out_sets = [out_host, torch.empty_like(out_host).pin_memory()]
-    dseq = [0]
-    d_in_flight = [None, None]
-
-    def decompress_e2e_pipelined():
-        oh = out_sets[dseq[0] & 1]
-        dseq[0] += 1
-        d_in_flight[dseq[0] & 1] = codec.decode_arrays_host(keyp_host, body_host, enc0.table, enc0.shape, 0, net, oh,
-                                                            first_mode=first_mode, first_x=first_x, wait_copies=False)
-
     def timed(fn, steps, warm, flush=None):
         for _ in range(warm):
             fn()

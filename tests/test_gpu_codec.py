@@ -259,3 +259,83 @@ def test_fused_lossy_pass_equals_separate_kernels(cuda_lib, H, W, C):
             hp = torch.zeros(TZ_HIST_BINS + 1, dtype=torch.int64, device=dev)
             ops.finding_difference_hist(x_ref, hp[:-1], hp[-1:], 1, 7)
             assert torch.equal(h3[:TZ_HIST_BINS + 1], hp)
+
+
+def _np_delta(x, has_prev, prev_x):
+    """compress.py:73-77 in int16 arithmetic (y[0] = x[0], or prev_x - x[0] on a shard)."""
+    x = x.astype(np.int16)
+    y = np.empty_like(x)
+    y[1:] = (x[:-1].astype(np.int32) - x[1:].astype(np.int32)).astype(np.int16)
+    y[0] = x[0] if not has_prev else np.int16(np.int32(prev_x) - np.int32(x[0]))
+    return y
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 255, 1024, 1032, 4095, 4096, 8 * 1024 + 8, 300001])
+def test_stream_kernels_chunk_edges(cuda_lib, n):
+    """The warp-chunk stream kernels (1024 elements per warp, four rounds of 256) on a materialised x: lengths around
+    the round / chunk / block boundaries, every has_prev mode (0 = start of the stream, 1 = shard with a halo element,
+    2 = a chunk of a longer stream), against numpy -- histogram, rank map, raw delta stream, and the decoder's
+    prefix-sum inverse of it."""
+    import torch
+    from tezip_b200 import ops, _lib
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(n)
+    full = rng.randint(-40, 41, size=n + 8).astype(np.int16)
+    full[rng.rand(n + 8) < 0.01] = 255            # a few large jumps
+    xt_full = torch.from_numpy(full).to(dev)      # (chunks of a longer stream start at multiples of 8 elements)
+    for has_prev, prev_x, x_np, x_t in ((0, 0, full[8:], xt_full[8:].clone()), (1, -17, full[8:], xt_full[8:].clone()),
+                                        (2, int(full[7]), full[8:], xt_full[8:])):
+        y = _np_delta(x_np, has_prev != 0, prev_x)
+        sym = (1600 - y.astype(np.int32)).astype(np.int16)
+        hist = torch.zeros(_lib.TZ_HIST_BINS, dtype=torch.int64, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops.finding_difference_hist(x_t, hist, ovf, has_prev, prev_x)
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(sym.astype(np.int64), minlength=_lib.TZ_HIST_BINS)), \
+            (n, has_prev)
+        assert int(ovf[0]) == 0
+        table = ops.build_table(hist.cpu().numpy())
+        lut = torch.from_numpy(ops.encode_lut(table)).to(dev)
+        ranks = ops.finding_difference_rank(x_t, lut, has_prev=has_prev, prev_x=prev_x).cpu().numpy()
+        pos = {int(s): i for i, s in enumerate(table)}
+        assert np.array_equal(ranks, np.array([pos[int(s)] for s in sym], np.int16)), (n, has_prev)
+        raw = ops.finding_difference_rank(x_t, None, has_prev=has_prev, prev_x=prev_x).cpu().numpy()
+        assert np.array_equal(raw, y), (n, has_prev)
+
+
+@pytest.mark.parametrize("H,W,C,nt", [(8, 8, 1, 70), (4, 8, 3, 41), (16, 24, 3, 9), (5, 7, 3, 30), (128, 160, 3, 3)])
+def test_stream_kernels_many_small_frames(cuda_lib, H, W, C, nt):
+    """Fused lossless passes and the decoder where a 1024-element chunk spans many frames (tiny frames: the in-frame
+    offset wraps several times inside one chunk), rows that are / are not multiples of 8 samples, key frames inside
+    the stream: the two passes equal the unfused kernels on the materialised residual, and the decoder returns the
+    frames and x."""
+    import torch
+    from tezip_b200 import ops, _lib
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(H * W + nt)
+    frames = rng.randint(0, 256, size=(nt, H, W, C)).astype(np.uint8)
+    pool_np = rng.rand(nt + 1, H, W, C).astype(np.float32)
+    slot_np = np.arange(1, nt + 1, dtype=np.int32)
+    slot_np[::5] = -1                                   # window starts: x = 0, decoded from the key plane
+    fr, pool, slot = (torch.from_numpy(a).to(dev) for a in (frames, pool_np, slot_np))
+    x = ops.residual(fr, pool, slot)
+    x_np = x.cpu().numpy().reshape(-1)
+    q = (pool_np[np.maximum(slot_np, 0)] * np.float32(255)).astype(np.int64)      # trunc toward zero (values >= 0)
+    ref = np.where((slot_np >= 0)[:, None, None, None], q - frames, 0).reshape(-1)
+    assert np.array_equal(x_np, ref.astype(np.int16))
+    hist_a = torch.zeros(_lib.TZ_HIST_BINS, dtype=torch.int64, device=dev)
+    hist_b = torch.zeros_like(hist_a)
+    ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+    ops.finding_difference_hist(x, hist_a, ovf)
+    ops.encode_lossless(fr, pool, slot, 0, hist=hist_b, overflow=ovf)
+    assert torch.equal(hist_a, hist_b) and int(ovf[0]) == 0
+    table = ops.build_table(hist_a.cpu().numpy())
+    lut = torch.from_numpy(ops.encode_lut(table)).to(dev)
+    body_a = ops.finding_difference_rank(x, lut)
+    body_b = torch.empty_like(body_a)
+    ops.encode_lossless(fr, pool, slot, 1, lut=lut, out=body_b)
+    assert torch.equal(body_a, body_b)
+    key_plane = torch.from_numpy(np.where((slot_np < 0)[:, None, None, None], frames, 0).astype(np.uint8)).to(dev)
+    lut_d = torch.from_numpy(ops.decode_lut(table)).to(dev)
+    out, x_back = ops.reconstruct(body_a, (nt, H, W, C), H, W, len(table), lut_d, pool, slot, key_plane, want_x=True)
+    assert np.array_equal(x_back.cpu().numpy(), x_np)
+    assert np.array_equal(out.cpu().numpy(), frames)    # lossless: P - (P - frame), and the key frames verbatim

@@ -268,3 +268,23 @@ def test_run_plan_arrival_ranges_cover_the_sequence_in_order():
             assert calls == want
     finally:
         codec.ops.pad_normalize = real
+
+
+def test_container_level_override_and_concurrent_frames(tmp_path, monkeypatch):
+    """write_container compresses the two files concurrently and honours TEZIP_ZSTD_LEVEL; every level gives single
+    frames with content size that read_container (and the reference's zstd.decompress) take."""
+    from tezip_b200 import container
+    rng = np.random.RandomState(3)
+    payload = (rng.geometric(0.3, size=200000) - 1).astype(np.int16)
+    key = np.zeros(50000, np.uint8)
+    key[:5000] = rng.randint(0, 256, 5000)
+    sizes = {}
+    for lvl, workers in (("9", 0), ("3", 4), ("1", 2)):
+        monkeypatch.setenv("TEZIP_ZSTD_LEVEL", lvl)
+        d = str(tmp_path / ("c" + lvl))
+        sizes[lvl] = container.write_container(d, ["a.png", "b.png"], True, key, payload, workers=workers)
+        names, rgb, k2, p2 = container.read_container(d)
+        assert names == ["a.png", "b.png"] and rgb and np.array_equal(k2, key) and np.array_equal(p2, payload)
+    monkeypatch.delenv("TEZIP_ZSTD_LEVEL")
+    assert container.container_level() == 9
+    assert sizes["9"][1] <= sizes["1"][1]
