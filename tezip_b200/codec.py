@@ -393,8 +393,8 @@ class _Landing:
         return self.tm[wide]
 
     def flag_pair(self, nt):
-        if self.flags is None or self.flags.shape[1] < nt:
-            self.flags = torch.empty((2, max(nt, 1024)), dtype=torch.uint8).pin_memory()
+        if self.flags is None or self.flags.shape[1] < nt:   # generous: growing means a cudaHostAlloc (a device-wide stall)
+            self.flags = torch.empty((2, max(2 * nt, 32768)), dtype=torch.uint8).pin_memory()
         return self.flags[0, :nt], self.flags[1, :nt]
 
 
