@@ -128,7 +128,7 @@ def load_predictor(WEIGHTS_DIR, max_batch, device=0):
 
 
 def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE, BOUND_VALUE, VERBOSE, ENTROPY_RUN,
-                zstd_workers=0, THRESHOLD=None, dwp_chains=1):
+                zstd_workers=None, THRESHOLD=None, dwp_chains=1):
     """compress.run under torchrun (one process per GPU): every rank decodes and encodes the images of its own shard,
     the ranks exchange the 1-element delta halo and sum the symbol histogram (dist.ShardComm), rank 0 gathers the
     streams and writes the single container.  Static windows (-w): window-aligned shards
@@ -183,7 +183,7 @@ def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE
 
 
 def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, MODE, BOUND_VALUE, GPU_FLAG, VERBOSE,
-        ENTROPY_RUN, dwp_chains=1, zstd_workers=0):
+        ENTROPY_RUN, dwp_chains=1, zstd_workers=None):
     if not GPU_FLAG:
         _die("ERROR: tezip_b200 has no CPU path; a B200 (sm_100) GPU is required.")
     from . import dist as tzdist

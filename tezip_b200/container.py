@@ -14,7 +14,7 @@ import numpy as np
 ZSTD_LEVEL = 9                       # compress.py:276,398
 MAX_DECODED_BYTES = 1 << 37          # 128 GiB: a 32767-frame 1024x1024x1 v2 stream is 2^37 bytes
 KEY_FILE, ENTROPY_FILE, NAMES_FILE = "key_frame.dat", "entropy.dat", "filename.txt"
-_ZSTD_c_compressionLevel, _ZSTD_c_contentSizeFlag, _ZSTD_c_nbWorkers = 100, 200, 400
+_ZSTD_c_compressionLevel, _ZSTD_c_contentSizeFlag, _ZSTD_c_nbWorkers, _ZSTD_c_jobSize = 100, 200, 400, 401
 
 _z = None
 
@@ -51,6 +51,10 @@ def zstd_compress(buf, level=ZSTD_LEVEL, workers=0):
             z.ZSTD_CCtx_setParameter(c, _ZSTD_c_compressionLevel, level)
             z.ZSTD_CCtx_setParameter(c, _ZSTD_c_contentSizeFlag, 1)
             z.ZSTD_CCtx_setParameter(c, _ZSTD_c_nbWorkers, int(workers))
+            # libzstd's default job is 4 x the window (32 MB at level 9): a 123 MB stream would keep four workers
+            # busy.  Jobs of n / (4 x workers), between 1 and 8 MB, keep them all busy; the compressed size is unchanged
+            # to four digits (the jobs still overlap: ZSTD_c_overlapLog is left at its default)
+            z.ZSTD_CCtx_setParameter(c, _ZSTD_c_jobSize, int(min(8 << 20, max(1 << 20, n // (4 * int(workers))))))
             r = z.ZSTD_compress2(c, dst.ctypes.data, cap, a.ctypes.data, n)
         finally:
             z.ZSTD_freeCCtx(c)
@@ -90,7 +94,14 @@ def container_level():
     return int(os.environ.get("TEZIP_ZSTD_LEVEL", str(ZSTD_LEVEL)))
 
 
-def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
+def default_workers():
+    """zstd worker threads of the container stage: TEZIP_ZSTD_WORKERS, else every host core (0 = libzstd's
+    single-threaded encoder).  Any count gives one frame with content size, which is all the reference's decoder needs."""
+    v = os.environ.get("TEZIP_ZSTD_WORKERS")
+    return int(v) if v is not None else (os.cpu_count() or 1)
+
+
+def write_container(out_dir, names, is_rgb, key_plane, payload, workers=None):
     """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd).
     Container v2 (16-bit samples): key_plane u16 and payload int32, both little-endian, same three files.
     The two zstd frames are produced concurrently (libzstd releases the GIL under ctypes)."""
@@ -103,6 +114,8 @@ def write_container(out_dir, names, is_rgb, key_plane, payload, workers=0):
     if wide != (np.asarray(key_plane).dtype == np.uint16):
         raise ValueError("key plane and stream disagree about the sample width")
     level = container_level()
+    if workers is None:
+        workers = default_workers()
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(2) as pool:
         fk = pool.submit(zstd_compress, np.ascontiguousarray(key_plane, "<u2" if wide else np.uint8), level,
