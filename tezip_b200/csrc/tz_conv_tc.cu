@@ -1504,6 +1504,13 @@ static int make_conv(tz_prednet *h, ConvTc *c, int epi, int l, __half *X, int cx
   if (epi == 1) {
     A.R = n_real;
     n_unit = largest_divisor_le(n_real, 64);
+    // A/B switch for the im2col-fed gate convolution (image width not a multiple of 8: gates3 of the 128x160 net):
+    // R channels per N tile.  64 (N = 256) leaves 750 tile units for 148 CTAs; 48 (N = 192) gives 1000 smaller ones.
+    const char *gu = getenv("TZ_GATE_UNIT");
+    if (gu && (A.W % 8) != 0) {
+      const int u = atoi(gu);
+      if (u > 0 && u <= 64 && n_real % u == 0) n_unit = u;
+    }
   } else {
     n_unit = largest_divisor_le(n_real, 256);
   }
