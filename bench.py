@@ -898,6 +898,35 @@ def run_native(args):
             net_w.close()
     sweep["w%d" % Wn] = {"decompress_MB_per_s": world * raw_bytes / 1e6 / (ms_d * 1e-3), "ms": ms_d}
 
+    # ---- BASELINE configs[0] (lossless, 100 frames, window 10 -- the reference's own CPU-runnable case) as a sub-record:
+    # only ten windows are in flight, so this is the small-batch end of the same kernels
+    c1_rec = None
+    if not args.dwp and not args.no_subrecords:
+        n1 = min(100, nt)
+        fr1 = frames_dev[:n1].contiguous()
+        keep1 = {}
+
+        def c1_compress():
+            keep1["enc"] = codec.encode_frames(fr1, net, 0, 10, None, "abs", [0.0], True, comm=comm)
+
+        def c1_decompress():
+            e = keep1["enc"]
+            keep1["out"] = codec.decode_arrays(e.key_plane, e.body, e.table, e.shape, 0, net, first_mode=first_mode,
+                                               first_x=first_x)[0]
+        ms1c, _w, l1c = timed(c1_compress, args.steps, 2)
+        ms1d, _w, _l = timed(c1_decompress, args.steps, 2)
+        c1_rec = {"workload": "lossless (abs 0), %d x 128x160x3 u8 frames per GPU, window 10, p=0 (BASELINE configs[0])" % n1,
+                  "compress": {"value": world * fr1.numel() / 1e6 / (ms1c * 1e-3), "unit": "MB/s", "ms_per_step": ms1c},
+                  "decompress": {"value": world * fr1.numel() / 1e6 / (ms1d * 1e-3), "unit": "MB/s", "ms_per_step": ms1d},
+                  "lossless_roundtrip_exact": bool(torch.equal(keep1["out"], fr1)), "windows_in_flight": -(-n1 // 10),
+                  "table_symbols": int(len(keep1["enc"].table)), "gpu_launches": int(l1c)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from tezip_b200 import container as tzc1
+            e1 = keep1["enc"]
+            c1_rec["ratio_zstd9"] = fr1.numel() / float(len(tzc1.zstd_compress(e1.payload())) +
+                                                      len(tzc1.zstd_compress(e1.key_plane.cpu().numpy())))
+        del keep1, fr1
+
     # ---- BASELINE configs[2] (dynamic windows, 10k frames over 8 GPUs = 1250 per GPU) as a sub-record of every line
     dwp_rec = None
     if not args.dwp and not args.no_subrecords:
@@ -1031,7 +1060,7 @@ def run_native(args):
                                                           # table before it queues the next step (GPU idles meanwhile)
             "clocks": clocks, "max_abs_error_levels": maxerr,
             "roofline": roofline, "roofline_codec": roofline_codec, "cpu_baseline": cpu, "ratio": ratio,
-            "decompress_sweep": sweep, "container": cont, "dwp": dwp_rec, "config4": c4_rec,
+            "decompress_sweep": sweep, "container": cont, "config1": c1_rec, "dwp": dwp_rec, "config4": c4_rec,
             "prednet_gflop_per_frame": net.flops_per_frame() / 1e9,
         }
         print(json.dumps(line))

@@ -398,6 +398,34 @@ class _Landing:
         return self.flags[0, :nt], self.flags[1, :nt]
 
 
+_STAGING = {}
+
+
+def _staging(device, name, shape, dtype, depth=3):
+    """Device staging buffers of the streaming host-buffer calls: a ring of `depth` tensors per (device, purpose,
+    shape, type), allocated once, with one event per slot ("busy until") that the NEXT user of the slot waits for.
+    The caching allocator is deliberately not used here: a tensor that is filled on a copy stream and read on the
+    compute stream can only be recycled after cross-stream events, so its blocks come free at timing-dependent
+    moments and an occasional cudaMalloc lands in the middle of a stream of sequences -- seen to stall the host for
+    50-170 ms.  -> (tensor, ring, slot index); the caller stores ring["busy"][slot] when it has queued its last
+    reader."""
+    key = (str(device), name, tuple(int(v) for v in shape), dtype)
+    ring = _STAGING.get(key)
+    if ring is None:
+        stale = [k for k in _STAGING if k[:2] == key[:2]]       # another shape for the same purpose: drop the old ring
+        if stale:
+            torch.cuda.synchronize(device)                      # (copies on the side streams may still touch it)
+            for k in stale:
+                del _STAGING[k]
+        bufs = [torch.empty(key[2], dtype=dtype, device=device) for _ in range(depth)]
+        # fresh blocks may alias memory that kernels already queued on the current stream still use
+        born = torch.cuda.current_stream(device).record_event()
+        ring = _STAGING[key] = {"bufs": bufs, "busy": [born] * depth, "i": 0}
+    i = ring["i"]
+    ring["i"] = (i + 1) % depth
+    return ring["bufs"][i], ring, i
+
+
 _LANDING = {}
 
 
@@ -672,6 +700,8 @@ def encode_with_pool(frames, pool, pred_slot_np, apply_np, keys, p, mode, bound,
                     rank_pass(torch.from_numpy(ops.encode_lut(table)).to(dev))
                     if sink is not None:
                         sink.finish()
+                    if defer:   # (rare) the repeated pass may re-read a staging buffer that is about to be recycled
+                        torch.cuda.current_stream(dev).synchronize()
         check_key_frames(staged)
         return table
 
@@ -731,12 +761,12 @@ def parse_payload(data):
 
 
 def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mode=0, first_x=0, body_event=None,
-                  nonzero=None):
+                  nonzero=None, out=None):
     """decompress.py:115-256,269 on device tensors: key_plane u8 [nt,H,W,C], body int16 [N] -> u8 frames.
     body_event: optional CUDA event after which `body` is valid (its host->device copy may still be in flight on
     another stream while the predictions are replayed; only the final reconstruct needs it).
     nonzero: optional host u8[nt], the key-frame flags of decompress.py:123-127 when the caller has already computed
-    them (decode_arrays_host does, on its upload stream)."""
+    them (decode_arrays_host does, on its upload stream).  out: optional preallocated result tensor."""
     _one, nt, H, W, C = shape
     dev = key_plane.device
     Hp, Wp = padding_size(H), padding_size(W)
@@ -761,7 +791,7 @@ def decode_arrays(key_plane, body, table, shape, p, net, want_x=False, first_mod
     if body_event is not None:
         torch.cuda.current_stream(dev).wait_event(body_event)
     return ops.reconstruct(body, (nt, H, W, C), Hp, Wp, tl, lut, pool, pred_slot, key_plane, first_mode, first_x,
-                           want_x=want_x), plan
+                           want_x=want_x, out=out), plan
 
 
 def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_host, body_host, entropy=True,
@@ -781,16 +811,19 @@ def encode_frames_host(frames_host, net, p, window, threshold, mode, bound, key_
         # streaming: the host runs a sequence ahead of the GPU, so the whole upload goes to the upload stream NOW (it
         # lands while the previous sequence is still being predicted) instead of key-frames-first on the compute stream
         main, side = torch.cuda.current_stream(dev), side_stream(dev, "in")
-        with torch.cuda.stream(side):          # allocated from the upload stream's pool: free to be written at once
-            frames = frames_host.to(dev, non_blocking=True)
+        frames, ring, slot = _staging(dev, "frames_in", frames_host.shape, frames_host.dtype)
+        side.wait_event(ring["busy"][slot])    # the sequence that last used this staging buffer has been encoded
+        with torch.cuda.stream(side):
+            frames.copy_(frames_host, non_blocking=True)
             landed = side.record_event()
-        frames.record_stream(main)
         main.wait_event(landed)
         ready = None
     else:
-        frames, ready = upload_frames(frames_host, dev, p, window, threshold)
+        frames, ready, ring = upload_frames(frames_host, dev, p, window, threshold) + (None,)
     enc = encode_frames(frames, net, p, window, threshold, mode, bound, entropy, dwp_chains, comm=comm, sink=sink,
                         frames_ready=ready, defer=defer)
+    if ring is not None:
+        ring["busy"][slot] = torch.cuda.current_stream(dev).record_event()   # every reader of `frames` is queued
     enc.copies_done = sink.done
     return enc
 
@@ -836,28 +869,37 @@ def decode_arrays_host(key_host, body_host, table, shape, p, net, out_host, firs
     main = torch.cuda.current_stream(dev)
     _one, nt, H, W, C = shape
     s_in = side_stream(dev, "in")
-    with torch.cuda.stream(s_in):      # allocations below belong to the upload stream's pool: safe to fill right away
-        key_plane = key_host.to(dev, non_blocking=True)
+    # device staging from rings (see _staging): key plane and stream are filled on the upload stream, read on the
+    # compute stream; the result is written on the compute stream and read by the download stream
+    key_plane, kring, kslot = _staging(dev, "key_in", key_host.shape, key_host.dtype)
+    body, bring, bslot = _staging(dev, "body_in", body_host.shape, body_host.dtype)
+    s_in.wait_event(kring["busy"][kslot])
+    s_in.wait_event(bring["busy"][bslot])
+    with torch.cuda.stream(s_in):
+        key_plane.copy_(key_host, non_blocking=True)
         nz_dev = ops.frames_nonzero(key_plane.view(nt, H, W, C))
         nz_host = _flag_scratch(dev, nt)[0]
         nz_host.copy_(nz_dev, non_blocking=True)
         ev_key = s_in.record_event()
-        body = body_host.to(dev, non_blocking=True)
+        body.copy_(body_host, non_blocking=True)
         ev_body = s_in.record_event()
-    key_plane.record_stream(main)      # used by the kernels of the main stream from here on
-    body.record_stream(main)
     ev_key.synchronize()               # the host needs the key positions to build the schedule
     nz = nz_host.numpy().copy()
     main.wait_event(ev_key)
-    out, plan = decode_arrays(key_plane, body, table, shape, p, net, first_mode=first_mode, first_x=first_x,
-                              body_event=ev_body, nonzero=nz)
+    out_dev = oring = None
+    if not wait_copies:
+        out_dev, oring, oslot = _staging(dev, "frames_out", (nt, H, W, C), key_host.dtype)
+        main.wait_event(oring["busy"][oslot])      # its previous contents have been downloaded
+    out, plan = decode_arrays(key_plane.view(nt, H, W, C), body.view(-1), table, shape, p, net, first_mode=first_mode,
+                              first_x=first_x, body_event=ev_body, nonzero=nz, out=out_dev)
+    kring["busy"][kslot] = bring["busy"][bslot] = main.record_event()   # every reader of the two inputs is queued
     if wait_copies:
         out_host.copy_(out, non_blocking=True)
         return out, plan
     s_out = side_stream(dev, "out")
     s_out.wait_event(main.record_event())
-    out.record_stream(s_out)
     with torch.cuda.stream(s_out):
         out_host.copy_(out, non_blocking=True)
         done = s_out.record_event()
+    oring["busy"][oslot] = done
     return out, plan, done

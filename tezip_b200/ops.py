@@ -280,21 +280,28 @@ def decode_lut(table):
 
 
 def reconstruct(body, shape, Hp, Wp, table_len, rank_lut, pred_pool, pred_slot, key_plane, first_mode=0, first_x=0,
-                want_x=False):
-    """decompress.py:229,236,240-245,252-256,269 -> u8 [n,H,W,C] (and x int16 if want_x)."""
+                want_x=False, out=None):
+    """decompress.py:229,236,240-245,252-256,269 -> u8 [n,H,W,C] (and x int16 if want_x).
+    out: optional preallocated result (same shape and sample type), e.g. a staging buffer the caller recycles."""
     n, H, W, C = shape
     dev = body.device
     lib = _lib.load()
+    if out is not None:
+        want = torch.uint16 if is_wide(body) else torch.uint8
+        if tuple(out.shape) != (n, H, W, C) or out.dtype != want or not out.is_contiguous() or out.device != dev:
+            raise ValueError("out must be a contiguous %s [%d,%d,%d,%d] tensor on %s" % (want, n, H, W, C, dev))
     if is_wide(body):
         ws = torch.empty(int(lib.tz_reconstruct16_workspace_bytes(n * H * W * C)), dtype=torch.uint8, device=dev)
-        out = torch.empty((n, H, W, C), dtype=torch.uint16, device=dev)
+        if out is None:
+            out = torch.empty((n, H, W, C), dtype=torch.uint16, device=dev)
         x = torch.empty(n * H * W * C, dtype=torch.int32, device=dev) if want_x else None
         check(lib.tz_reconstruct16(ptr(body), n, H, W, C, Hp, Wp, int(table_len), ptr(rank_lut), int(first_mode),
                                    int(first_x), ptr(pred_pool), ptr(pred_slot), ptr(key_plane), ptr(out), ptr(x),
                                    ptr(ws), _st(dev)), "tz_reconstruct16")
         return (out, x) if want_x else out
     ws = torch.empty(int(lib.tz_reconstruct_workspace_bytes(n * H * W * C)), dtype=torch.uint8, device=dev)
-    out = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((n, H, W, C), dtype=torch.uint8, device=dev)
     x = torch.empty(n * H * W * C, dtype=torch.int16, device=dev) if want_x else None
     check(lib.tz_reconstruct(ptr(body), n, H, W, C, Hp, Wp, int(table_len), ptr(rank_lut), int(first_mode),
                              int(first_x), ptr(pred_pool), ptr(pred_slot), ptr(key_plane), ptr(out), ptr(x), ptr(ws),
