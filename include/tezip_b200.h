@@ -275,6 +275,26 @@ int tz_frames_nonzero(const uint8_t *key_plane, uint8_t *nonzero, long long nt, 
 int tz_memcpy2d_async(void *dst, long long dpitch, const void *src, long long spitch, long long width,
                       long long height, void *stream);
 
+/* ---- the container's lossless back-end: compress.py:276 (`zstd.compress(key_frame_str, 9)`) and compress.py:398
+ * (`zstd.compress(entropy bytes, 9)`) -- the reference's decoder (decompress.py:89,98 `zstd.decompress`) needs one zstd
+ * frame with its content size, nothing else.  These two calls write such a frame from `n` bytes that are already in
+ * device memory: per 128 KB block an RLE block (one repeated byte), a raw block, or a compressed block that holds the
+ * block Huffman-coded as four literal streams and no sequences (RFC 8878 3.1.1.3).  The Huffman code is the caller's
+ * (host side: tezip_b200/zstd_frames.py builds it from the histogram of tz_zstd_hist).
+ *
+ * tz_zstd_hist:   hist: device u32[256], byte counts of the blocks that are neither uniform nor shorter than 1024;
+ *                 uniform: device i32[ceil(n / 131072)], the byte value of a block that holds one value only, else -1.
+ * tz_zstd_encode: ctable: device u32[256], code | nbits << 16 (nbits <= 11; canonical order of the zstd decoder);
+ *                 tree: device bytes of the Huffman_Tree_Description, tree_len of them (0: no code, blocks are RLE or
+ *                 raw); uniform: as written by tz_zstd_hist; workspace: tz_zstd_workspace_bytes(n) device bytes;
+ *                 out: tz_zstd_bound(n) device bytes, 4-byte aligned; total: device u64, the frame's size in bytes. */
+unsigned long long tz_zstd_bound(unsigned long long n);
+unsigned long long tz_zstd_workspace_bytes(unsigned long long n);
+int tz_zstd_hist(const uint8_t *src, unsigned long long n, uint32_t *hist, int32_t *uniform, void *stream);
+int tz_zstd_encode(const uint8_t *src, unsigned long long n, const uint32_t *ctable, const uint8_t *tree,
+                   unsigned tree_len, const int32_t *uniform, void *workspace, uint8_t *out,
+                   unsigned long long *total, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

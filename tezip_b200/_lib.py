@@ -17,6 +17,7 @@ TZ_WIDE_BINS = 262144
 MODES = {"abs": 0, "rel": 1, "absrel": 2, "pwrel": 3}
 
 c_vp, c_int, c_ll, c_dbl, c_flt = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_float
+c_ull, c_uint = ctypes.c_ulonglong, ctypes.c_uint
 
 
 class TezipError(RuntimeError):
@@ -80,6 +81,10 @@ SIGNATURES = {
     "tz_key_plane": (c_int, [c_vp, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "tz_frames_nonzero": (c_int, [c_vp, c_vp, c_ll, c_ll, c_vp]),
     "tz_memcpy2d_async": (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_ll, c_vp]),
+    "tz_zstd_bound": (c_ull, [c_ull]),
+    "tz_zstd_workspace_bytes": (c_ull, [c_ull]),
+    "tz_zstd_hist": (c_int, [c_vp, c_ull, c_vp, c_vp, c_vp]),
+    "tz_zstd_encode": (c_int, [c_vp, c_ull, c_vp, c_vp, c_uint, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

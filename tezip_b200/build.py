@@ -22,7 +22,7 @@ def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         [os.path.join(HERE, "..", "include", "tezip_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -173,9 +173,14 @@ def run_sharded(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, MODE
     tdist.all_gather_object(names, files)
     if rank == 0:
         H, W, C = frames.shape[1:]
-        payload = codec.pack_payload(body.cpu().numpy(), enc.table, (1, nt, H, W, C), PREPROCESS)
-        kb, eb = container.write_container(OUTPUT_DIR, [f for part in names for f in part], isRGB,
-                                           keyp.cpu().numpy(), payload, workers=zstd_workers)
+        if container.gpu_writer():      # TEZIP_ZSTD_LEVEL=gpu: the frames are written from the device copies
+            tail = codec.pack_payload(body[:0].cpu().numpy(), enc.table, (1, nt, H, W, C), PREPROCESS)
+            kb, eb = container.write_container_device(OUTPUT_DIR, [f for part in names for f in part], isRGB,
+                                                      keyp, body, tail)
+        else:
+            payload = codec.pack_payload(body.cpu().numpy(), enc.table, (1, nt, H, W, C), PREPROCESS)
+            kb, eb = container.write_container(OUTPUT_DIR, [f for part in names for f in part], isRGB,
+                                               keyp.cpu().numpy(), payload, workers=zstd_workers)
         if VERBOSE:
             print("ranks:", world, "ratio:", nt * fe / float(kb + eb))
     tdist.barrier()
@@ -220,15 +225,21 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, PREPROCESS, WINDOW_SIZE, THRESHOLD, M
             enc = codec.encode_frames(loader.tensor.to(dev, non_blocking=True), net, PREPROCESS, WINDOW_SIZE,
                                       THRESHOLD, MODE, list(BOUND_VALUE), ENTROPY_RUN, dwp_chains=dwp_chains)
         loader.close()
-        payload = enc.payload()
-        key_plane = enc.key_plane.cpu().numpy()
+        on_gpu = container.gpu_writer()         # TEZIP_ZSTD_LEVEL=gpu: the frames are written from the device copies
+        if not on_gpu:
+            payload = enc.payload()
+            key_plane = enc.key_plane.cpu().numpy()
         torch.cuda.synchronize(dev)
         if VERBOSE:
             print("gpu_encode:{0}".format(time.time() - t0) + "[sec]")
+        t0 = time.time()
+        if on_gpu:
+            tail = codec.pack_payload(enc.body[:0].cpu().numpy(), enc.table, enc.shape, enc.p)
+            kb, eb = container.write_container_device(OUTPUT_DIR, files, isRGB, enc.key_plane, enc.body, tail)
     except TezipError as e:
         _die(str(e))
-    t0 = time.time()
-    kb, eb = container.write_container(OUTPUT_DIR, files, isRGB, key_plane, payload, workers=zstd_workers)
+    if not on_gpu:
+        kb, eb = container.write_container(OUTPUT_DIR, files, isRGB, key_plane, payload, workers=zstd_workers)
     if VERBOSE:
         print("zstd+write:{0}".format(time.time() - t0) + "[sec]")
         print("key frames:", len(enc.keys), "ratio:", frames.nbytes / float(kb + eb))

@@ -91,7 +91,15 @@ def container_level():
     """zstd level of the container files: 9 like the reference (compress.py:276,398) unless TEZIP_ZSTD_LEVEL says
     otherwise -- any level gives a frame the reference's decoder reads; lower levels trade a few per cent of ratio for
     a several times faster container stage (bench.py's `container` record quotes both)."""
-    return int(os.environ.get("TEZIP_ZSTD_LEVEL", str(ZSTD_LEVEL)))
+    v = os.environ.get("TEZIP_ZSTD_LEVEL", str(ZSTD_LEVEL))
+    return ZSTD_LEVEL if v.strip().lower() == "gpu" else int(v)
+
+
+def gpu_writer():
+    """True when TEZIP_ZSTD_LEVEL=gpu: the two frames are written by the CUDA kernels of zstd_frames.py from the device
+    copies of key plane and stream (Huffman-coded literal blocks, no match finding: an order-0 ratio at memory speed)
+    instead of by libzstd from host copies.  Either way the files are single zstd frames with content size."""
+    return os.environ.get("TEZIP_ZSTD_LEVEL", "").strip().lower() == "gpu"
 
 
 def default_workers():
@@ -101,15 +109,39 @@ def default_workers():
     return int(v) if v is not None else (os.cpu_count() or 1)
 
 
-def write_container(out_dir, names, is_rgb, key_plane, payload, workers=None):
-    """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd).
-    Container v2 (16-bit samples, DESIGN.md): key_plane u16 and payload int32, both little-endian, same three files.
-    The two zstd frames are produced concurrently (libzstd releases the GIL under ctypes)."""
+def _write_names(out_dir, names, is_rgb):
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, NAMES_FILE), "w", encoding="UTF-8") as f:     # compress.py:133-136
         f.write("%d\n" % int(is_rgb))
         for nm in names:
             f.write("%s\n" % nm)
+
+
+def write_container_device(out_dir, names, is_rgb, key_plane, body, tail):
+    """write_container with the zstd frames written on the GPU (gpu_writer()): key_plane and body are CUDA tensors
+    (u8 + int16, or u16 + int32 for container v2), tail the host array that follows the codes in entropy.dat (table,
+    its length, shape, p: codec.pack_payload of an empty body).  -> (key_frame.dat bytes, entropy.dat bytes)."""
+    import torch
+    from . import zstd_frames
+    _write_names(out_dir, names, is_rgb)
+    wide = body.dtype == torch.int32
+    if wide != (key_plane.dtype == torch.uint16) or np.asarray(tail).dtype != (np.int32 if wide else np.int16):
+        raise ValueError("key plane, stream and trailer disagree about the sample width")
+    kb = zstd_frames.compress_device(key_plane)                                              # compress.py:271-278
+    tail_dev = torch.from_numpy(np.ascontiguousarray(tail)).to(body.device)
+    eb = zstd_frames.compress_device(torch.cat([body.reshape(-1), tail_dev]))              # compress.py:394-400
+    with open(os.path.join(out_dir, KEY_FILE), "wb") as f:
+        f.write(kb)
+    with open(os.path.join(out_dir, ENTROPY_FILE), "wb") as f:
+        f.write(eb)
+    return len(kb), len(eb)
+
+
+def write_container(out_dir, names, is_rgb, key_plane, payload, workers=None):
+    """key_plane: u8 array (any shape); payload: int16 array (entropy.dat before zstd).
+    Container v2 (16-bit samples, DESIGN.md): key_plane u16 and payload int32, both little-endian, same three files.
+    The two zstd frames are produced concurrently (libzstd releases the GIL under ctypes)."""
+    _write_names(out_dir, names, is_rgb)
     wide = np.asarray(payload).dtype == np.int32
     if wide != (np.asarray(key_plane).dtype == np.uint16):
         raise ValueError("key plane and stream disagree about the sample width")

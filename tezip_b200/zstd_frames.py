@@ -1,0 +1,301 @@
+"""The container's lossless back-end on the GPU: compress.py:276,398 call
+`zstd.compress(bytes, 9)` on the key plane and on the packed stream, decompress.py:89,98 call `zstd.decompress`.
+All the reference's decoder needs is ONE valid zstd frame that carries its content size, so the frame is written
+by CUDA kernels (csrc/tz_zstd.cu) from data that is already in HBM, in the subset of the format (RFC 8878) whose
+blocks do not depend on each other: per 128 KB block an RLE block (the zero frames of the key plane cost 4 bytes),
+a raw block, or a compressed block = the block's bytes Huffman-coded as four literal streams + zero sequences.  No
+match finding: the ratio is that of an order-0 byte coder, the rate that of a memory pass (bench.py `container`
+quotes both beside libzstd level 9, which stays the default: TEZIP_ZSTD_LEVEL=gpu selects this writer).
+
+Host side (this file): the Huffman code of the frame from the device's byte histogram (length-limited to 11 bits,
+canonical order of the zstd decoder), its tree description (weights, FSE-compressed as HUF_compressWeights does or
+4-bit direct), and the calls.  The kernels do the rest; nothing here touches the data."""
+import heapq
+
+import numpy as np
+
+BLOCK = 131072
+MAX_BITS = 11                 # Max_Number_of_Bits of a literals Huffman code (RFC 8878 4.2.1)
+FRAME_HEADER = 14
+_FSE_LOG = 6                  # accuracy log of the weights' FSE table (the format's maximum for weights)
+
+
+def frame_header(n):
+    """magic, descriptor 0xC0 (8-byte content size), window descriptor 0x38 (128 KB), content size."""
+    return b"\x28\xb5\x2f\xfd\xc0\x38" + int(n).to_bytes(8, "little")
+
+
+def empty_frame():
+    return frame_header(0) + b"\x01\x00\x00"          # one empty raw block, last
+
+
+def _huffman_lengths(counts):
+    """Plain Huffman code lengths of `counts` (all > 0, at least two)."""
+    n = len(counts)
+    heap = [(int(c), i) for i, c in enumerate(counts)]
+    heapq.heapify(heap)
+    parent = [-1] * (2 * n - 1)
+    nxt = n
+    while len(heap) > 1:
+        c1, a = heapq.heappop(heap)
+        c2, b = heapq.heappop(heap)
+        parent[a] = parent[b] = nxt
+        heapq.heappush(heap, (c1 + c2, nxt))
+        nxt += 1
+    depth = [0] * (2 * n - 1)
+    for i in range(2 * n - 3, -1, -1):
+        depth[i] = depth[parent[i]] + 1
+    return np.array(depth[:n], np.int64)
+
+
+def code_lengths(hist, max_bits=MAX_BITS):
+    """hist: 256 counts -> 256 code lengths (0 = absent), complete prefix code with lengths <= max_bits; None if
+    fewer than two byte values occur (such data is RLE, not Huffman)."""
+    hist = np.asarray(hist, np.int64)
+    sym = np.nonzero(hist)[0]
+    if len(sym) < 2:
+        return None
+    counts = hist[sym].copy()
+    while True:
+        lens = _huffman_lengths(counts)
+        if lens.max() <= max_bits:
+            break
+        counts = (counts + 1) // 2                    # flatten the distribution until the deepest leaf fits
+    out = np.zeros(256, np.int64)
+    out[sym] = lens
+    return out
+
+
+def weights_and_codes(lens):
+    """-> (weights[256], ctable u32[256] = code | nbits << 16).  Weight = tableLog + 1 - length; codes in the order in
+    which zstd's decoder fills its table: weights ascending (longest codes first, from code 0), byte values ascending."""
+    lens = np.asarray(lens, np.int64)
+    table_log = int(lens.max())
+    w = np.where(lens > 0, table_log + 1 - lens, 0)
+    ct = np.zeros(256, np.uint32)
+    pos = 0
+    for wt in range(1, table_log + 1):
+        for s in np.nonzero(w == wt)[0]:
+            ct[s] = (pos >> (wt - 1)) | (int(lens[s]) << 16)
+            pos += 1 << (wt - 1)
+    assert pos == 1 << table_log, "code is not complete"
+    return w, ct
+
+
+# ---- FSE coding of the weights (zstd's HUF_compressWeights: FSE_normalizeCount / FSE_writeNCount / FSE_buildCTable /
+# FSE_compress_usingCTable restated from the published format, RFC 8878 4.1 and 4.2.1.2) ---------------------------------
+
+def _normalize(count, total, log):
+    """Normalised counts with sum 2^log and >= 1 for every symbol that occurs."""
+    size = 1 << log
+    norm = [0] * len(count)
+    for s, c in enumerate(count):
+        if c:
+            norm[s] = max(1, int(round(c * size / float(total))))
+    while sum(norm) != size:
+        diff = size - sum(norm)
+        if diff > 0:
+            norm[int(np.argmax(norm))] += diff
+        else:
+            s = int(np.argmax(norm))
+            step = min(-diff, norm[s] - 1)
+            if step == 0:
+                return None
+            norm[s] -= step
+    return norm
+
+
+def _write_ncount(norm, log):
+    size = 1 << log
+    bits, nbits = log - 5, 4
+    remaining, threshold, nb = size + 1, size, log + 1
+    symbol, alphabet, previous0 = 0, len(norm), False
+    while symbol < alphabet and remaining > 1:
+        if previous0:
+            start = symbol
+            while symbol < alphabet and norm[symbol] == 0:
+                symbol += 1
+            if symbol == alphabet:
+                break
+            while symbol >= start + 24:
+                start += 24
+                bits |= 0xFFFF << nbits
+                nbits += 16
+            while symbol >= start + 3:
+                start += 3
+                bits |= 3 << nbits
+                nbits += 2
+            bits |= (symbol - start) << nbits
+            nbits += 2
+        count = norm[symbol]
+        symbol += 1
+        mx = (2 * threshold - 1) - remaining
+        remaining -= abs(count)
+        count += 1
+        if count >= threshold:
+            count += mx
+        bits |= count << nbits
+        nbits += nb
+        nbits -= 1 if count < mx else 0
+        previous0 = count == 1
+        if remaining < 1:
+            return None
+        while remaining < threshold:
+            nb -= 1
+            threshold >>= 1
+    if remaining != 1:
+        return None
+    return bits.to_bytes((nbits + 7) // 8, "little")
+
+
+def _build_ctable(norm, log):
+    size = 1 << log
+    mask, step = size - 1, (size >> 1) + (size >> 3) + 3
+    cumul = [0]
+    for c in norm:
+        cumul.append(cumul[-1] + c)
+    spread = [0] * size
+    pos = 0
+    for s, c in enumerate(norm):
+        for _ in range(c):
+            spread[pos] = s
+            pos = (pos + step) & mask
+    assert pos == 0
+    state_table = [0] * size
+    cur = list(cumul)
+    for u in range(size):
+        s = spread[u]
+        state_table[cur[s]] = size + u
+        cur[s] += 1
+    delta_bits, delta_state = [0] * len(norm), [0] * len(norm)
+    total = 0
+    for s, c in enumerate(norm):
+        if c == 0:
+            delta_bits[s] = ((log + 1) << 16) - size
+        elif c == 1:
+            delta_bits[s] = (log << 16) - size
+            delta_state[s] = total - 1
+            total += 1
+        else:
+            max_bits_out = log - ((c - 1).bit_length() - 1)
+            delta_bits[s] = (max_bits_out << 16) - (c << max_bits_out)
+            delta_state[s] = total - c
+            total += c
+    return state_table, delta_bits, delta_state
+
+
+def fse_compress_weights(w):
+    """w: the weights of byte values 0 .. last-1 -> FSE table description + bit stream, or None when FSE cannot code
+    them (fewer than two weights, or all equal)."""
+    w = [int(v) for v in w]
+    n = len(w)
+    if n < 2:
+        return None
+    count = [0] * (max(w) + 1)
+    for v in w:
+        count[v] += 1
+    if max(count) == n:
+        return None
+    log = _FSE_LOG
+    norm = _normalize(count, n, log)
+    if norm is None:
+        return None
+    head = _write_ncount(norm, log)
+    if head is None:
+        return None
+    state_table, delta_bits, delta_state = _build_ctable(norm, log)
+    acc = [0, 0]                                       # bit container (LSB first), bit count
+
+    def add(value, nb):
+        acc[0] |= (value & ((1 << nb) - 1)) << acc[1]
+        acc[1] += nb
+
+    def init(sym):                                     # FSE_initCState2
+        nb_out = (delta_bits[sym] + (1 << 15)) >> 16
+        value = (nb_out << 16) - delta_bits[sym]
+        return state_table[(value >> nb_out) + delta_state[sym]]
+
+    def encode(state, sym):                            # FSE_encodeSymbol
+        nb_out = (state + delta_bits[sym]) >> 16
+        add(state, nb_out)
+        return state_table[(state >> nb_out) + delta_state[sym]]
+
+    ip = n
+    if n & 1:
+        s1 = init(w[ip - 1]); s2 = init(w[ip - 2]); s1 = encode(s1, w[ip - 3])
+        ip -= 3
+    else:
+        s2 = init(w[ip - 1]); s1 = init(w[ip - 2])
+        ip -= 2
+    while ip > 0:
+        s2 = encode(s2, w[ip - 1])
+        s1 = encode(s1, w[ip - 2])
+        ip -= 2
+    add(s2, log)
+    add(s1, log)
+    add(1, 1)                                          # end mark
+    return head + acc[0].to_bytes((acc[1] + 7) // 8, "little")
+
+
+def tree_description(weights):
+    """Huffman_Tree_Description (RFC 8878 4.2.1) of weights[256]: the weights of every byte value below the largest one
+    that occurs (its own weight is implied).  FSE-compressed when that is possible and shorter, else 4 bits per weight
+    (at most 128 of them), else None: no tree can be written and the blocks stay raw."""
+    weights = np.asarray(weights)
+    last = int(np.nonzero(weights)[0].max())
+    w = [int(v) for v in weights[:last]]
+    direct = None
+    if 1 <= len(w) <= 128:
+        padded = w + [0] * (len(w) & 1)
+        direct = bytes([127 + len(w)]) + bytes((padded[i] << 4) | padded[i + 1] for i in range(0, len(padded), 2))
+    fse = fse_compress_weights(w)
+    if fse is not None and 1 < len(fse) < 128 and (direct is None or len(fse) + 1 < len(direct)):
+        return bytes([len(fse)]) + fse
+    return direct
+
+
+def huffman_tables(hist):
+    """-> (ctable u32[256], tree bytes); (zeros, b"") when the bytes cannot be Huffman-coded."""
+    lens = code_lengths(hist)
+    if lens is not None:
+        w, ct = weights_and_codes(lens)
+        tree = tree_description(w)
+        if tree is not None:
+            return ct, tree
+    return np.zeros(256, np.uint32), b""
+
+
+def frame_device(t):
+    """t: a contiguous CUDA tensor (any element type; its bytes are compressed) -> (u8 CUDA tensor, size): the first
+    `size` bytes of the tensor are one zstd frame with content size.  One small device->host read in the middle (the
+    1 KB histogram: the Huffman code is built on the host) and one at the end (the size)."""
+    import torch
+    from . import _lib
+    from .ops import check, ptr, _st
+    if not t.is_cuda:
+        raise ValueError("the zstd frame writer takes a CUDA tensor (there is no CPU path)")
+    raw = t.contiguous().view(-1).view(torch.uint8)
+    n = raw.numel()
+    dev = raw.device
+    if n == 0:
+        return torch.from_numpy(np.frombuffer(empty_frame(), np.uint8).copy()).to(dev), len(empty_frame())
+    lib = _lib.load()
+    nblocks = -(-n // BLOCK)
+    hist = torch.empty(256, dtype=torch.int32, device=dev)
+    uniform = torch.empty(nblocks, dtype=torch.int32, device=dev)
+    check(lib.tz_zstd_hist(ptr(raw), n, ptr(hist), ptr(uniform), _st(dev)), "tz_zstd_hist")
+    ct, tree = huffman_tables(hist.cpu().numpy().view(np.uint32))
+    ct_dev = torch.from_numpy(ct.view(np.int32)).to(dev)
+    tree_dev = torch.from_numpy(np.frombuffer(tree + b"\0", np.uint8).copy()).to(dev)
+    ws = torch.empty(int(lib.tz_zstd_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    out = torch.empty(int(lib.tz_zstd_bound(n)), dtype=torch.uint8, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    check(lib.tz_zstd_encode(ptr(raw), n, ptr(ct_dev), ptr(tree_dev), len(tree), ptr(uniform), ptr(ws), ptr(out),
+                             ptr(total), _st(dev)), "tz_zstd_encode")
+    return out, int(total.item())
+
+
+def compress_device(t):
+    """-> bytes: the frame of frame_device(t), copied to the host."""
+    out, size = frame_device(t)
+    return out[:size].cpu().numpy().tobytes()
