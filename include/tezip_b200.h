@@ -295,6 +295,16 @@ int tz_zstd_encode(const uint8_t *src, unsigned long long n, const uint32_t *cta
                    unsigned tree_len, const int32_t *uniform, void *workspace, uint8_t *out,
                    unsigned long long *total, void *stream);
 
+/* decompress.py:89,98 (`zstd.decompress`) for frames of that subset: the host walks the frame and block headers
+ * (tezip_b200/zstd_frames.py parse_frame; any other frame is decoded by libzstd as in the reference) and the device
+ * decodes all blocks, and the four Huffman streams of each, at once.
+ * frame: the compressed frame in device memory; blocks: device array of nblocks records {u64 src_off, u64 dst_off,
+ * u32 type (0 raw, 1 RLE, 2 Huffman), u32 regen, u32 stream_bytes[4], u32 table, u32 pad} (48 bytes each); dtables:
+ * device u16[T][2048], symbol | nbits << 8 indexed by the next 11 bits (NULL if no block is Huffman-coded); out: the
+ * decoded content; err: device i32, 0 or the code of a malformed stream. */
+int tz_zstd_decode(const uint8_t *frame, const void *blocks, unsigned long long nblocks, const uint16_t *dtables,
+                   uint8_t *out, int32_t *err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

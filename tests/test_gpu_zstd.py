@@ -23,6 +23,8 @@ def test_device_frame_equals_emulation(cuda_lib, name):
     assert raw.size == 0 or cuda_lib.tz_launch_count() > l0
     assert np.array_equal(container.zstd_decompress(frame), raw)
     assert frame == zstd_emu.compress(a)
+    back = zf.decompress_device(frame, "cuda:0")             # the device decoder reads it back
+    assert back is not None and back.dtype == torch.uint8 and np.array_equal(back.cpu().numpy(), raw)
 
 
 def test_device_frame_large_stream(cuda_lib):
@@ -35,6 +37,20 @@ def test_device_frame_large_stream(cuda_lib):
     frame = zf.compress_device(t)
     assert len(frame) < t.numel()           # < 8 bits per int16 code
     assert np.array_equal(container.zstd_decompress(frame).view("<i2"), t.cpu().numpy())
+    assert torch.equal(zf.decompress_device(frame, t.device).view(torch.int16), t)
+
+
+def test_device_decoder_leaves_libzstd_frames_alone_and_reports_corruption(cuda_lib):
+    import torch
+    from tezip_b200 import container, zstd_frames as zf
+    a = (np.arange(300000) % 251).astype(np.uint8)
+    assert zf.decompress_device(container.zstd_compress(a), "cuda:0") is None
+    src = torch.from_numpy(np.random.default_rng(4).geometric(0.2, 200000).clip(0, 255).astype(np.uint8)).cuda()
+    frame = bytearray(zf.compress_device(src))
+    _content, blocks, _tables = zf.parse_frame(bytes(frame))
+    frame[int(blocks[0]["src_off"]) + int(blocks[0]["stream_bytes"][0]) - 1] = 0
+    with pytest.raises(RuntimeError):
+        zf.decompress_device(bytes(frame), "cuda:0")
 
 
 def test_container_written_on_gpu_round_trips(cuda_lib, tmp_path, monkeypatch):

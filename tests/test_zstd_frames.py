@@ -85,3 +85,58 @@ def test_gpu_writer_switch(monkeypatch):
     assert container.gpu_writer() and container.container_level() == 9
     monkeypatch.setenv("TEZIP_ZSTD_LEVEL", "3")
     assert not container.gpu_writer() and container.container_level() == 3
+
+
+@pytest.mark.parametrize("name", sorted(zstd_emu.cases()))
+def test_emulated_decoder_reads_the_frames(name):
+    """Header walk (zstd_frames.parse_frame, tree descriptions included) + the per-stream decoder bodies."""
+    a = zstd_emu.cases()[name]
+    raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    got = zstd_emu.decompress(zstd_emu.compress(a))
+    assert got is not None and np.array_equal(got, raw)
+
+
+def test_weights_survive_fse_round_trip():
+    for seed in range(200):
+        r = np.random.default_rng(seed)
+        k = int(r.integers(3, 257))
+        hist = np.zeros(256, np.int64)
+        hist[r.permutation(256)[:k]] = (r.random(k) ** int(r.integers(1, 10)) * 1e6).astype(np.int64) + 1
+        w, ct = zf.weights_and_codes(zf.code_lengths(hist))
+        last = int(np.nonzero(w)[0].max())
+        packed = zf.fse_compress_weights(w[:last])
+        if packed is not None:
+            assert zf.fse_decompress_weights(packed) == [int(v) for v in w[:last]], seed
+        tree = zf.tree_description(w)
+        if tree is not None:
+            table, used = zf.decode_table(tree)
+            assert used == len(tree)
+            for s in np.nonzero(w)[0]:                      # every code of the encoder's table decodes to its byte
+                code, nb = int(ct[s]) & 0xFFFF, int(ct[s]) >> 16
+                e = int(table[code << (zf.DLOG - nb)])
+                assert e & 0xFF == s and e >> 8 == nb
+
+
+def test_frames_outside_the_subset_are_left_to_libzstd():
+    a = (np.arange(300000) % 251).astype(np.uint8)
+    assert zf.parse_frame(container.zstd_compress(a)) is None                 # matches and sequences
+    assert zf.parse_frame(container.zstd_compress(a, workers=2)) is None
+    assert zf.parse_frame(b"") is None and zf.parse_frame(b"\x28\xb5\x2f\xfd") is None
+    good = zstd_emu.compress(np.random.default_rng(3).geometric(0.2, 200000).clip(0, 255).astype(np.uint8))
+    assert zf.parse_frame(good) is not None
+    assert zf.parse_frame(good[:-1]) is None and zf.parse_frame(good + b"\0") is None   # truncated / trailing bytes
+
+
+def test_corrupt_stream_is_reported():
+    a = np.random.default_rng(4).geometric(0.2, 200000).clip(0, 255).astype(np.uint8)
+    frame = bytearray(zstd_emu.compress(a))
+    content, blocks, tables = zf.parse_frame(bytes(frame))
+    end = int(blocks[0]["src_off"]) + int(blocks[0]["stream_bytes"][0])
+    frame[end - 1] = 0                                                        # the first stream loses its end mark
+    with pytest.raises(RuntimeError):
+        zstd_emu.decompress(bytes(frame))
+    start = int(blocks[0]["src_off"])
+    frame[start:end - 1] = bytes(end - 1 - start)                             # all-zero payload: every symbol takes the
+    frame[end - 1] = 1                                                        # longest code, the stream runs out of bits
+    with pytest.raises(RuntimeError):
+        zstd_emu.decompress(bytes(frame))

@@ -79,4 +79,26 @@ unsigned long long emu_encode(const uint8_t *src, unsigned long long n, const ui
   return run;
 }
 
+// tz_zstd_decode: zs_copy_kernel + zs_decode_kernel.  Returns the largest error code (0 = fine).
+int emu_decode(const uint8_t *frame, const ZsDBlock *blk, unsigned long long nblocks, const uint16_t *dtables,
+               uint8_t *out) {
+  int err = 0;
+  for (uint64_t b = 0; b < nblocks; ++b) {
+    const ZsDBlock &k = blk[b];
+    if (k.type == ZS_RLE) memset(out + k.dst_off, frame[k.src_off], k.regen);
+    else if (k.type == ZS_RAW) memcpy(out + k.dst_off, frame + k.src_off, k.regen);
+  }
+  for (uint64_t t = 0; t < nblocks * 4; ++t) {
+    const ZsDBlock &k = blk[t >> 2];
+    uint32_t s = (uint32_t)t & 3u;
+    if (k.type != ZS_HUF) continue;
+    uint64_t so = k.src_off;
+    for (uint32_t i = 0; i < s; ++i) so += k.stream_bytes[i];
+    int r = zs_decode_stream(frame + so, k.stream_bytes[s], dtables + ((uint64_t)k.table << ZS_DLOG),
+                             out + k.dst_off + (uint64_t)s * zs_seg_len(k.regen, 0), zs_seg_len(k.regen, s));
+    if (r > err) err = r;
+  }
+  return err;
+}
+
 }  // extern "C"

@@ -26,6 +26,7 @@ def load():
         e.emu_bound.restype, e.emu_bound.argtypes = ull, [ull]
         e.emu_hist.restype, e.emu_hist.argtypes = None, [vp, ull, vp, vp]
         e.emu_encode.restype, e.emu_encode.argtypes = ull, [vp, ull, vp, vp, ctypes.c_uint, vp, vp]
+        e.emu_decode.restype, e.emu_decode.argtypes = ctypes.c_int, [vp, vp, ull, vp, vp]
         _emu = e
     return _emu
 
@@ -47,6 +48,24 @@ def compress(a):
     size = emu.emu_encode(raw.ctypes.data, n, ct.ctypes.data, tb.ctypes.data, len(tree), uniform.ctypes.data,
                           out.ctypes.data)
     return out.view(np.uint8)[:size].tobytes()
+
+
+def decompress(frame):
+    """What tezip_b200.zstd_frames.decompress_device returns for `frame`, computed on the CPU; None if the frame is
+    outside the subset the kernels read."""
+    from tezip_b200 import zstd_frames as zf
+    parsed = zf.parse_frame(frame)
+    if parsed is None:
+        return None
+    content, blocks, tables = parsed
+    out = np.zeros(max(content, 1), np.uint8)
+    src = np.frombuffer(frame, np.uint8).copy()
+    blocks = np.ascontiguousarray(blocks)
+    tables = np.ascontiguousarray(tables)
+    err = load().emu_decode(src.ctypes.data, blocks.ctypes.data, len(blocks), tables.ctypes.data, out.ctypes.data)
+    if err:
+        raise RuntimeError("corrupt zstd frame (Huffman stream error %d)" % err)
+    return out[:content]
 
 
 def cases():

@@ -85,6 +85,7 @@ SIGNATURES = {
     "tz_zstd_workspace_bytes": (c_ull, [c_ull]),
     "tz_zstd_hist": (c_int, [c_vp, c_ull, c_vp, c_vp, c_vp]),
     "tz_zstd_encode": (c_int, [c_vp, c_ull, c_vp, c_vp, c_uint, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tz_zstd_decode": (c_int, [c_vp, c_vp, c_ull, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

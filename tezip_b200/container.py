@@ -127,14 +127,15 @@ def write_container_device(out_dir, names, is_rgb, key_plane, body, tail):
     wide = body.dtype == torch.int32
     if wide != (key_plane.dtype == torch.uint16) or np.asarray(tail).dtype != (np.int32 if wide else np.int16):
         raise ValueError("key plane, stream and trailer disagree about the sample width")
-    kb = zstd_frames.compress_device(key_plane)                                              # compress.py:271-278
+    sizes = []
     tail_dev = torch.from_numpy(np.ascontiguousarray(tail)).to(body.device)
-    eb = zstd_frames.compress_device(torch.cat([body.reshape(-1), tail_dev]))              # compress.py:394-400
-    with open(os.path.join(out_dir, KEY_FILE), "wb") as f:
-        f.write(kb)
-    with open(os.path.join(out_dir, ENTROPY_FILE), "wb") as f:
-        f.write(eb)
-    return len(kb), len(eb)
+    for fn, t in ((KEY_FILE, key_plane),                                                   # compress.py:271-278
+                  (ENTROPY_FILE, torch.cat([body.reshape(-1), tail_dev]))):                # compress.py:394-400
+        frame = zstd_frames.frame_host(t)          # a view of a pinned buffer: written out before the next frame
+        with open(os.path.join(out_dir, fn), "wb") as f:
+            f.write(memoryview(frame))
+        sizes.append(int(frame.size))
+    return sizes[0], sizes[1]
 
 
 def write_container(out_dir, names, is_rgb, key_plane, payload, workers=None):
@@ -177,3 +178,41 @@ def read_container(comp_dir):
     if is_v2_payload(raw):
         return names, is_rgb, key_plane.view("<u2"), raw.view("<i4")
     return names, is_rgb, key_plane, raw.view("<i2")
+
+
+def read_container_device(comp_dir, device):
+    """read_container with the two frames decoded on the GPU: -> (names, is_rgb, key plane, payload) as CUDA tensors
+    (u8 + int16, or u16 + int32 for container v2), or None when a frame uses parts of the zstd format that the kernels
+    of zstd_frames.py do not read (frames written by libzstd: read_container decodes those, like decompress.py:89,98).
+    TEZIP_ZSTD_DECODER=cpu turns this path off."""
+    if os.environ.get("TEZIP_ZSTD_DECODER", "").strip().lower() == "cpu":
+        return None
+    import torch
+    from . import zstd_frames
+    from .codec import V2_MAGIC
+    raws = []
+    for fn in (KEY_FILE, ENTROPY_FILE):
+        data = np.fromfile(os.path.join(comp_dir, fn), np.uint8)
+        parsed_size = zstd_frames.parse_frame(data)
+        if parsed_size is None:
+            return None
+        cap = int(os.environ.get("TEZIP_MAX_DECODED_BYTES", str(MAX_DECODED_BYTES)))
+        if parsed_size[0] > cap:
+            raise RuntimeError("zstd frame declares %d bytes of content, more than the limit of %d "
+                               "(TEZIP_MAX_DECODED_BYTES)" % (parsed_size[0], cap))
+        raws.append(zstd_frames.decompress_device(data, device, parsed=parsed_size))
+    with open(os.path.join(comp_dir, NAMES_FILE), "r", encoding="UTF-8") as f:
+        names = [s.strip() for s in f.readlines()]
+    is_rgb = True
+    if names and len(names[0]) == 1 and names[0].isdigit():                               # decompress.py:55-56
+        is_rgb = bool(int(names.pop(0)))
+    key, raw = raws
+    n = raw.numel()
+    wide = n >= 44 and n % 4 == 0 and int.from_bytes(bytes(raw[-4:].cpu().numpy()), "little") == V2_MAGIC
+    if wide:
+        if key.numel() % 2:
+            raise RuntimeError("key plane of a 16-bit container has an odd number of bytes")
+        return names, is_rgb, key.view(torch.uint16), raw.view(torch.int32)
+    if n % 2:
+        raise RuntimeError("entropy.dat holds an odd number of bytes")
+    return names, is_rgb, key, raw.view(torch.int16)

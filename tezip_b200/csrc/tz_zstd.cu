@@ -153,6 +153,40 @@ __global__ void __launch_bounds__(256) zs_encode_kernel(const uint8_t *__restric
                   byte * 8 + chunk_off[t], (j + 1) * ZS_CHUNK >= seglen);
 }
 
+// Decoder: one thread per Huffman stream.  A CTA holds the streams of eight blocks; the decoding table (4 KB) of each
+// block is read through L1 -- the blocks of one frame nearly always share one table.
+__global__ void __launch_bounds__(32) zs_decode_kernel(const uint8_t *__restrict__ frame, const ZsDBlock *__restrict__ blk,
+                                                       uint64_t nblocks, const uint16_t *__restrict__ dtables,
+                                                       uint8_t *__restrict__ out, int32_t *__restrict__ err) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = t >> 2;
+  const uint32_t s = (uint32_t)t & 3u;
+  if (b >= nblocks) return;
+  const ZsDBlock k = blk[b];
+  if (k.type != ZS_HUF) return;
+  uint64_t so = k.src_off;
+  for (uint32_t i = 0; i < s; ++i) so += k.stream_bytes[i];
+  const uint32_t q = zs_seg_len(k.regen, 0);
+  int r = zs_decode_stream(frame + so, k.stream_bytes[s], dtables + ((uint64_t)k.table << ZS_DLOG),
+                           out + k.dst_off + (uint64_t)s * q, zs_seg_len(k.regen, s));
+  if (r) atomicMax(err, r);
+}
+
+// Raw and RLE blocks: one CTA per block.
+__global__ void __launch_bounds__(256) zs_copy_kernel(const uint8_t *__restrict__ frame, const ZsDBlock *__restrict__ blk,
+                                                      uint8_t *__restrict__ out) {
+  const ZsDBlock k = blk[blockIdx.x];
+  if (k.type == ZS_HUF) return;
+  uint8_t *dst = out + k.dst_off;
+  const uint8_t *p = frame + k.src_off;
+  if (k.type == ZS_RLE) {
+    const uint8_t v = p[0];
+    for (uint32_t i = threadIdx.x; i < k.regen; i += blockDim.x) dst[i] = v;
+  } else {
+    for (uint32_t i = threadIdx.x; i < k.regen; i += blockDim.x) dst[i] = p[i];
+  }
+}
+
 inline uint64_t n_blocks(uint64_t n) { return (n + ZS_BLOCK - 1) / ZS_BLOCK; }
 inline uint64_t align256(uint64_t v) { return (v + 255) & ~(uint64_t)255; }
 
@@ -206,6 +240,21 @@ int tz_zstd_encode(const uint8_t *src, unsigned long long n, const uint32_t *cta
   if (tree_len) {
     zs_encode_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(src, n, ctable, tree_len, blk, chunk_off,
                                                                       (uint32_t *)out, slots);
+    TZ_CHECK_LAUNCH();
+  }
+  return TZ_OK;
+}
+
+int tz_zstd_decode(const uint8_t *frame, const void *blocks, unsigned long long nblocks, const uint16_t *dtables,
+                   uint8_t *out, int32_t *err, void *stream) {
+  TZ_REQUIRE(frame && blocks && out && err && nblocks > 0 && nblocks < 2147483647ULL / 4, "tz_zstd_decode: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  TZ_CHECK_CUDA(cudaMemsetAsync(err, 0, sizeof(int32_t), st));
+  zs_copy_kernel<<<(unsigned)nblocks, 256, 0, st>>>(frame, (const ZsDBlock *)blocks, out);
+  TZ_CHECK_LAUNCH();
+  if (dtables) {
+    zs_decode_kernel<<<(unsigned)((nblocks * 4 + 31) / 32), 32, 0, st>>>(frame, (const ZsDBlock *)blocks, nblocks, dtables,
+                                                                        out, err);
     TZ_CHECK_LAUNCH();
   }
   return TZ_OK;

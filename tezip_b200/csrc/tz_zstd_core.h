@@ -206,3 +206,46 @@ ZS_HD void zs_frame_header(uint64_t n, uint8_t *dst) {
   dst[5] = 0x38;
   for (int i = 0; i < 8; ++i) dst[6 + i] = (uint8_t)(n >> (8 * i));
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Reading such frames back (decompress.py:89,98): the host walks the block headers (tezip_b200/zstd_frames.py), the
+// device decodes every block -- and every one of the four Huffman streams of a block -- independently.
+
+struct ZsDBlock {            // one block of a parsed frame
+  uint64_t src_off;          // frame offset of the payload: raw bytes, the RLE byte, or the first Huffman stream
+  uint64_t dst_off;          // offset of the block's bytes in the decoded content
+  uint32_t type;             // ZS_RAW / ZS_RLE / ZS_HUF
+  uint32_t regen;            // decoded bytes of the block
+  uint32_t stream_bytes[4];  // ZS_HUF: bytes of the four streams
+  uint32_t table;            // ZS_HUF: index of its decoding table
+  uint32_t pad;
+};
+
+#define ZS_DLOG 11u          // decoding tables are expanded to 2^11 entries: symbol | nbits << 8
+
+// Decodes one Huffman stream of nsym symbols (RFC 8878 4.2.2): the stream is read from its last byte down, starting
+// below the highest set bit of that byte.  Returns 0, or a non-zero code when the stream is malformed (no end mark, more
+// bits consumed than it holds, bits left over).
+ZS_HD int zs_decode_stream(const uint8_t *src, uint32_t nbytes, const uint16_t *dtable, uint8_t *dst, uint32_t nsym) {
+  if (nbytes == 0) return 1;
+  uint32_t last = src[nbytes - 1];
+  if (last == 0) return 2;
+  int top = 7;
+  while (!((last >> top) & 1)) --top;          // position of the end mark; `top` payload bits lie below it in this byte
+  uint64_t acc = top ? (uint64_t)(last & ((1u << top) - 1)) << (64 - top) : 0;   // next bit to read = bit 63
+  int avail = top;                                                         // valid bits in acc
+  uint32_t pos = nbytes - 1;                                               // bytes below `pos` are still unread
+  for (uint32_t i = 0; i < nsym; ++i) {
+    while (avail <= 56 && pos > 0) {
+      acc |= (uint64_t)src[--pos] << (56 - avail);
+      avail += 8;
+    }
+    uint32_t e = dtable[acc >> (64 - ZS_DLOG)];
+    uint32_t nb = e >> 8;
+    dst[i] = (uint8_t)e;
+    acc <<= nb;
+    avail -= (int)nb;
+    if (avail < 0) return 3;
+  }
+  return (avail == 0 && pos == 0) ? 0 : 4;
+}

@@ -90,9 +90,25 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, GPU_FLAG, VERBOSE):
     for fn in (container.NAMES_FILE, container.KEY_FILE, container.ENTROPY_FILE):
         if not os.path.exists(os.path.join(DATA_DIR, fn)):
             _die("ERROR: No such file or directory:", os.path.join(DATA_DIR, fn))     # decompress.py:51-53,90-101
-    file_names, isRGB, key_plane, payload = container.read_container(DATA_DIR)
+    # frames written by the GPU writer (TEZIP_ZSTD_LEVEL=gpu) are decoded on the device and never exist on the host;
+    # anything else goes through libzstd like decompress.py:89,98
+    on_dev = container.read_container_device(DATA_DIR, torch.device("cuda", torch.cuda.current_device())) \
+        if torch.cuda.is_available() else None
+    if on_dev is not None:
+        file_names, isRGB, key_plane, payload_dev = on_dev
+        tail_len = min(payload_dev.numel(), 1 << 19)         # trailer + table (at most 262144 + 11 entries)
+        payload = payload_dev[payload_dev.numel() - tail_len:].cpu().numpy()
+    else:
+        file_names, isRGB, key_plane, payload = container.read_container(DATA_DIR)
     try:
-        body, table, shape, p = codec.parse_payload(payload)
+        try:
+            body, table, shape, p = codec.parse_payload(payload)
+        except TezipError:
+            if on_dev is None or tail_len == payload_dev.numel():
+                raise
+            payload = payload_dev.cpu().numpy()              # (a table longer than the tail that was fetched)
+            tail_len = payload.size
+            body, table, shape, p = codec.parse_payload(payload)
         if len(file_names) != shape[1]:                                                # decompress.py:260-264
             print("ERROR：The lengths of filename.txt and images do not match.")
             print("filename.txt：", len(file_names))
@@ -101,8 +117,12 @@ def run(WEIGHTS_DIR, DATA_DIR, OUTPUT_DIR, GPU_FLAG, VERBOSE):
         net = load_predictor(WEIGHTS_DIR, max_batch=min(n_keys_guess, 256))
         dev = net.device
         t0 = time.time()
-        out, _plan = codec.decode_arrays(torch.from_numpy(np.ascontiguousarray(key_plane)).to(dev),
-                                         torch.from_numpy(np.ascontiguousarray(body)).to(dev), table, shape, p, net)
+        if on_dev is not None:
+            n_body = payload_dev.numel() - (tail_len - body.size)
+            out, _plan = codec.decode_arrays(key_plane.to(dev), payload_dev[:n_body].to(dev), table, shape, p, net)
+        else:
+            out, _plan = codec.decode_arrays(torch.from_numpy(np.ascontiguousarray(key_plane)).to(dev),
+                                             torch.from_numpy(np.ascontiguousarray(body)).to(dev), table, shape, p, net)
         frames = out.cpu().numpy()
         if VERBOSE:
             print("gpu_decode:{0}".format(time.time() - t0) + "[sec]")

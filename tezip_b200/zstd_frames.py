@@ -265,6 +265,263 @@ def huffman_tables(hist):
     return np.zeros(256, np.uint32), b""
 
 
+# ---- reading frames back (decompress.py:89,98): the host walks the headers, the device decodes the blocks ---------------
+
+DBLOCK = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("type", "<u4"), ("regen", "<u4"), ("stream_bytes", "<u4", 4),
+                   ("table", "<u4"), ("pad", "<u4")])          # struct ZsDBlock of csrc/tz_zstd_core.h
+DLOG = 11
+
+
+def _read_ncount(data):
+    """FSE table description (RFC 8878 4.1.1) -> (normalised counts, accuracy log, bytes used)."""
+    bits = int.from_bytes(data, "little")
+    log = (bits & 0xF) + 5
+    bits >>= 4
+    used = 4
+    if log > 6:
+        raise ValueError("accuracy log of the weights exceeds 6")
+    remaining, threshold, nb = (1 << log) + 1, 1 << log, log + 1
+    norm, previous0 = [], False
+    while remaining > 1 and len(norm) < 256:
+        if previous0:
+            n0 = 0
+            while bits & 0xFFFF == 0xFFFF:
+                n0 += 24
+                bits >>= 16
+                used += 16
+            while bits & 3 == 3:
+                n0 += 3
+                bits >>= 2
+                used += 2
+            n0 += bits & 3
+            bits >>= 2
+            used += 2
+            norm += [0] * n0
+        mx = (2 * threshold - 1) - remaining
+        if (bits & (threshold - 1)) < mx:
+            count = bits & (threshold - 1)
+            take = nb - 1
+        else:
+            count = bits & (2 * threshold - 1)
+            if count >= threshold:
+                count -= mx
+            take = nb
+        bits >>= take
+        used += take
+        count -= 1
+        remaining -= abs(count)
+        norm.append(count)
+        previous0 = count == 0
+        while remaining < threshold:
+            nb -= 1
+            threshold >>= 1
+    if remaining != 1 or (used + 7) // 8 > len(data):
+        raise ValueError("corrupt FSE table description")
+    return norm, log, (used + 7) // 8
+
+
+def fse_decompress_weights(data):
+    """Inverse of fse_compress_weights (zstd's FSE_decompress on Huffman weights, RFC 8878 4.2.1.2)."""
+    norm, log, used = _read_ncount(data)
+    size = 1 << log
+    high = size - 1
+    symbol = [0] * size
+    nxt = []
+    for s, c in enumerate(norm):
+        if c == -1:
+            symbol[high] = s
+            high -= 1
+            nxt.append(1)
+        else:
+            nxt.append(c)
+    step, pos = (size >> 1) + (size >> 3) + 3, 0
+    for s, c in enumerate(norm):
+        for _ in range(max(c, 0)):
+            symbol[pos] = s
+            pos = (pos + step) & (size - 1)
+            while pos > high:
+                pos = (pos + step) & (size - 1)
+    nbits, base = [0] * size, [0] * size
+    for u in range(size):
+        st = nxt[symbol[u]]
+        nxt[symbol[u]] += 1
+        nbits[u] = log - (st.bit_length() - 1)
+        base[u] = (st << nbits[u]) - size
+    stream = data[used:]
+    if not stream or stream[-1] == 0:
+        raise ValueError("corrupt FSE stream")
+    value = int.from_bytes(stream, "little")
+    left = (len(stream) - 1) * 8 + stream[-1].bit_length() - 1      # bits below the end mark
+
+    def read(n):                # the n bits below the cursor; reading past the start gives zeros and a negative `left`
+        nonlocal left
+        left -= n
+        return (value >> left) & ((1 << n) - 1) if left >= 0 else (value << -left) & ((1 << n) - 1)
+
+    s1 = read(log)
+    s2 = read(log)
+    out = []
+    while len(out) < 255:
+        out.append(symbol[s1])
+        s1 = base[s1] + read(nbits[s1])
+        if left < 0:
+            out.append(symbol[s2])
+            break
+        out.append(symbol[s2])
+        s2 = base[s2] + read(nbits[s2])
+        if left < 0:
+            out.append(symbol[s1])
+            break
+    else:
+        raise ValueError("corrupt FSE stream")
+    return out
+
+
+def decode_table(tree):
+    """Huffman_Tree_Description bytes -> (decoding table u16[2^11]: symbol | nbits << 8, bytes of the description)."""
+    head = tree[0]
+    if head >= 128:
+        count = head - 127
+        used = 1 + (count + 1) // 2
+        raw = tree[1:used]
+        if len(raw) < used - 1:
+            raise ValueError("truncated tree description")
+        w = []
+        for b in raw:
+            w += [b >> 4, b & 15]
+        w = w[:count]
+    else:
+        used = 1 + head
+        if head == 0 or len(tree) < used:
+            raise ValueError("truncated tree description")
+        w = fse_decompress_weights(bytes(tree[1:used]))
+    total = sum((1 << (v - 1)) for v in w if v)
+    if total == 0 or len(w) > 255:
+        raise ValueError("corrupt Huffman weights")
+    log = total.bit_length()                      # the implied last weight completes the sum to the next power of two
+    rest = (1 << log) - total
+    if log > DLOG or rest & (rest - 1) or rest == 0:
+        raise ValueError("corrupt Huffman weights")
+    w = w + [rest.bit_length()]
+    table = np.zeros(1 << DLOG, np.uint16)
+    pos = 0
+    for wt in range(1, log + 1):                  # the order of weights_and_codes
+        span = (1 << (wt - 1)) << (DLOG - log)
+        for s, v in enumerate(w):
+            if v == wt:
+                table[pos:pos + span] = s | ((log + 1 - wt) << 8)
+                pos += span
+    if pos != 1 << DLOG:
+        raise ValueError("corrupt Huffman weights")
+    return table, used
+
+
+def parse_frame(data):
+    """data: bytes / u8 array holding ONE zstd frame.  -> (content size, blocks as DBLOCK array, tables u16[T, 2048]) when
+    every block is raw, RLE, or 4-stream Huffman literals with zero sequences (what compress_device writes); None for
+    any other frame (the caller decodes those with libzstd, like the reference)."""
+    d = memoryview(data).cast("B") if not isinstance(data, np.ndarray) else \
+        memoryview(np.ascontiguousarray(data).view(np.uint8).reshape(-1))
+    n = len(d)
+    if n < 9 or bytes(d[:4]) != b"\x28\xb5\x2f\xfd":
+        return None
+    fhd = int(d[4])
+    fcs_flag, single, checksum, dict_flag = fhd >> 6, (fhd >> 5) & 1, (fhd >> 2) & 1, fhd & 3
+    if checksum or dict_flag or (fhd & 0x18):
+        return None
+    pos = 5 + (0 if single else 1)
+    fcs_bytes = (1 if single else 0, 2, 4, 8)[fcs_flag]
+    if fcs_bytes == 0 or pos + fcs_bytes > n:
+        return None
+    content = int.from_bytes(bytes(d[pos:pos + fcs_bytes]), "little") + (256 if fcs_bytes == 2 else 0)
+    pos += fcs_bytes
+    blocks, tables, table_ids, dst = [], [], {}, 0
+    while True:
+        if pos + 3 > n:
+            return None
+        h = int(d[pos]) | int(d[pos + 1]) << 8 | int(d[pos + 2]) << 16
+        last, btype, size = h & 1, (h >> 1) & 3, h >> 3
+        pos += 3
+        if btype == 0:
+            if pos + size > n:
+                return None
+            blocks.append((pos, dst, 0, size, (0, 0, 0, 0), 0, 0))
+            pos, dst = pos + size, dst + size
+        elif btype == 1:
+            if pos + 1 > n:
+                return None
+            blocks.append((pos, dst, 1, size, (0, 0, 0, 0), 0, 0))
+            pos, dst = pos + 1, dst + size
+        elif btype == 2:
+            end = pos + size
+            if end > n or size < 5:
+                return None
+            b0 = int(d[pos])
+            fmt = (b0 >> 2) & 3
+            if b0 & 3 != 2 or fmt == 0:
+                return None                                  # raw / RLE / treeless literals or a single stream
+            lh = 3 + (fmt - 1)
+            v = int.from_bytes(bytes(d[pos:pos + lh]), "little") >> 4
+            nbits = (10, 14, 18)[fmt - 1]
+            regen, csize = v & ((1 << nbits) - 1), v >> nbits
+            if pos + lh + csize + 1 != end or int(d[end - 1]) != 0 or regen < 6 or regen > BLOCK:
+                return None                                  # sequences follow the literals
+            head = int(d[pos + lh])
+            used = 1 + ((head - 126) // 2 if head >= 128 else head)      # bytes of the tree description
+            if used + 6 >= csize:
+                return None
+            tree = bytes(d[pos + lh:pos + lh + used])
+            try:
+                if tree not in table_ids:                    # the blocks of a frame nearly always share one tree
+                    table_ids[tree] = len(tables)
+                    tables.append(decode_table(tree)[0])
+                tid = table_ids[tree]
+            except (ValueError, IndexError):
+                return None
+            jt = pos + lh + used
+            s = [int(d[jt + 2 * i]) | int(d[jt + 2 * i + 1]) << 8 for i in range(3)]
+            s.append(csize - used - 6 - sum(s))
+            if min(s) <= 0:
+                return None
+            blocks.append((jt + 6, dst, 2, regen, tuple(s), tid, 0))
+            pos, dst = end, dst + regen
+        else:
+            return None
+        if last:
+            break
+    if pos != n or dst != content:
+        return None
+    return content, np.array(blocks, DBLOCK), (np.stack(tables) if tables else np.zeros((0, 1 << DLOG), np.uint16))
+
+
+def decompress_device(data, device, parsed=None):
+    """data: bytes / u8 array with one zstd frame -> u8 CUDA tensor with its content, decoded by the kernels of
+    csrc/tz_zstd.cu; None when the frame uses parts of the format they do not cover (decode it with libzstd then)."""
+    import torch
+    from . import _lib
+    from .ops import check, ptr, _st
+    if parsed is None:
+        parsed = parse_frame(data)
+    if parsed is None:
+        return None
+    content, blocks, tables = parsed
+    dev = torch.device(device)
+    out = torch.empty(content, dtype=torch.uint8, device=dev)
+    if content == 0:
+        return out
+    arr = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1)
+    frame = torch.from_numpy(arr if arr.flags.writeable else arr.copy()).to(dev)
+    blk = torch.from_numpy(blocks.view(np.uint8).reshape(-1).copy()).to(dev)
+    tab = torch.from_numpy(tables.view(np.int16).reshape(-1).copy()).to(dev) if len(tables) else None
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().tz_zstd_decode(ptr(frame), ptr(blk), len(blocks), ptr(tab), ptr(out), ptr(err), _st(dev)),
+          "tz_zstd_decode")
+    code = int(err.item())
+    if code:
+        raise RuntimeError("corrupt zstd frame (Huffman stream error %d)" % code)
+    return out
+
+
 def frame_device(t):
     """t: a contiguous CUDA tensor (any element type; its bytes are compressed) -> (u8 CUDA tensor, size): the first
     `size` bytes of the tensor are one zstd frame with content size.  One small device->host read in the middle (the
@@ -295,7 +552,23 @@ def frame_device(t):
     return out, int(total.item())
 
 
+_PINNED = {}
+
+
+def frame_host(t):
+    """-> u8 numpy view of the frame of frame_device(t) in a cached pinned host buffer (one per device, grown on
+    demand): valid until the next call for that device.  For callers that write the frame out at once."""
+    import torch
+    out, size = frame_device(t)
+    key = str(out.device)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < size:
+        buf = _PINNED[key] = torch.empty(max(size, 1 << 20), dtype=torch.uint8, pin_memory=True)
+    buf[:size].copy_(out[:size], non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return buf.numpy()[:size]
+
+
 def compress_device(t):
     """-> bytes: the frame of frame_device(t), copied to the host."""
-    out, size = frame_device(t)
-    return out[:size].cpu().numpy().tobytes()
+    return frame_host(t).tobytes()
