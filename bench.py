@@ -1015,17 +1015,24 @@ def run_native(args):
             tzf.frame_device(pay_dev)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        fb, nb_ = tzf.frame_device(pay_dev)
-        fk, nk_ = tzf.frame_device(enc0.key_plane)
+        marks = []
+        fb, nb_ = tzf.frame_device(pay_dev, marks)
+        fk, nk_ = tzf.frame_device(enc0.key_plane, marks)
         torch.cuda.synchronize(dev)
         t_dev = time.perf_counter() - t0
+        kern_ms = {}
+        for nm, a_, b_ in marks:
+            kern_ms[nm] = kern_ms.get(nm, 0.0) + a_.elapsed_time(b_)
+        src_bytes = pay_dev.numel() * 2 + enc0.key_plane.numel()
         zb_g, zk_g = fb[:nb_].cpu().numpy(), fk[:nk_].cpu().numpy()
         tzf.frame_host(pay_dev)                                      # (allocates the pinned landing buffer)
         t0 = time.perf_counter()
         n_h = tzf.frame_host(pay_dev).size + tzf.frame_host(enc0.key_plane).size
         t_all = time.perf_counter() - t0
         assert n_h == nb_ + nk_
-        cont["gpu"] = {"seconds_device": t_dev, "seconds_with_download": t_all, "raw_MB_per_s": raw_bytes / 1e6 / t_all,
+        cont["gpu"] = {"kernels_ms": kern_ms, "source_bytes": src_bytes,
+                       "kernels_GB_per_s_of_source": src_bytes / 1e6 / max(sum(kern_ms.values()), 1e-9),
+                       "seconds_device": t_dev, "seconds_with_download": t_all, "raw_MB_per_s": raw_bytes / 1e6 / t_all,
                        "raw_MB_per_s_device": raw_bytes / 1e6 / t_dev, "ratio": raw_bytes / float(nb_ + nk_),
                        "decodes_with_libzstd": bool(np.array_equal(tzc.zstd_decompress(zb_g).view("<i2"), payload) and
                                                     np.array_equal(tzc.zstd_decompress(zk_g), kp_np.reshape(-1))),

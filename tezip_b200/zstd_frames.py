@@ -522,10 +522,11 @@ def decompress_device(data, device, parsed=None):
     return out
 
 
-def frame_device(t):
+def frame_device(t, marks=None):
     """t: a contiguous CUDA tensor (any element type; its bytes are compressed) -> (u8 CUDA tensor, size): the first
     `size` bytes of the tensor are one zstd frame with content size.  One small device->host read in the middle (the
-    1 KB histogram: the Huffman code is built on the host) and one at the end (the size)."""
+    1 KB histogram: the Huffman code is built on the host) and one at the end (the size).
+    marks: optional list; CUDA events around the two device phases are appended as (name, start, end)."""
     import torch
     from . import _lib
     from .ops import check, ptr, _st
@@ -540,15 +541,22 @@ def frame_device(t):
     nblocks = -(-n // BLOCK)
     hist = torch.empty(256, dtype=torch.int32, device=dev)
     uniform = torch.empty(nblocks, dtype=torch.int32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    e0 = cur.record_event(torch.cuda.Event(enable_timing=True)) if marks is not None else None
     check(lib.tz_zstd_hist(ptr(raw), n, ptr(hist), ptr(uniform), _st(dev)), "tz_zstd_hist")
+    if marks is not None:
+        marks.append(("hist", e0, cur.record_event(torch.cuda.Event(enable_timing=True))))
     ct, tree = huffman_tables(hist.cpu().numpy().view(np.uint32))
     ct_dev = torch.from_numpy(ct.view(np.int32)).to(dev)
     tree_dev = torch.from_numpy(np.frombuffer(tree + b"\0", np.uint8).copy()).to(dev)
     ws = torch.empty(int(lib.tz_zstd_workspace_bytes(n)), dtype=torch.uint8, device=dev)
     out = torch.empty(int(lib.tz_zstd_bound(n)), dtype=torch.uint8, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
+    e0 = cur.record_event(torch.cuda.Event(enable_timing=True)) if marks is not None else None
     check(lib.tz_zstd_encode(ptr(raw), n, ptr(ct_dev), ptr(tree_dev), len(tree), ptr(uniform), ptr(ws), ptr(out),
                              ptr(total), _st(dev)), "tz_zstd_encode")
+    if marks is not None:
+        marks.append(("encode", e0, cur.record_event(torch.cuda.Event(enable_timing=True))))
     return out, int(total.item())
 
 
