@@ -48,6 +48,33 @@ def _huffman_lengths(counts):
     return np.array(depth[:n], np.int64)
 
 
+def _limit_lengths(lens, counts, max_bits):
+    """Code lengths clamped to max_bits and repaired to a complete code (Kraft sum exactly 1): symbols are lengthened
+    cheapest first (smallest count) until the clamped code fits, then the slack that the last step left is given back
+    to the most frequent symbols that can take it.  None if the repair does not close (the caller flattens instead)."""
+    lens = [min(int(v), max_bits) for v in lens]
+    full = 1 << max_bits
+    excess = sum(1 << (max_bits - v) for v in lens) - full
+    by_count = sorted(range(len(lens)), key=lambda i: (int(counts[i]), i))
+    at = 0
+    while excess > 0:
+        while at < len(by_count) and lens[by_count[at]] >= max_bits:
+            at += 1
+        if at == len(by_count):
+            return None
+        i = by_count[at]
+        excess -= 1 << (max_bits - lens[i] - 1)
+        lens[i] += 1
+    slack = -excess
+    for i in reversed(by_count):                       # most frequent first
+        while slack and lens[i] > 1 and (1 << (max_bits - lens[i])) <= slack:
+            slack -= 1 << (max_bits - lens[i])
+            lens[i] -= 1
+        if not slack:
+            break
+    return np.array(lens, np.int64) if slack == 0 else None
+
+
 def code_lengths(hist, max_bits=MAX_BITS):
     """hist: 256 counts -> 256 code lengths (0 = absent), complete prefix code with lengths <= max_bits; None if
     fewer than two byte values occur (such data is RLE, not Huffman)."""
@@ -56,11 +83,14 @@ def code_lengths(hist, max_bits=MAX_BITS):
     if len(sym) < 2:
         return None
     counts = hist[sym].copy()
-    while True:
-        lens = _huffman_lengths(counts)
-        if lens.max() <= max_bits:
-            break
-        counts = (counts + 1) // 2                    # flatten the distribution until the deepest leaf fits
+    lens = _huffman_lengths(counts)
+    if lens.max() > max_bits:
+        fixed = _limit_lengths(lens, counts, max_bits)
+        while fixed is None:                              # (not seen in practice) flatten until the plain code fits
+            counts = (counts + 1) // 2
+            lens = _huffman_lengths(counts)
+            fixed = lens if lens.max() <= max_bits else None
+        lens = fixed
     out = np.zeros(256, np.int64)
     out[sym] = lens
     return out
