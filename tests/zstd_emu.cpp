@@ -94,7 +94,7 @@ int emu_decode(const uint8_t *frame, const ZsDBlock *blk, unsigned long long nbl
     if (k.type != ZS_HUF) continue;
     uint64_t so = k.src_off;
     for (uint32_t i = 0; i < s; ++i) so += k.stream_bytes[i];
-    int r = zs_decode_stream(frame + so, k.stream_bytes[s], dtables + ((uint64_t)k.table << ZS_DLOG),
+    int r = zs_decode_stream((const uint32_t *)frame, so, k.stream_bytes[s], dtables + ((uint64_t)k.table << ZS_DLOG),
                              out + k.dst_off + (uint64_t)s * zs_seg_len(k.regen, 0), zs_seg_len(k.regen, s));
     if (r > err) err = r;
   }

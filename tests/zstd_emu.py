@@ -59,7 +59,8 @@ def decompress(frame):
         return None
     content, blocks, tables = parsed
     out = np.zeros(max(content, 1), np.uint8)
-    src = np.frombuffer(frame, np.uint8).copy()
+    src = np.zeros(len(frame) + 8, np.uint8)                  # (the stream decoder reads aligned 32-bit words)
+    src[:len(frame)] = np.frombuffer(frame, np.uint8)
     blocks = np.ascontiguousarray(blocks)
     tables = np.ascontiguousarray(tables)
     err = load().emu_decode(src.ctypes.data, blocks.ctypes.data, len(blocks), tables.ctypes.data, out.ctypes.data)

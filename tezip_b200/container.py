@@ -180,6 +180,9 @@ def read_container(comp_dir):
     return names, is_rgb, key_plane, raw.view("<i2")
 
 
+_PINNED_IN = {}
+
+
 def read_container_device(comp_dir, device):
     """read_container with the two frames decoded on the GPU: -> (names, is_rgb, key plane, payload) as CUDA tensors
     (u8 + int16, or u16 + int32 for container v2), or None when a frame uses parts of the zstd format that the kernels
@@ -191,16 +194,25 @@ def read_container_device(comp_dir, device):
     from . import zstd_frames
     from .codec import V2_MAGIC
     raws = []
+    cap = int(os.environ.get("TEZIP_MAX_DECODED_BYTES", str(MAX_DECODED_BYTES)))
     for fn in (KEY_FILE, ENTROPY_FILE):
-        data = np.fromfile(os.path.join(comp_dir, fn), np.uint8)
-        parsed_size = zstd_frames.parse_frame(data)
-        if parsed_size is None:
+        path = os.path.join(comp_dir, fn)
+        size = os.path.getsize(path)
+        with open(path, "rb") as f:
+            head = f.read(6)
+            if head != b"\x28\xb5\x2f\xfd\xc0\x38":      # not the GPU writer's frame header: libzstd's business
+                return None
+            buf = _PINNED_IN.get(fn)                       # read into pinned memory (cached buffer): the upload is
+            if buf is None or buf.numel() < size:          # asynchronous and overlaps the header walk
+                buf = _PINNED_IN[fn] = torch.empty(max(size, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            data = buf.numpy()[:size]
+            data[:6] = np.frombuffer(head, np.uint8)
+            if f.readinto(memoryview(data)[6:]) != size - 6:
+                raise RuntimeError("short read of %s" % path)
+        got = zstd_frames.decompress_device(data, device, max_bytes=cap)
+        if got is None:
             return None
-        cap = int(os.environ.get("TEZIP_MAX_DECODED_BYTES", str(MAX_DECODED_BYTES)))
-        if parsed_size[0] > cap:
-            raise RuntimeError("zstd frame declares %d bytes of content, more than the limit of %d "
-                               "(TEZIP_MAX_DECODED_BYTES)" % (parsed_size[0], cap))
-        raws.append(zstd_frames.decompress_device(data, device, parsed=parsed_size))
+        raws.append(got)
     with open(os.path.join(comp_dir, NAMES_FILE), "r", encoding="UTF-8") as f:
         names = [s.strip() for s in f.readlines()]
     is_rgb = True

@@ -153,21 +153,34 @@ __global__ void __launch_bounds__(256) zs_encode_kernel(const uint8_t *__restric
                   byte * 8 + chunk_off[t], (j + 1) * ZS_CHUNK >= seglen);
 }
 
-// Decoder: one thread per Huffman stream.  A CTA holds the streams of eight blocks; the decoding table (4 KB) of each
-// block is read through L1 -- the blocks of one frame nearly always share one table.
+// Decoder: one thread per Huffman stream; a CTA (one warp) holds the streams of eight blocks.  The decoding table of
+// the CTA's first block is staged in shared memory -- the blocks of one frame nearly always share one table -- and a
+// block with another table reads its own through L1.  The kernel is latency-bound by construction (a stream is a
+// serial chain), so the per-symbol chain is what counts: one table look-up, one shift.
 __global__ void __launch_bounds__(32) zs_decode_kernel(const uint8_t *__restrict__ frame, const ZsDBlock *__restrict__ blk,
                                                        uint64_t nblocks, const uint16_t *__restrict__ dtables,
                                                        uint8_t *__restrict__ out, int32_t *__restrict__ err) {
+  __shared__ uint16_t tab[1u << ZS_DLOG];
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t b = t >> 2;
   const uint32_t s = (uint32_t)t & 3u;
+  const uint32_t tab0 = blk[(uint64_t)blockIdx.x * 8].table;          // (0 for raw / RLE blocks: any valid table)
+  {
+    const uint4 *g = reinterpret_cast<const uint4 *>(dtables + ((uint64_t)tab0 << ZS_DLOG));
+    uint4 *d = reinterpret_cast<uint4 *>(tab);
+    for (uint32_t i = threadIdx.x; i < (2u << ZS_DLOG) / 16; i += 32) d[i] = g[i];
+  }
+  __syncthreads();
   if (b >= nblocks) return;
   const ZsDBlock k = blk[b];
   if (k.type != ZS_HUF) return;
-  uint64_t so = k.src_off;
-  for (uint32_t i = 0; i < s; ++i) so += k.stream_bytes[i];
+  const uint64_t so = k.src_off + (s > 0 ? k.stream_bytes[0] : 0u) + (s > 1 ? k.stream_bytes[1] : 0u) +
+                      (s > 2 ? k.stream_bytes[2] : 0u);
+  const uint32_t nbytes = s == 0 ? k.stream_bytes[0] : s == 1 ? k.stream_bytes[1] : s == 2 ? k.stream_bytes[2]
+                                                                                             : k.stream_bytes[3];
   const uint32_t q = zs_seg_len(k.regen, 0);
-  int r = zs_decode_stream(frame + so, k.stream_bytes[s], dtables + ((uint64_t)k.table << ZS_DLOG),
+  const uint16_t *table = k.table == tab0 ? tab : dtables + ((uint64_t)k.table << ZS_DLOG);
+  int r = zs_decode_stream(reinterpret_cast<const uint32_t *>(frame), so, nbytes, table,
                            out + k.dst_off + (uint64_t)s * q, zs_seg_len(k.regen, s));
   if (r) atomicMax(err, r);
 }
@@ -247,7 +260,8 @@ int tz_zstd_encode(const uint8_t *src, unsigned long long n, const uint32_t *cta
 
 int tz_zstd_decode(const uint8_t *frame, const void *blocks, unsigned long long nblocks, const uint16_t *dtables,
                    uint8_t *out, int32_t *err, void *stream) {
-  TZ_REQUIRE(frame && blocks && out && err && nblocks > 0 && nblocks < 2147483647ULL / 4, "tz_zstd_decode: bad arguments");
+  TZ_REQUIRE(frame && blocks && out && err && nblocks > 0 && nblocks < 2147483647ULL / 4 && ((uintptr_t)frame & 3) == 0 &&
+             ((uintptr_t)dtables & 15) == 0, "tz_zstd_decode: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   TZ_CHECK_CUDA(cudaMemsetAsync(err, 0, sizeof(int32_t), st));
   zs_copy_kernel<<<(unsigned)nblocks, 256, 0, st>>>(frame, (const ZsDBlock *)blocks, out);

@@ -224,28 +224,60 @@ struct ZsDBlock {            // one block of a parsed frame
 #define ZS_DLOG 11u          // decoding tables are expanded to 2^11 entries: symbol | nbits << 8
 
 // Decodes one Huffman stream of nsym symbols (RFC 8878 4.2.2): the stream is read from its last byte down, starting
-// below the highest set bit of that byte.  Returns 0, or a non-zero code when the stream is malformed (no end mark, more
-// bits consumed than it holds, bits left over).
-ZS_HD int zs_decode_stream(const uint8_t *src, uint32_t nbytes, const uint16_t *dtable, uint8_t *dst, uint32_t nsym) {
+// below the highest set bit of that byte.  The frame is read as aligned 32-bit words (frame: 4-byte aligned base, the
+// stream occupies bytes [off, off + nbytes)); a refill may load words that lie below the stream's first byte, but a
+// well-formed stream never consumes their bits: `left` counts the stream's own bits and must end at exactly zero.
+// Four symbols are assembled per 32-bit store where dst allows.  Returns 0, or a non-zero code when the stream is
+// malformed (no end mark, more bits consumed than it holds, bits left over).
+ZS_HD int zs_decode_stream(const uint32_t *frame, uint64_t off, uint32_t nbytes, const uint16_t *dtable, uint8_t *dst,
+                           uint32_t nsym) {
   if (nbytes == 0) return 1;
-  uint32_t last = src[nbytes - 1];
+  const uint32_t last = reinterpret_cast<const uint8_t *>(frame)[off + nbytes - 1];
   if (last == 0) return 2;
   int top = 7;
-  while (!((last >> top) & 1)) --top;          // position of the end mark; `top` payload bits lie below it in this byte
-  uint64_t acc = top ? (uint64_t)(last & ((1u << top) - 1)) << (64 - top) : 0;   // next bit to read = bit 63
-  int avail = top;                                                         // valid bits in acc
-  uint32_t pos = nbytes - 1;                                               // bytes below `pos` are still unread
-  for (uint32_t i = 0; i < nsym; ++i) {
-    while (avail <= 56 && pos > 0) {
-      acc |= (uint64_t)src[--pos] << (56 - avail);
-      avail += 8;
-    }
-    uint32_t e = dtable[acc >> (64 - ZS_DLOG)];
-    uint32_t nb = e >> 8;
-    dst[i] = (uint8_t)e;
-    acc <<= nb;
-    avail -= (int)nb;
-    if (avail < 0) return 3;
+  while (!((last >> top) & 1)) --top;                   // the end mark; `top` payload bits lie below it in this byte
+  const uint64_t mark = (off + nbytes - 1) * 8 + (uint32_t)top;   // absolute bit position of the end mark
+  long long left = (long long)(nbytes - 1) * 8 + top;             // payload bits of the stream
+  long long wi = (long long)(mark >> 5);
+  const uint32_t b = (uint32_t)mark & 31u;
+  uint64_t acc = b ? (uint64_t)(frame[wi] & ((1u << b) - 1u)) << (64 - b) : 0;   // next bit to read = bit 63
+  int have = (int)b;                                                               // bits loaded into acc
+  --wi;
+#define ZS_REFILL()                                     \
+  if (have <= 32) {                                     \
+    uint32_t w_ = wi >= 0 ? frame[wi] : 0u;             \
+    --wi;                                               \
+    acc |= (uint64_t)w_ << (32 - have);                 \
+    have += 32;                                         \
   }
-  return (avail == 0 && pos == 0) ? 0 : 4;
+#define ZS_DEC(v)                                       \
+  {                                                     \
+    uint32_t e_ = dtable[acc >> (64 - ZS_DLOG)];        \
+    uint32_t nb_ = e_ >> 8;                             \
+    (v) = e_ & 0xFFu;                                   \
+    acc <<= nb_;                                        \
+    have -= (int)nb_;                                   \
+    left -= nb_;                                        \
+  }
+  uint32_t i = 0, v0, v1, v2, v3;
+  while (i < nsym && ((uintptr_t)(dst + i) & 3)) {      // head: up to the first aligned output word
+    ZS_REFILL();
+    ZS_DEC(v0);
+    dst[i++] = (uint8_t)v0;
+  }
+  for (; i + 4 <= nsym; i += 4) {
+    ZS_REFILL();
+    ZS_DEC(v0); ZS_DEC(v1);
+    ZS_REFILL();
+    ZS_DEC(v2); ZS_DEC(v3);
+    *reinterpret_cast<uint32_t *>(dst + i) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+  }
+  for (; i < nsym; ++i) {
+    ZS_REFILL();
+    ZS_DEC(v0);
+    dst[i] = (uint8_t)v0;
+  }
+#undef ZS_REFILL
+#undef ZS_DEC
+  return left == 0 ? 0 : (left < 0 ? 3 : 4);
 }

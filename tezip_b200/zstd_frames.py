@@ -524,23 +524,36 @@ def parse_frame(data):
     return content, np.array(blocks, DBLOCK), (np.stack(tables) if tables else np.zeros((0, 1 << DLOG), np.uint16))
 
 
-def decompress_device(data, device, parsed=None):
+def decompress_device(data, device, max_bytes=None):
     """data: bytes / u8 array with one zstd frame -> u8 CUDA tensor with its content, decoded by the kernels of
-    csrc/tz_zstd.cu; None when the frame uses parts of the format they do not cover (decode it with libzstd then)."""
+    csrc/tz_zstd.cu; None when the frame uses parts of the format they do not cover (decode it with libzstd then).
+    The upload of a frame that carries this writer's header is queued before the host walks the block headers (from
+    pinned memory the two overlap).  max_bytes: refuse frames that declare more content than this."""
     import torch
     from . import _lib
     from .ops import check, ptr, _st
-    if parsed is None:
-        parsed = parse_frame(data)
+    arr = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1)
+    dev = torch.device(device)
+
+    def upload():
+        # (the stream decoder reads aligned 32-bit words: room for the word that holds the frame's last byte)
+        f = torch.empty(arr.size + 8, dtype=torch.uint8, device=dev)
+        f[:arr.size].copy_(torch.from_numpy(arr if arr.flags.writeable else arr.copy()), non_blocking=True)
+        return f
+
+    frame = upload() if arr.size > 6 and bytes(arr[4:6]) == b"\xc0\x38" else None
+    parsed = parse_frame(arr)
     if parsed is None:
         return None
     content, blocks, tables = parsed
-    dev = torch.device(device)
+    if max_bytes is not None and content > max_bytes:
+        raise RuntimeError("zstd frame declares %d bytes of content, more than the limit of %d "
+                           "(TEZIP_MAX_DECODED_BYTES)" % (content, max_bytes))
     out = torch.empty(content, dtype=torch.uint8, device=dev)
     if content == 0:
         return out
-    arr = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1)
-    frame = torch.from_numpy(arr if arr.flags.writeable else arr.copy()).to(dev)
+    if frame is None:
+        frame = upload()
     blk = torch.from_numpy(blocks.view(np.uint8).reshape(-1).copy()).to(dev)
     tab = torch.from_numpy(tables.view(np.int16).reshape(-1).copy()).to(dev) if len(tables) else None
     err = torch.zeros(1, dtype=torch.int32, device=dev)
