@@ -31,10 +31,12 @@ for name, t in (("stream", stream), ("key_plane", key)):
     frame = out[:size].cpu().numpy()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    back = zf.decompress_device(frame, dev)
+    dm = []
+    back = zf.decompress_device(frame, dev, marks=dm)
     torch.cuda.synchronize(dev)
     dwall = time.perf_counter() - t0
+    ms["decode"] = dm[0][1].elapsed_time(dm[0][2])
     nbytes = t.numel() * t.element_size()
-    print("%s: %d -> %d bytes (%.3f), write kernels %s ms, wall %.2f ms; read back wall %.2f ms, identical %s" %
+    print("%s: %d -> %d bytes (%.3f), kernels %s ms, write wall %.2f ms; read back wall %.2f ms, identical %s" %
           (name, nbytes, size, size / nbytes, {k: round(v, 3) for k, v in ms.items()}, wall * 1e3, dwall * 1e3,
            bool(torch.equal(back, t.reshape(-1).view(torch.uint8)))))

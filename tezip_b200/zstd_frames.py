@@ -11,6 +11,7 @@ Host side (this file): the Huffman code of the frame from the device's byte hist
 canonical order of the zstd decoder), its tree description (weights, FSE-compressed as HUF_compressWeights does or
 4-bit direct), and the calls.  The kernels do the rest; nothing here touches the data."""
 import heapq
+import struct
 
 import numpy as np
 
@@ -465,70 +466,82 @@ def parse_frame(data):
         return None
     content = int.from_bytes(bytes(d[pos:pos + fcs_bytes]), "little") + (256 if fcs_bytes == 2 else 0)
     pos += fcs_bytes
-    blocks, tables, table_ids, dst = [], [], {}, 0
+    tables, table_ids, dst = [], {}, 0
+    c_src, c_dst, c_type, c_regen, c_s0, c_s1, c_s2, c_s3, c_tab = [], [], [], [], [], [], [], [], []
+    u32 = struct.Struct("<I").unpack_from
+    jump = struct.Struct("<HHH").unpack_from
+    last_tree, last_tid = None, 0
     while True:
         if pos + 3 > n:
             return None
-        h = int(d[pos]) | int(d[pos + 1]) << 8 | int(d[pos + 2]) << 16
+        h = u32(d, pos)[0] & 0xFFFFFF if pos + 4 <= n else int(d[pos]) | int(d[pos + 1]) << 8 | int(d[pos + 2]) << 16
         last, btype, size = h & 1, (h >> 1) & 3, h >> 3
         pos += 3
+        s0 = s1 = s2 = s3 = tid = 0
         if btype == 0:
             if pos + size > n:
                 return None
-            blocks.append((pos, dst, 0, size, (0, 0, 0, 0), 0, 0))
-            pos, dst = pos + size, dst + size
+            src, regen, pos = pos, size, pos + size
         elif btype == 1:
             if pos + 1 > n:
                 return None
-            blocks.append((pos, dst, 1, size, (0, 0, 0, 0), 0, 0))
-            pos, dst = pos + 1, dst + size
+            src, regen, pos = pos, size, pos + 1
         elif btype == 2:
             end = pos + size
-            if end > n or size < 5:
+            if end > n or size < 16:
                 return None
-            b0 = int(d[pos])
+            b0 = d[pos]
             fmt = (b0 >> 2) & 3
             if b0 & 3 != 2 or fmt == 0:
                 return None                                  # raw / RLE / treeless literals or a single stream
-            lh = 3 + (fmt - 1)
-            v = int.from_bytes(bytes(d[pos:pos + lh]), "little") >> 4
-            nbits = (10, 14, 18)[fmt - 1]
-            regen, csize = v & ((1 << nbits) - 1), v >> nbits
-            if pos + lh + csize + 1 != end or int(d[end - 1]) != 0 or regen < 6 or regen > BLOCK:
+            lh = 2 + fmt
+            v = (u32(d, pos)[0] | d[pos + 4] << 32) >> 4
+            nbits = 6 + 4 * fmt                              # 10, 14 or 18 bits per size
+            regen, csize = v & ((1 << nbits) - 1), (v >> nbits) & ((1 << nbits) - 1)
+            if pos + lh + csize + 1 != end or d[end - 1] != 0 or regen < 6 or regen > BLOCK:
                 return None                                  # sequences follow the literals
-            head = int(d[pos + lh])
+            head = d[pos + lh]
             used = 1 + ((head - 126) // 2 if head >= 128 else head)      # bytes of the tree description
             if used + 6 >= csize:
                 return None
-            tree = bytes(d[pos + lh:pos + lh + used])
-            try:
-                if tree not in table_ids:                    # the blocks of a frame nearly always share one tree
-                    table_ids[tree] = len(tables)
-                    tables.append(decode_table(tree)[0])
-                tid = table_ids[tree]
-            except (ValueError, IndexError):
-                return None
+            tree = d[pos + lh:pos + lh + used]
+            if tree != last_tree:                            # the blocks of a frame nearly always share one tree
+                key = bytes(tree)
+                try:
+                    if key not in table_ids:
+                        table_ids[key] = len(tables)
+                        tables.append(decode_table(key)[0])
+                except (ValueError, IndexError):
+                    return None
+                last_tree, last_tid = key, table_ids[key]
+            tid = last_tid
             jt = pos + lh + used
-            s = [int(d[jt + 2 * i]) | int(d[jt + 2 * i + 1]) << 8 for i in range(3)]
-            s.append(csize - used - 6 - sum(s))
-            if min(s) <= 0:
+            s0, s1, s2 = jump(d, jt)
+            s3 = csize - used - 6 - s0 - s1 - s2
+            if s0 == 0 or s1 == 0 or s2 == 0 or s3 <= 0:
                 return None
-            blocks.append((jt + 6, dst, 2, regen, tuple(s), tid, 0))
-            pos, dst = end, dst + regen
+            src, pos = jt + 6, end
         else:
             return None
+        c_src.append(src); c_dst.append(dst); c_type.append(btype); c_regen.append(regen); c_tab.append(tid)
+        c_s0.append(s0); c_s1.append(s1); c_s2.append(s2); c_s3.append(s3)
+        dst += regen
         if last:
             break
     if pos != n or dst != content:
         return None
-    return content, np.array(blocks, DBLOCK), (np.stack(tables) if tables else np.zeros((0, 1 << DLOG), np.uint16))
+    blocks = np.zeros(len(c_src), DBLOCK)
+    blocks["src_off"], blocks["dst_off"], blocks["type"], blocks["regen"], blocks["table"] = c_src, c_dst, c_type, c_regen, c_tab
+    blocks["stream_bytes"] = np.array([c_s0, c_s1, c_s2, c_s3], np.uint32).T
+    return content, blocks, (np.stack(tables) if tables else np.zeros((0, 1 << DLOG), np.uint16))
 
 
-def decompress_device(data, device, max_bytes=None):
+def decompress_device(data, device, max_bytes=None, marks=None):
     """data: bytes / u8 array with one zstd frame -> u8 CUDA tensor with its content, decoded by the kernels of
     csrc/tz_zstd.cu; None when the frame uses parts of the format they do not cover (decode it with libzstd then).
     The upload of a frame that carries this writer's header is queued before the host walks the block headers (from
-    pinned memory the two overlap).  max_bytes: refuse frames that declare more content than this."""
+    pinned memory the two overlap).  max_bytes: refuse frames that declare more content than this.  marks: optional
+    list; CUDA events around the decoding kernels are appended as ("decode", start, end)."""
     import torch
     from . import _lib
     from .ops import check, ptr, _st
@@ -557,8 +570,12 @@ def decompress_device(data, device, max_bytes=None):
     blk = torch.from_numpy(blocks.view(np.uint8).reshape(-1).copy()).to(dev)
     tab = torch.from_numpy(tables.view(np.int16).reshape(-1).copy()).to(dev) if len(tables) else None
     err = torch.zeros(1, dtype=torch.int32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    e0 = cur.record_event(torch.cuda.Event(enable_timing=True)) if marks is not None else None
     check(_lib.load().tz_zstd_decode(ptr(frame), ptr(blk), len(blocks), ptr(tab), ptr(out), ptr(err), _st(dev)),
           "tz_zstd_decode")
+    if marks is not None:
+        marks.append(("decode", e0, cur.record_event(torch.cuda.Event(enable_timing=True))))
     code = int(err.item())
     if code:
         raise RuntimeError("corrupt zstd frame (Huffman stream error %d)" % code)
