@@ -140,3 +140,17 @@ def test_corrupt_stream_is_reported():
     frame[end - 1] = 1                                                        # longest code, the stream runs out of bits
     with pytest.raises(RuntimeError):
         zstd_emu.decompress(bytes(frame))
+
+
+def test_frames_decode_with_a_second_zstd_build():
+    """pyarrow bundles its own libzstd: a second decoder build reads the frames too (one-shot, size from the caller)."""
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("zstd"):
+        pytest.skip("pyarrow without zstd")
+    codec = pa.Codec("zstd")
+    for name, a in zstd_emu.cases().items():
+        raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        if raw.size == 0:
+            continue
+        out = codec.decompress(zstd_emu.compress(a), decompressed_size=raw.size)
+        assert np.array_equal(np.frombuffer(out, np.uint8), raw), name
